@@ -1,0 +1,121 @@
+"""Load the REAL reference implementation of the hot path from ``/root/reference``.
+
+Test infrastructure (see ``oracle/__init__.py``).  Only usable in the build
+container: ``/root/reference`` does not exist on the GPU box, so nothing that
+runs there (``-m gpu`` tests, ``smoke()``, ``bench.py``) may call this module.
+It is used by ``oracle/gen_golden.py`` (to create ``tests/golden/*.npz``) and by
+the ``-m "not gpu"`` tests that pin ``oracle/mgd_oracle.py`` against the
+reference when the reference tree is present.
+
+How the reference is loaded (it cannot be imported as a package because
+``multigriddet/__init__.py`` pulls in TensorFlow, which is not installed):
+
+* encoder: the four pure-NumPy ``FunctionDef`` nodes ``get_anchor_mask``,
+  ``iol_common_center``, ``best_fit_and_layer`` and ``preprocess_true_boxes``
+  are cut out of ``multigriddet/data/generators.py`` (:2473-2544, :3393-3473)
+  with ``ast`` and exec'd with only ``np`` in scope.  No reference text is
+  copied into this repo; the source is read where it lies at run time.
+* decoder / NMS: ``multigriddet/postprocess/{nms,wbf,multigrid_decode}.py`` are
+  loaded by file path under a stub ``tensorflow`` module
+  (``multigrid_decode.py:9`` imports TF but never uses it).
+
+``np.argsort`` on AVX-512/AVX2 hosts is not stable; the reference relies on it
+for anchor choice under rounded-IoL ties (``generators.py:2530``).  Call
+``pin_numpy_env()`` *before* NumPy is first imported to get the portable
+(lowest-index-first) behaviour the oracle and the CUDA kernels implement.
+"""
+from __future__ import annotations
+
+import ast
+import importlib.util
+import os
+import sys
+import types
+import warnings
+
+REFERENCE_ROOT = os.environ.get("MGD_REFERENCE_ROOT", "/root/reference")
+
+NUMPY_PIN = ("AVX512F AVX512CD AVX512_SKX AVX512_CLX AVX512_CNL AVX512_ICL "
+             "AVX512_SPR AVX2 FMA3")
+
+
+def pin_numpy_env() -> None:
+    """Disable NumPy's AVX dispatch (stable small argsort, libm transcendentals).
+
+    Must run before the first ``import numpy`` of the process to take effect.
+    """
+    os.environ.setdefault("NPY_DISABLE_CPU_FEATURES", NUMPY_PIN)
+
+
+def numpy_is_pinned() -> bool:
+    return os.environ.get("NPY_DISABLE_CPU_FEATURES", "") == NUMPY_PIN
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(
+        REFERENCE_ROOT, "multigriddet", "data", "generators.py"))
+
+
+_ENCODER_NAMES = ("get_anchor_mask", "iol_common_center", "best_fit_and_layer",
+                  "preprocess_true_boxes")
+_cache: dict = {}
+
+
+def load_encoder():
+    """Return the reference's ``preprocess_true_boxes`` (NumPy encoder)."""
+    if "enc" in _cache:
+        return _cache["enc"]
+    import numpy as np
+    path = os.path.join(REFERENCE_ROOT, "multigriddet", "data", "generators.py")
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    picked = [n for n in tree.body
+              if isinstance(n, ast.FunctionDef) and n.name in _ENCODER_NAMES]
+    if len(picked) != len(_ENCODER_NAMES):
+        raise RuntimeError("reference encoder functions not found in " + path)
+    mod = ast.Module(body=picked, type_ignores=[])
+    scope = {"np": np}
+    exec(compile(mod, path, "exec"), scope)
+    raw = scope["preprocess_true_boxes"]
+
+    def preprocess_true_boxes(*a, **k):
+        # generators.py:3441 does int(<1-element array>), deprecated in NumPy 2
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            return raw(*a, **k)
+
+    preprocess_true_boxes.scope = scope
+    _cache["enc"] = preprocess_true_boxes
+    return preprocess_true_boxes
+
+
+def load_postprocess():
+    """Return a namespace with the reference ``MultiGridDecoder`` and NMS classes."""
+    if "post" in _cache:
+        return _cache["post"]
+    if "tensorflow" not in sys.modules:
+        sys.modules["tensorflow"] = types.ModuleType("tensorflow")
+    pkg_root = os.path.join(REFERENCE_ROOT, "multigriddet")
+    names = {}
+    for pkg, sub in (("_mgd_ref", pkg_root),
+                     ("_mgd_ref.postprocess", os.path.join(pkg_root, "postprocess"))):
+        m = types.ModuleType(pkg)
+        m.__path__ = [sub]
+        sys.modules[pkg] = m
+    for name in ("nms", "wbf", "multigrid_decode"):
+        full = "_mgd_ref.postprocess." + name
+        spec = importlib.util.spec_from_file_location(
+            full, os.path.join(pkg_root, "postprocess", name + ".py"))
+        module = importlib.util.module_from_spec(spec)
+        sys.modules[full] = module
+        spec.loader.exec_module(module)
+        names[name] = module
+    ns = types.SimpleNamespace(
+        MultiGridDecoder=names["multigrid_decode"].MultiGridDecoder,
+        NMS=names["nms"].NMS, StandardNMS=names["nms"].StandardNMS,
+        DIoUNMS=names["nms"].DIoUNMS, SoftNMS=names["nms"].SoftNMS,
+        ClusterNMS=names["nms"].ClusterNMS, nms_boxes=names["nms"].nms_boxes,
+        fast_cluster_nms_boxes=names["nms"].fast_cluster_nms_boxes,
+        WeightedBoxesFusion=names["wbf"].WeightedBoxesFusion)
+    _cache["post"] = ns
+    return ns
