@@ -1,0 +1,208 @@
+/*
+ * libmgd -- B200-native (sm_100a) detection-head grid path for MultiGridDet.
+ *
+ * C ABI of the drop-in boundary.  The reference (solufast-cvprojects/multigriddet)
+ * is pure Python and has no FFI of its own; these entry points are what a ctypes
+ * binding inside the reference's two hot-path modules calls instead of the NumPy
+ * loops.  Each entry point names the reference interface it replaces (paths are
+ * relative to the reference repository root).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every function returns an mgd_status; on failure mgd_last_error() returns a
+ *     thread-local, NUL-terminated description.  No C++ exception crosses the ABI.
+ *   - tensors are dense, row-major, caller-allocated.  `memory` says where ALL
+ *     tensor arguments of the call live: MGD_MEM_DEVICE (CUDA device `device`;
+ *     work is enqueued on `stream`, the call returns without synchronising unless
+ *     MGD_FLAG_SYNC is set) or MGD_MEM_HOST (the library stages through the GPU:
+ *     H2D, kernels, D2H; the call is synchronous; pinned host memory is faster).
+ *   - the library never frees or keeps caller memory; scratch comes from the CUDA
+ *     stream-ordered pool of `device`, so calls are re-entrant and may be issued
+ *     concurrently from several host threads on different streams.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with MGD_ERR_NO_DEVICE.
+ */
+#ifndef MGD_H_
+#define MGD_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MGD_API __attribute__((visibility("default")))
+#else
+#define MGD_API
+#endif
+
+#define MGD_VERSION 100            /* 0.1.0 */
+#define MGD_MAX_LAYERS 5           /* generators.py:3423 knows strides 32,16,8,4,2 */
+#define MGD_MAX_ANCHORS_PER_LAYER 8
+
+typedef enum {
+    MGD_OK = 0,
+    MGD_ERR_INVALID_ARGUMENT = 1,  /* Python shim raises ValueError               */
+    MGD_ERR_CLASS_RANGE = 2,       /* class id >= num_classes -> AssertionError,
+                                      generators.py:3409                          */
+    MGD_ERR_CUDA = 3,              /* RuntimeError                                */
+    MGD_ERR_NO_DEVICE = 4,         /* RuntimeError: no CPU fallback exists        */
+    MGD_ERR_UNSUPPORTED = 5        /* NotImplementedError                         */
+} mgd_status;
+
+enum { MGD_MEM_HOST = 0, MGD_MEM_DEVICE = 1 };
+
+enum {
+    MGD_FLAG_SYNC = 1              /* synchronise `stream` before returning and
+                                      report deferred device-side errors          */
+};
+
+enum { MGD_NMS_IOU = 0, MGD_NMS_DIOU = 1 };
+
+/*
+ * Geometry of the detection head: what `anchors`, `num_classes`, `input_shape`
+ * and `grid_shapes` carry in preprocess_true_boxes (multigriddet/data/
+ * generators.py:3393) and in MultiGridDecoder.__init__ (multigriddet/postprocess/
+ * multigrid_decode.py:25-30).  Layer l has grid_h[l] x grid_w[l] cells and
+ * 5 + num_anchors[l] + num_classes channels per cell:
+ * [tx, ty, tw, th, obj, anchor one-hot/logits..., class one-hot/logits...].
+ * Only square inputs and grids are supported (the reference's index arithmetic is
+ * only self-consistent there: generators.py:3438-3439,3459-3470).
+ */
+typedef struct {
+    int num_layers;
+    int num_classes;
+    int input_h, input_w;
+    int grid_h[MGD_MAX_LAYERS];
+    int grid_w[MGD_MAX_LAYERS];
+    int num_anchors[MGD_MAX_LAYERS];
+    double anchors[MGD_MAX_LAYERS][MGD_MAX_ANCHORS_PER_LAYER][2];   /* (w, h) px */
+    /* 0: the caller's anchors were float32 (generators.py:1446), arithmetic that
+       touches them runs in float32 like NumPy does; 1: float64 anchors
+       (utils/anchors.py:311 load_anchors) and float64 arithmetic.              */
+    int anchors_f64;
+} mgd_head_config;
+
+/* Knobs of MultiGridDecoder.postprocess (multigrid_decode.py:347-357). */
+typedef struct {
+    int use_softmax;          /* multigrid_decode.py:140-145                      */
+    int rescore_confidence;   /* multigrid_decode.py:166-170                      */
+    double confidence;        /* keep score >= confidence, :271                   */
+    double nms_threshold;     /* suppress metric >= threshold, nms.py:180         */
+    int nms_method;           /* MGD_NMS_DIOU ('diou') or MGD_NMS_IOU
+                                 ('standard'/'cluster')                           */
+    int per_class;            /* 0: class-agnostic (the reference's NMS classes);
+                                 1: candidates of different argmax class never
+                                 suppress each other                              */
+    int max_boxes;            /* top-k after NMS, :336-345                        */
+} mgd_post_config;
+
+MGD_API int mgd_version(void);
+MGD_API const char *mgd_last_error(void);
+MGD_API int mgd_device_count(void);   /* 0 when no CUDA device / driver is usable */
+
+/*
+ * Multi-grid y_true target encoder.
+ * Replaces preprocess_true_boxes (multigriddet/data/generators.py:3393-3473,
+ * with best_fit_and_layer :2514-2544 and iol_common_center :2486-2494), called
+ * from MultiGridDataGenerator.__getitem__ (:1756).
+ *
+ *   boxes   (batch, max_boxes, 5) float32  [x1, y1, x2, y2, class] pixels;
+ *           rows with (x2-x1)*(y2-y1) <= 0 are padding (:3431)
+ *   y_true  num_layers pointers (array itself in host memory), each
+ *           (batch, grid_h, grid_w, 5+A_l+C) float32, fully overwritten
+ *   stats   optional host int64[4]: valid boxes, candidate writes skipped by the
+ *           occupancy rule (:3463), positive cells, reserved.  Only filled when
+ *           the call synchronises (host memory or MGD_FLAG_SYNC).
+ *
+ * MGD_ERR_CLASS_RANGE if any class id >= num_classes (all rows, like :3409);
+ * MGD_ERR_INVALID_ARGUMENT for a negative class id on a valid box (the reference
+ * would silently write a wrong channel).  For device memory without
+ * MGD_FLAG_SYNC these two are reported by the next synchronising call on the
+ * same thread via mgd_poll_status().
+ */
+MGD_API int mgd_encode_targets(const mgd_head_config *cfg, const float *boxes,
+                       int batch, int max_boxes, float *const *y_true,
+                       int memory, int device, void *stream, int flags,
+                       long long *stats);
+
+/*
+ * Dense head decode + score threshold + NMS + top-k + xyxy, per image.
+ * Replaces MultiGridDecoder.postprocess (multigriddet/postprocess/
+ * multigrid_decode.py:347-395 = decode_predictions :48-183, correct_boxes
+ * :185-235, handle_predictions :237-345, _convert_to_xyxy :397-422) and the
+ * greedy NMS classes (multigriddet/postprocess/nms.py:83-231, 320-385), called
+ * per image from evaluator.py:262 and inference_engine.py:127.  A batch is B
+ * independent batch-1 reference calls.
+ *
+ *   preds       num_layers pointers, each (batch, grid_h, grid_w, 5+A_l+C) float32
+ *   image_hw    (batch, 2) int32 original image (h, w); NULL = model input size
+ *   boxes_xywh  (batch, max_boxes, 4) float64 [x_min, y_min, w, h] (return_xyxy=False)
+ *   boxes_xyxy  (batch, max_boxes, 4) int32, clipped and rounded (:409-420)
+ *   scores      (batch, max_boxes) float64 (float32 values, like the reference)
+ *   classes     (batch, max_boxes) int32
+ *   index       (batch, max_boxes) int32 flat cell index of each detection in the
+ *               decode_predictions concatenation order (layer, row, col)
+ *   counts      (batch,) int32 detections per image; rows beyond it are 0 / -1
+ *   Any output pointer except counts may be NULL.
+ *   stats       optional host int64[4]: candidates >= confidence, detections,
+ *               reserved, reserved (filled only when the call synchronises).
+ * Detections are in descending score order; equal scores: lower cell index first.
+ */
+MGD_API int mgd_decode_nms(const mgd_head_config *cfg, const mgd_post_config *post,
+                   const float *const *preds, int batch, const int *image_hw,
+                   double *boxes_xywh, int *boxes_xyxy, double *scores,
+                   int *classes, int *index, int *counts,
+                   int memory, int device, void *stream, int flags,
+                   long long *stats);
+
+/*
+ * Dense decode only.  Replaces MultiGridDecoder.decode_predictions
+ * (multigrid_decode.py:48-98) and, when image_hw != NULL, correct_boxes
+ * (:185-235) applied per image.
+ *   out (batch, cells, 5+C) float64: [x, y, w, h, score, class probabilities...]
+ */
+MGD_API int mgd_decode_dense(const mgd_head_config *cfg, const mgd_post_config *post,
+                     const float *const *preds, int batch, const int *image_hw,
+                     double *out, int memory, int device, void *stream, int flags);
+
+/*
+ * Greedy NMS on caller-supplied boxes.  Replaces StandardNMS/DIoUNMS/ClusterNMS
+ * .apply_nms and nms_boxes (multigriddet/postprocess/nms.py:86-119, 154-187,
+ * 323-356, 389-399).
+ *   boxes (n, 4) float64 xywh, scores (n,) float64, classes (n,) int32 or NULL
+ *   keep  (n,) int32: kept positions in descending score order (ties: lower
+ *         position first); *n_keep (one int32 in the same memory space) = how many.
+ */
+MGD_API int mgd_nms(const double *boxes, const double *scores, const int *classes, int n,
+            double nms_threshold, int nms_method, int per_class, int max_keep,
+            int *keep, int *n_keep, int memory, int device, void *stream, int flags);
+
+/*
+ * Deferred device-side status of asynchronous calls issued by this thread on
+ * `device` (class-range errors found by the encode kernel).  Synchronises `stream`.
+ */
+MGD_API int mgd_poll_status(int device, void *stream);
+
+/* ---- DLPack zero-copy variants -------------------------------------------------
+ * The tensors arrive as DLTensor* (dlpack.h ABI, v0.8+): dtype, shape, strides and
+ * device are validated and the call forwards to the pointer entry point above.
+ * kDLCPU / kDLCUDAHost -> MGD_MEM_HOST, kDLCUDA -> MGD_MEM_DEVICE on that device.
+ * The library only borrows the tensors for the duration of the call (for async
+ * device calls: until `stream` reaches the enqueued work); it never calls a
+ * DLManagedTensor deleter.
+ */
+struct DLTensor;
+MGD_API int mgd_encode_targets_dlpack(const mgd_head_config *cfg, const struct DLTensor *boxes,
+                              struct DLTensor *const *y_true, void *stream, int flags,
+                              long long *stats);
+MGD_API int mgd_decode_nms_dlpack(const mgd_head_config *cfg, const mgd_post_config *post,
+                          const struct DLTensor *const *preds,
+                          const struct DLTensor *image_hw,
+                          struct DLTensor *boxes_xywh, struct DLTensor *boxes_xyxy,
+                          struct DLTensor *scores, struct DLTensor *classes,
+                          struct DLTensor *index, struct DLTensor *counts,
+                          void *stream, int flags, long long *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGD_H_ */

@@ -1,0 +1,164 @@
+"""ctypes binding of ``libmgd.so`` (the C ABI in ``include/mgd.h``).
+
+This is the only place the Python drop-ins touch native code.  There is no CPU
+or NumPy fallback: if the library is missing, or no B200 is visible, every
+compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmgd.so")
+
+MGD_MAX_LAYERS = 5
+MGD_MAX_ANCHORS_PER_LAYER = 8
+MEM_HOST, MEM_DEVICE = 0, 1
+FLAG_SYNC = 1
+NMS_IOU, NMS_DIOU = 0, 1
+
+OK, ERR_INVALID_ARGUMENT, ERR_CLASS_RANGE, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(6)
+
+
+class HeadConfig(ctypes.Structure):
+    """``mgd_head_config``"""
+    _fields_ = [
+        ("num_layers", ctypes.c_int),
+        ("num_classes", ctypes.c_int),
+        ("input_h", ctypes.c_int),
+        ("input_w", ctypes.c_int),
+        ("grid_h", ctypes.c_int * MGD_MAX_LAYERS),
+        ("grid_w", ctypes.c_int * MGD_MAX_LAYERS),
+        ("num_anchors", ctypes.c_int * MGD_MAX_LAYERS),
+        ("anchors", ((ctypes.c_double * 2) * MGD_MAX_ANCHORS_PER_LAYER) * MGD_MAX_LAYERS),
+        ("anchors_f64", ctypes.c_int),
+    ]
+
+
+class PostConfig(ctypes.Structure):
+    """``mgd_post_config``"""
+    _fields_ = [
+        ("use_softmax", ctypes.c_int),
+        ("rescore_confidence", ctypes.c_int),
+        ("confidence", ctypes.c_double),
+        ("nms_threshold", ctypes.c_double),
+        ("nms_method", ctypes.c_int),
+        ("per_class", ctypes.c_int),
+        ("max_boxes", ctypes.c_int),
+    ]
+
+
+class MgdError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_FP = ctypes.POINTER(ctypes.c_float)
+_DP = ctypes.POINTER(ctypes.c_double)
+_IP = ctypes.POINTER(ctypes.c_int)
+_LLP = ctypes.POINTER(ctypes.c_longlong)
+
+EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targets",
+           "mgd_decode_nms", "mgd_decode_dense", "mgd_nms", "mgd_poll_status",
+           "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack")
+
+
+def load():
+    """Load ``libmgd.so`` (building it is ``__graft_entry__.build()``'s job)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise MgdError(
+            f"{LIB_PATH} not found: build it with `python -m multigriddet_b200.build` "
+            "(needs nvcc).  multigriddet_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mgd_version.restype = ctypes.c_int
+    lib.mgd_last_error.restype = ctypes.c_char_p
+    lib.mgd_device_count.restype = ctypes.c_int
+    lib.mgd_encode_targets.restype = ctypes.c_int
+    lib.mgd_encode_targets.argtypes = [
+        ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+        ctypes.c_int, _LLP]
+    lib.mgd_decode_nms.restype = ctypes.c_int
+    lib.mgd_decode_nms.argtypes = [
+        ctypes.POINTER(HeadConfig), ctypes.POINTER(PostConfig),
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, _LLP]
+    lib.mgd_decode_dense.restype = ctypes.c_int
+    lib.mgd_decode_dense.argtypes = [
+        ctypes.POINTER(HeadConfig), ctypes.POINTER(PostConfig),
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.mgd_nms.restype = ctypes.c_int
+    lib.mgd_nms.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.mgd_poll_status.restype = ctypes.c_int
+    lib.mgd_poll_status.argtypes = [ctypes.c_int, ctypes.c_void_p]
+    lib.mgd_encode_targets_dlpack.restype = ctypes.c_int
+    lib.mgd_encode_targets_dlpack.argtypes = [
+        ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+        ctypes.c_void_p, ctypes.c_int, _LLP]
+    lib.mgd_decode_nms_dlpack.restype = ctypes.c_int
+    lib.mgd_decode_nms_dlpack.argtypes = [
+        ctypes.POINTER(HeadConfig), ctypes.POINTER(PostConfig),
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int, _LLP]
+    _lib = lib
+    return lib
+
+
+def raise_for_status(rc: int) -> None:
+    """Map ``mgd_status`` to the reference's exception types."""
+    if rc == OK:
+        return
+    msg = load().mgd_last_error().decode("utf-8", "replace")
+    if rc == ERR_CLASS_RANGE:
+        raise AssertionError(msg)              # generators.py:3409
+    if rc == ERR_INVALID_ARGUMENT:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise MgdError(msg)
+
+
+def make_head_config(anchors, num_classes, input_shape, grid_shapes=None) -> HeadConfig:
+    """``anchors``: list of (A_l, 2) arrays; their dtype picks the arithmetic path
+    (float64 only if the caller's anchors are float64, like NumPy promotion)."""
+    arrs = [np.asarray(a) for a in anchors]
+    num_layers = len(arrs)
+    if not 1 <= num_layers <= MGD_MAX_LAYERS:
+        raise ValueError(f"between 1 and {MGD_MAX_LAYERS} layers supported, got {num_layers}")
+    cfg = HeadConfig()
+    cfg.num_layers = num_layers
+    cfg.num_classes = int(num_classes)
+    cfg.input_h, cfg.input_w = int(input_shape[0]), int(input_shape[1])
+    if grid_shapes is None:                     # generators.py:3423
+        strides = (32, 16, 8, 4, 2)
+        grid_shapes = [(cfg.input_h // strides[l], cfg.input_w // strides[l])
+                       for l in range(num_layers)]
+    f64 = False
+    for l, a in enumerate(arrs):
+        if a.ndim != 2 or a.shape[1] != 2 or not 1 <= a.shape[0] <= MGD_MAX_ANCHORS_PER_LAYER:
+            raise ValueError(f"anchors[{l}] must have shape (1..{MGD_MAX_ANCHORS_PER_LAYER}, 2)")
+        f64 = f64 or a.dtype == np.float64
+        cfg.grid_h[l], cfg.grid_w[l] = int(grid_shapes[l][0]), int(grid_shapes[l][1])
+        cfg.num_anchors[l] = a.shape[0]
+        for i in range(a.shape[0]):
+            cfg.anchors[l][i][0] = float(a[i, 0])
+            cfg.anchors[l][i][1] = float(a[i, 1])
+    cfg.anchors_f64 = int(f64)
+    return cfg
+
+
+def ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) for p in ptrs])

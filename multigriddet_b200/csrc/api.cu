@@ -1,0 +1,802 @@
+// C ABI of libmgd (include/mgd.h): validation, scratch management, batching,
+// host staging and DLPack adapters around the kernels in encode.cu / decode.cu /
+// nms.cu.  No compute happens on the host and there is no CPU fallback.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "dlpack_abi.h"
+
+namespace {
+
+thread_local std::string t_error;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (expr);                                                        \
+        if (e__ != cudaSuccess)                                                          \
+            return fail(MGD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- per-device state -----------------------------------------------------------
+struct DeviceInfo {
+    bool ready = false;
+    int num_sms = 0;
+};
+std::mutex g_mutex;
+DeviceInfo g_dev[64];
+
+int device_count_quiet()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int prepare_device(int device, int* num_sms)
+{
+    const int n = device_count_quiet();
+    if (n == 0)
+        return fail(MGD_ERR_NO_DEVICE,
+                    "no CUDA device available: libmgd has no CPU fallback (sm_100a kernels only)");
+    if (device < 0 || device >= n || device >= 64)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "device %d out of range (have %d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceInfo& d = g_dev[device];
+    if (!d.ready) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            return fail(MGD_ERR_NO_DEVICE,
+                        "device %d is sm_%d%d; libmgd is built for sm_100a (B200) only",
+                        device, prop.major, prop.minor);
+        d.num_sms = prop.multiProcessorCount;
+        // keep freed scratch in the stream-ordered pool instead of returning it to the OS
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        d.ready = true;
+    }
+    *num_sms = d.num_sms;
+    return MGD_OK;
+}
+
+// ---- geometry --------------------------------------------------------------------
+int build_geom(const mgd_head_config* cfg, HeadGeom* g)
+{
+    if (!cfg) return fail(MGD_ERR_INVALID_ARGUMENT, "cfg is NULL");
+    if (cfg->num_layers < 1 || cfg->num_layers > MGD_MAX_LAYERS)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "num_layers must be in [1, %d], got %d",
+                    MGD_MAX_LAYERS, cfg->num_layers);
+    if (cfg->num_classes < 1)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "num_classes must be >= 1, got %d", cfg->num_classes);
+    if (cfg->input_h < 1 || cfg->input_w < 1)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "input shape must be positive");
+    if (cfg->input_h != cfg->input_w)
+        return fail(MGD_ERR_UNSUPPORTED,
+                    "non-square input %dx%d: the reference's cell arithmetic is only "
+                    "self-consistent for square inputs (generators.py:3438-3470)",
+                    cfg->input_h, cfg->input_w);
+    memset(g, 0, sizeof(*g));
+    g->L = cfg->num_layers;
+    g->C = cfg->num_classes;
+    g->in_h = cfg->input_h;
+    g->in_w = cfg->input_w;
+    g->anchors_f64 = cfg->anchors_f64 ? 1 : 0;
+    int k = 0;
+    long long cells = 0;
+    for (int l = 0; l < g->L; ++l) {
+        if (cfg->grid_h[l] < 1 || cfg->grid_w[l] < 1 || cfg->grid_h[l] > 8192)
+            return fail(MGD_ERR_INVALID_ARGUMENT, "grid of layer %d must be in [1, 8192]", l);
+        if (cfg->grid_h[l] != cfg->grid_w[l])
+            return fail(MGD_ERR_UNSUPPORTED, "non-square grid %dx%d on layer %d",
+                        cfg->grid_h[l], cfg->grid_w[l], l);
+        if (cfg->num_anchors[l] < 1 || cfg->num_anchors[l] > MGD_MAX_ANCHORS_PER_LAYER)
+            return fail(MGD_ERR_INVALID_ARGUMENT, "layer %d: anchors per layer must be in [1, %d]",
+                        l, MGD_MAX_ANCHORS_PER_LAYER);
+        g->gh[l] = cfg->grid_h[l];
+        g->gw[l] = cfg->grid_w[l];
+        g->na[l] = cfg->num_anchors[l];
+        g->D[l] = 5 + g->na[l] + g->C;
+        g->anchor_first[l] = k;
+        g->cell_off[l] = (int)cells;
+        for (int i = 0; i < g->na[l]; ++i, ++k) {
+            const double w = cfg->anchors[l][i][0], h = cfg->anchors[l][i][1];
+            if (!(w > 0.0) || !(h > 0.0))
+                return fail(MGD_ERR_INVALID_ARGUMENT, "anchor %d of layer %d is not positive", i, l);
+            g->anc64[k][0] = w; g->anc64[k][1] = h;
+            g->anc32[k][0] = (float)w; g->anc32[k][1] = (float)h;
+        }
+        cells += (long long)g->gh[l] * g->gw[l];
+    }
+    if (cells > (1 << 24))
+        return fail(MGD_ERR_UNSUPPORTED, "%lld cells per image exceeds the supported 2^24", cells);
+    g->K = k;
+    g->cells = (int)cells;
+    return MGD_OK;
+}
+
+int check_memory_arg(int memory)
+{
+    if (memory != MGD_MEM_HOST && memory != MGD_MEM_DEVICE)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "memory must be MGD_MEM_HOST or MGD_MEM_DEVICE");
+    return MGD_OK;
+}
+
+// images per internal chunk: keeps the per-chunk scratch (owner table / candidate
+// lists) around 32 MB so it stays L2-resident between the two kernels that share it
+int chunk_images(const HeadGeom& g, int batch)
+{
+    long long n = (32ll << 20) / ((long long)g.cells * 4);
+    if (n < 1) n = 1;
+    if (n > batch) n = batch;
+    return (int)n;
+}
+
+// ---- deferred device-side status of asynchronous encode calls ---------------------
+struct Pending { int* host; int device; };
+thread_local std::vector<Pending> t_pending;
+thread_local std::vector<int*> t_free_slots;
+
+int* take_status_slot()
+{
+    if (!t_free_slots.empty()) { int* p = t_free_slots.back(); t_free_slots.pop_back(); return p; }
+    int* p = nullptr;
+    if (cudaMallocHost(&p, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+int status_to_error(int st)
+{
+    if (st & 1) return fail(MGD_ERR_CLASS_RANGE, "class id must be less than num_classes");
+    if (st & 2)
+        return fail(MGD_ERR_INVALID_ARGUMENT,
+                    "negative class id on a valid box (the reference would write a wrong channel)");
+    return MGD_OK;
+}
+
+// ---- encode ------------------------------------------------------------------------
+struct EncodeScratch { int* table; BoxRec* recs; };
+
+int encode_device(const HeadGeom& g, const float* boxes, int batch, int N, float* const* y,
+                  int num_sms, cudaStream_t stream, int* d_status, unsigned long long* d_stats)
+{
+    const int step = chunk_images(g, batch);
+    for (int b0 = 0; b0 < batch; b0 += step) {
+        const int nb = batch - b0 < step ? batch - b0 : step;
+        EncodeArgs a;
+        a.g = g;
+        a.B = nb;
+        a.N = N;
+        a.boxes = boxes + (size_t)b0 * N * 5;
+        for (int l = 0; l < g.L; ++l)
+            a.y[l] = y[l] + (size_t)b0 * g.gh[l] * g.gw[l] * g.D[l];
+        a.status = d_status;
+        a.stats = d_stats;
+        CUDA_TRY(cudaMallocAsync(&a.table, (size_t)nb * g.cells * sizeof(int), stream));
+        CUDA_TRY(cudaMallocAsync(&a.recs, (size_t)nb * (N > 0 ? N : 1) * sizeof(BoxRec), stream));
+        CUDA_TRY(launch_encode(a, num_sms, stream));
+        CUDA_TRY(cudaFreeAsync(a.table, stream));
+        CUDA_TRY(cudaFreeAsync(a.recs, stream));
+    }
+    return MGD_OK;
+}
+
+// ---- decode + nms -------------------------------------------------------------------
+float objectness_prefilter(const mgd_post_config& post)
+{
+    // score <= sigmoid(obj): a row with sigmoid(obj) < confidence can never pass.
+    // Compare raw logits against logit(confidence) minus a margin that dwarfs any
+    // float32 rounding in the reference's sigmoid (relative 1e-4 vs 1e-7).
+    const double c = post.confidence;
+    if (!(c > 0.0)) return -INFINITY;
+    if (c >= 1.0) return 15.0f;            // sigmoid_f32(x) reaches 1.0f only for x > 17.3
+    const double logit = log(c / (1.0 - c));
+    return (float)(logit - 1e-3 - 1e-4 * fabs(logit));
+}
+
+int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const float* const* preds,
+                      int batch, const int* image_hw, double* xywh, int* xyxy, double* scores,
+                      int* classes, int* index, int* counts, int num_sms, cudaStream_t stream,
+                      unsigned long long* d_stats)
+{
+    const int step = chunk_images(g, batch);
+    const int M = post.max_boxes;
+    int pow2 = 2;
+    while (pow2 < g.cells) pow2 <<= 1;
+    const bool big_sort = g.cells > nms_smem_capacity();
+    const bool big_keep = nms_kept_bytes(M) > 64 * 1024;
+    for (int b0 = 0; b0 < batch; b0 += step) {
+        const int nb = batch - b0 < step ? batch - b0 : step;
+        DecodeArgs d;
+        memset(&d, 0, sizeof(d));
+        d.g = g;
+        d.B = nb;
+        for (int l = 0; l < g.L; ++l)
+            d.pred[l] = preds[l] + (size_t)b0 * g.gh[l] * g.gw[l] * g.D[l];
+        d.image_hw = image_hw ? image_hw + 2 * (size_t)b0 : nullptr;
+        d.use_softmax = post.use_softmax;
+        d.rescore = post.rescore_confidence;
+        d.confidence = post.confidence;
+        d.obj_logit_min = objectness_prefilter(post);
+        CUDA_TRY(cudaMallocAsync(&d.cand, (size_t)nb * g.cells * sizeof(Cand), stream));
+        CUDA_TRY(cudaMallocAsync(&d.counts, (size_t)nb * sizeof(int), stream));
+        CUDA_TRY(cudaMemsetAsync(d.counts, 0, (size_t)nb * sizeof(int), stream));
+        CUDA_TRY(launch_decode(d, num_sms, stream));
+
+        NmsArgs n;
+        memset(&n, 0, sizeof(n));
+        n.B = nb;
+        n.cap = g.cells;
+        n.cand = d.cand;
+        n.counts = d.counts;
+        n.image_hw = d.image_hw;
+        n.in_h = g.in_h; n.in_w = g.in_w;
+        n.thr = post.nms_threshold;
+        n.use_diou = post.nms_method == MGD_NMS_DIOU;
+        n.per_class = post.per_class;
+        n.max_boxes = M;
+        if (big_sort) {
+            n.sort_scratch_stride = pow2;
+            CUDA_TRY(cudaMallocAsync(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long), stream));
+        }
+        if (big_keep) {
+            n.kept_scratch_stride = (nms_kept_bytes(M) + 15) & ~(size_t)15;
+            CUDA_TRY(cudaMallocAsync(&n.kept_scratch, (size_t)nb * n.kept_scratch_stride, stream));
+        }
+        n.out_xywh = xywh ? xywh + (size_t)b0 * M * 4 : nullptr;
+        n.out_xyxy = xyxy ? xyxy + (size_t)b0 * M * 4 : nullptr;
+        n.out_scores = scores ? scores + (size_t)b0 * M : nullptr;
+        n.out_classes = classes ? classes + (size_t)b0 * M : nullptr;
+        n.out_index = index ? index + (size_t)b0 * M : nullptr;
+        n.out_counts = counts + b0;
+        n.stats = d_stats;
+        CUDA_TRY(launch_nms(n, num_sms, stream));
+        if (n.sort_scratch) CUDA_TRY(cudaFreeAsync(n.sort_scratch, stream));
+        if (n.kept_scratch) CUDA_TRY(cudaFreeAsync(n.kept_scratch, stream));
+        CUDA_TRY(cudaFreeAsync(d.cand, stream));
+        CUDA_TRY(cudaFreeAsync(d.counts, stream));
+    }
+    return MGD_OK;
+}
+
+int check_post(const mgd_post_config* post)
+{
+    if (!post) return fail(MGD_ERR_INVALID_ARGUMENT, "post config is NULL");
+    if (post->max_boxes < 1 || post->max_boxes > (1 << 20))
+        return fail(MGD_ERR_INVALID_ARGUMENT, "max_boxes must be in [1, 2^20], got %d", post->max_boxes);
+    if (post->nms_method != MGD_NMS_IOU && post->nms_method != MGD_NMS_DIOU)
+        return fail(MGD_ERR_UNSUPPORTED, "nms_method %d: only MGD_NMS_IOU / MGD_NMS_DIOU are built",
+                    post->nms_method);
+    if (post->confidence != post->confidence || post->nms_threshold != post->nms_threshold)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "confidence / nms_threshold is NaN");
+    return MGD_OK;
+}
+
+// streams used for host-memory calls, one pair per host thread and device
+struct HostStreams { cudaStream_t s[2] = {nullptr, nullptr}; };
+thread_local HostStreams t_streams[64];
+
+int host_streams(int device, cudaStream_t** out)
+{
+    HostStreams& hs = t_streams[device];
+    for (int i = 0; i < 2; ++i)
+        if (!hs.s[i]) CUDA_TRY(cudaStreamCreateWithFlags(&hs.s[i], cudaStreamNonBlocking));
+    *out = hs.s;
+    return MGD_OK;
+}
+
+int host_chunk(const HeadGeom& g, int batch)
+{
+    // ~0.7 GB of y_true / predictions per chunk: long enough copies to run the PCIe
+    // link at speed, short enough for the two streams to overlap H2D, kernels and D2H
+    long long per_image = 0;
+    for (int l = 0; l < g.L; ++l) per_image += (long long)g.gh[l] * g.gw[l] * g.D[l] * 4;
+    long long n = (700ll << 20) / (per_image > 0 ? per_image : 1);
+    if (n < 1) n = 1;
+    if (n > batch) n = batch;
+    return (int)n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgd_version(void) { return MGD_VERSION; }
+
+const char* mgd_last_error(void) { return t_error.c_str(); }
+
+int mgd_device_count(void) { return device_count_quiet(); }
+
+int mgd_poll_status(int device, void* stream)
+{
+    int num_sms;
+    int rc = prepare_device(device, &num_sms);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    int st = 0;
+    std::vector<Pending> keep;
+    for (Pending& p : t_pending) {
+        if (p.device == device) { st |= *p.host; t_free_slots.push_back(p.host); }
+        else keep.push_back(p);
+    }
+    t_pending.swap(keep);
+    return status_to_error(st);
+}
+
+int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch, int max_boxes,
+                       float* const* y_true, int memory, int device, void* stream, int flags,
+                       long long* stats)
+{
+    HeadGeom g;
+    int rc = build_geom(cfg, &g);
+    if (rc) return rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (batch < 0 || max_boxes < 0)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "batch and max_boxes must be >= 0");
+    if (!y_true) return fail(MGD_ERR_INVALID_ARGUMENT, "y_true is NULL");
+    for (int l = 0; l < g.L; ++l)
+        if (!y_true[l] && batch > 0) return fail(MGD_ERR_INVALID_ARGUMENT, "y_true[%d] is NULL", l);
+    if (!boxes && (long long)batch * max_boxes > 0)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "boxes is NULL");
+    if (max_boxes > 65000)
+        return fail(MGD_ERR_UNSUPPORTED, "max_boxes per image must be <= 65000, got %d", max_boxes);
+    if ((long long)chunk_images(g, batch > 0 ? batch : 1) * max_boxes >= (1ll << 27))
+        return fail(MGD_ERR_UNSUPPORTED, "batch chunk x max_boxes too large");
+    if (encode_assign_smem_bytes(g, max_boxes) > 220 * 1024)
+        return fail(MGD_ERR_UNSUPPORTED,
+                    "%d cells + %d boxes per image do not fit the 227 KB shared memory of one SM",
+                    g.cells, max_boxes);
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    if (stats) memset(stats, 0, 4 * sizeof(long long));
+    if (batch == 0) return MGD_OK;
+
+    if (memory == MGD_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)stream;
+        int* d_status;
+        unsigned long long* d_stats = nullptr;
+        CUDA_TRY(cudaMallocAsync(&d_status, sizeof(int) + 4 * sizeof(unsigned long long), st));
+        CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int) + 4 * sizeof(unsigned long long), st));
+        // keep the 8-byte counters aligned: status word sits after them
+        d_stats = reinterpret_cast<unsigned long long*>(d_status);
+        int* d_flag = reinterpret_cast<int*>(d_stats + 4);
+        rc = encode_device(g, boxes, batch, max_boxes, y_true, num_sms, st, d_flag, d_stats);
+        if (rc) return rc;
+        if (flags & MGD_FLAG_SYNC) {
+            unsigned long long h[5] = {0, 0, 0, 0, 0};
+            CUDA_TRY(cudaMemcpyAsync(h, d_status, sizeof(int) + 4 * sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaFreeAsync(d_status, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
+            return status_to_error((int)(h[4] & 0xffffffffu));
+        }
+        int* slot = take_status_slot();
+        if (slot) {
+            *slot = 0;
+            CUDA_TRY(cudaMemcpyAsync(slot, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            t_pending.push_back({slot, device});
+        }
+        CUDA_TRY(cudaFreeAsync(d_status, st));
+        return MGD_OK;
+    }
+
+    // host memory: stage through the GPU in chunks, two streams so that the D2H of one
+    // chunk overlaps the H2D + kernels of the next
+    cudaStream_t* ss;
+    if ((rc = host_streams(device, &ss))) return rc;
+    unsigned long long* d_meta;      // [4 stats][status]
+    CUDA_TRY(cudaMalloc(&d_meta, 5 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d_meta, 0, 5 * sizeof(unsigned long long)));
+    const int step = host_chunk(g, batch);
+    int k = 0;
+    for (int b0 = 0; b0 < batch; b0 += step, ++k) {
+        const int nb = batch - b0 < step ? batch - b0 : step;
+        cudaStream_t st = ss[k & 1];
+        float* d_boxes;
+        float* d_y[MGD_MAX_LAYERS];
+        const size_t box_bytes = (size_t)nb * max_boxes * 5 * sizeof(float);
+        CUDA_TRY(cudaMallocAsync(&d_boxes, box_bytes ? box_bytes : 4, st));
+        if (box_bytes)
+            CUDA_TRY(cudaMemcpyAsync(d_boxes, boxes + (size_t)b0 * max_boxes * 5, box_bytes,
+                                     cudaMemcpyHostToDevice, st));
+        for (int l = 0; l < g.L; ++l)
+            CUDA_TRY(cudaMallocAsync(&d_y[l], (size_t)nb * g.gh[l] * g.gw[l] * g.D[l] * 4, st));
+        rc = encode_device(g, d_boxes, nb, max_boxes, d_y, num_sms, st,
+                           reinterpret_cast<int*>(d_meta + 4), d_meta);
+        if (rc) { cudaFree(d_meta); return rc; }
+        for (int l = 0; l < g.L; ++l) {
+            const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
+            CUDA_TRY(cudaMemcpyAsync(y_true[l] + (size_t)b0 * per, d_y[l], (size_t)nb * per * 4,
+                                     cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaFreeAsync(d_y[l], st));
+        }
+        CUDA_TRY(cudaFreeAsync(d_boxes, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ss[0]));
+    CUDA_TRY(cudaStreamSynchronize(ss[1]));
+    unsigned long long h[5];
+    CUDA_TRY(cudaMemcpy(h, d_meta, sizeof(h), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFree(d_meta));
+    if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
+    return status_to_error((int)(h[4] & 0xffffffffu));
+}
+
+int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
+                   const float* const* preds, int batch, const int* image_hw,
+                   double* boxes_xywh, int* boxes_xyxy, double* scores, int* classes, int* index,
+                   int* counts, int memory, int device, void* stream, int flags, long long* stats)
+{
+    HeadGeom g;
+    int rc = build_geom(cfg, &g);
+    if (rc) return rc;
+    if ((rc = check_post(post))) return rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (batch < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (!preds) return fail(MGD_ERR_INVALID_ARGUMENT, "preds is NULL");
+    for (int l = 0; l < g.L; ++l)
+        if (!preds[l] && batch > 0) return fail(MGD_ERR_INVALID_ARGUMENT, "preds[%d] is NULL", l);
+    if (!counts && batch > 0) return fail(MGD_ERR_INVALID_ARGUMENT, "counts is NULL");
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    if (stats) memset(stats, 0, 4 * sizeof(long long));
+    if (batch == 0) return MGD_OK;
+    const int M = post->max_boxes;
+
+    if (memory == MGD_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)stream;
+        unsigned long long* d_stats = nullptr;
+        const bool want_stats = stats && (flags & MGD_FLAG_SYNC);
+        if (want_stats) {
+            CUDA_TRY(cudaMallocAsync(&d_stats, 4 * sizeof(unsigned long long), st));
+            CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
+        }
+        rc = decode_nms_device(g, *post, preds, batch, image_hw, boxes_xywh, boxes_xyxy, scores,
+                               classes, index, counts, num_sms, st, d_stats);
+        if (rc) return rc;
+        if (flags & MGD_FLAG_SYNC) {
+            unsigned long long h[4] = {0, 0, 0, 0};
+            if (want_stats) {
+                CUDA_TRY(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaFreeAsync(d_stats, st));
+            }
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
+        }
+        return MGD_OK;
+    }
+
+    cudaStream_t* ss;
+    if ((rc = host_streams(device, &ss))) return rc;
+    unsigned long long* d_stats;
+    CUDA_TRY(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
+    const int step = host_chunk(g, batch);
+    int k = 0;
+    for (int b0 = 0; b0 < batch; b0 += step, ++k) {
+        const int nb = batch - b0 < step ? batch - b0 : step;
+        cudaStream_t st = ss[k & 1];
+        float* d_pred[MGD_MAX_LAYERS];
+        for (int l = 0; l < g.L; ++l) {
+            const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
+            CUDA_TRY(cudaMallocAsync(&d_pred[l], (size_t)nb * per * 4, st));
+            CUDA_TRY(cudaMemcpyAsync(d_pred[l], preds[l] + (size_t)b0 * per, (size_t)nb * per * 4,
+                                     cudaMemcpyHostToDevice, st));
+        }
+        int* d_hw = nullptr;
+        if (image_hw) {
+            CUDA_TRY(cudaMallocAsync(&d_hw, (size_t)nb * 2 * sizeof(int), st));
+            CUDA_TRY(cudaMemcpyAsync(d_hw, image_hw + 2 * (size_t)b0, (size_t)nb * 2 * sizeof(int),
+                                     cudaMemcpyHostToDevice, st));
+        }
+        // one output slab: xywh f64 | scores f64 | xyxy i32 | classes i32 | index i32 | counts i32
+        const size_t n_det = (size_t)nb * M;
+        const size_t off_scores = n_det * 4 * sizeof(double);
+        const size_t off_xyxy = off_scores + n_det * sizeof(double);
+        const size_t off_cls = off_xyxy + n_det * 4 * sizeof(int);
+        const size_t off_idx = off_cls + n_det * sizeof(int);
+        const size_t off_cnt = off_idx + n_det * sizeof(int);
+        const size_t slab = off_cnt + (size_t)nb * sizeof(int);
+        unsigned char* d_out;
+        CUDA_TRY(cudaMallocAsync(&d_out, slab, st));
+        rc = decode_nms_device(g, *post, d_pred, nb, d_hw,
+                               reinterpret_cast<double*>(d_out),
+                               reinterpret_cast<int*>(d_out + off_xyxy),
+                               reinterpret_cast<double*>(d_out + off_scores),
+                               reinterpret_cast<int*>(d_out + off_cls),
+                               reinterpret_cast<int*>(d_out + off_idx),
+                               reinterpret_cast<int*>(d_out + off_cnt), num_sms, st, d_stats);
+        if (rc) { cudaFree(d_stats); return rc; }
+        if (boxes_xywh)
+            CUDA_TRY(cudaMemcpyAsync(boxes_xywh + (size_t)b0 * M * 4, d_out, n_det * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (scores)
+            CUDA_TRY(cudaMemcpyAsync(scores + (size_t)b0 * M, d_out + off_scores, n_det * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (boxes_xyxy)
+            CUDA_TRY(cudaMemcpyAsync(boxes_xyxy + (size_t)b0 * M * 4, d_out + off_xyxy, n_det * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (classes)
+            CUDA_TRY(cudaMemcpyAsync(classes + (size_t)b0 * M, d_out + off_cls, n_det * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (index)
+            CUDA_TRY(cudaMemcpyAsync(index + (size_t)b0 * M, d_out + off_idx, n_det * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(counts + b0, d_out + off_cnt, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaFreeAsync(d_out, st));
+        if (d_hw) CUDA_TRY(cudaFreeAsync(d_hw, st));
+        for (int l = 0; l < g.L; ++l) CUDA_TRY(cudaFreeAsync(d_pred[l], st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ss[0]));
+    CUDA_TRY(cudaStreamSynchronize(ss[1]));
+    unsigned long long h[4];
+    CUDA_TRY(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFree(d_stats));
+    if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
+    return MGD_OK;
+}
+
+int mgd_decode_dense(const mgd_head_config* cfg, const mgd_post_config* post,
+                     const float* const* preds, int batch, const int* image_hw, double* out,
+                     int memory, int device, void* stream, int flags)
+{
+    HeadGeom g;
+    int rc = build_geom(cfg, &g);
+    if (rc) return rc;
+    if (!post) return fail(MGD_ERR_INVALID_ARGUMENT, "post config is NULL");
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (batch < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (batch > 0 && (!preds || !out)) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    if (batch == 0) return MGD_OK;
+    DecodeArgs d;
+    memset(&d, 0, sizeof(d));
+    d.g = g;
+    d.use_softmax = post->use_softmax;
+    d.rescore = post->rescore_confidence;
+    const size_t out_per = (size_t)g.cells * (5 + g.C);
+    if (memory == MGD_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)stream;
+        d.B = batch;
+        for (int l = 0; l < g.L; ++l) d.pred[l] = preds[l];
+        CUDA_TRY(launch_decode_dense(d, image_hw, out, st));
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    cudaStream_t* ss;
+    if ((rc = host_streams(device, &ss))) return rc;
+    cudaStream_t st = ss[0];
+    long long per_image = (long long)out_per * 8;
+    int step = (int)((512ll << 20) / per_image);
+    if (step < 1) step = 1;
+    for (int b0 = 0; b0 < batch; b0 += step) {
+        const int nb = batch - b0 < step ? batch - b0 : step;
+        float* d_pred[MGD_MAX_LAYERS];
+        d.B = nb;
+        for (int l = 0; l < g.L; ++l) {
+            const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
+            CUDA_TRY(cudaMallocAsync(&d_pred[l], (size_t)nb * per * 4, st));
+            CUDA_TRY(cudaMemcpyAsync(d_pred[l], preds[l] + (size_t)b0 * per, (size_t)nb * per * 4,
+                                     cudaMemcpyHostToDevice, st));
+            d.pred[l] = d_pred[l];
+        }
+        int* d_hw = nullptr;
+        if (image_hw) {
+            CUDA_TRY(cudaMallocAsync(&d_hw, (size_t)nb * 2 * sizeof(int), st));
+            CUDA_TRY(cudaMemcpyAsync(d_hw, image_hw + 2 * (size_t)b0, (size_t)nb * 2 * sizeof(int),
+                                     cudaMemcpyHostToDevice, st));
+        }
+        double* d_out;
+        CUDA_TRY(cudaMallocAsync(&d_out, (size_t)nb * out_per * 8, st));
+        CUDA_TRY(launch_decode_dense(d, d_hw, d_out, st));
+        CUDA_TRY(cudaMemcpyAsync(out + (size_t)b0 * out_per, d_out, (size_t)nb * out_per * 8,
+                                 cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaFreeAsync(d_out, st));
+        if (d_hw) CUDA_TRY(cudaFreeAsync(d_hw, st));
+        for (int l = 0; l < g.L; ++l) CUDA_TRY(cudaFreeAsync(d_pred[l], st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return MGD_OK;
+}
+
+int mgd_nms(const double* boxes, const double* scores, const int* classes, int n,
+            double nms_threshold, int nms_method, int per_class, int max_keep, int* keep,
+            int* n_keep, int memory, int device, void* stream, int flags)
+{
+    int rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (n < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n must be >= 0");
+    if (nms_method != MGD_NMS_IOU && nms_method != MGD_NMS_DIOU)
+        return fail(MGD_ERR_UNSUPPORTED, "nms_method %d not built", nms_method);
+    if (!n_keep) return fail(MGD_ERR_INVALID_ARGUMENT, "n_keep is NULL");
+    if (n > 0 && (!boxes || !scores || !keep)) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    if (max_keep <= 0 || max_keep > n) max_keep = n;
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    const bool host = memory == MGD_MEM_HOST;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (host) {
+        cudaStream_t* ss;
+        if ((rc = host_streams(device, &ss))) return rc;
+        st = ss[0];
+    }
+    if (n == 0) {
+        if (host) { *n_keep = 0; return MGD_OK; }
+        CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int), st));
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    const double* d_boxes = boxes; const double* d_scores = scores; const int* d_classes = classes;
+    int* d_keep = keep; int* d_nkeep = n_keep;
+    void* staged = nullptr;
+    if (host) {
+        const size_t bytes = (size_t)n * (4 * 8 + 8 + 4 + 4) + 16;
+        CUDA_TRY(cudaMallocAsync(&staged, bytes, st));
+        double* p = reinterpret_cast<double*>(staged);
+        CUDA_TRY(cudaMemcpyAsync(p, boxes, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(p + 4 * (size_t)n, scores, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        int* q = reinterpret_cast<int*>(p + 5 * (size_t)n);
+        if (classes) CUDA_TRY(cudaMemcpyAsync(q, classes, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        d_boxes = p; d_scores = p + 4 * (size_t)n; d_classes = classes ? q : nullptr;
+        d_keep = q + n; d_nkeep = q + 2 * (size_t)n;
+    }
+    Cand* cand; int* count; int* d_index; int* d_counts;
+    CUDA_TRY(cudaMallocAsync(&cand, (size_t)n * sizeof(Cand), st));
+    CUDA_TRY(cudaMallocAsync(&count, 2 * sizeof(int) + (size_t)max_keep * sizeof(int), st));
+    d_counts = count + 1;
+    d_index = count + 2;
+    CUDA_TRY(launch_pack_candidates(d_boxes, d_scores, d_classes, n, cand, count, st));
+    NmsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = 1; a.cap = n; a.cand = cand; a.counts = count;
+    a.thr = nms_threshold; a.use_diou = nms_method == MGD_NMS_DIOU; a.per_class = per_class;
+    a.max_boxes = max_keep;
+    int pow2 = 2;
+    while (pow2 < n) pow2 <<= 1;
+    if (n > nms_smem_capacity()) {
+        a.sort_scratch_stride = pow2;
+        CUDA_TRY(cudaMallocAsync(&a.sort_scratch, (size_t)2 * pow2 * sizeof(unsigned long long), st));
+    }
+    if (nms_kept_bytes(max_keep) > 64 * 1024) {
+        a.kept_scratch_stride = (nms_kept_bytes(max_keep) + 15) & ~(size_t)15;
+        CUDA_TRY(cudaMallocAsync(&a.kept_scratch, a.kept_scratch_stride, st));
+    }
+    a.out_index = d_index;
+    a.out_counts = d_counts;
+    CUDA_TRY(launch_nms(a, num_sms, st));
+    CUDA_TRY(launch_keep_from_index(d_index, d_counts, max_keep, d_keep, d_nkeep, st));
+    if (host) {
+        CUDA_TRY(cudaMemcpyAsync(n_keep, d_nkeep, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(keep, d_keep, (size_t)max_keep * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    if (a.sort_scratch) CUDA_TRY(cudaFreeAsync(a.sort_scratch, st));
+    if (a.kept_scratch) CUDA_TRY(cudaFreeAsync(a.kept_scratch, st));
+    CUDA_TRY(cudaFreeAsync(cand, st));
+    CUDA_TRY(cudaFreeAsync(count, st));
+    if (staged) CUDA_TRY(cudaFreeAsync(staged, st));
+    if (host || (flags & MGD_FLAG_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
+    return MGD_OK;
+}
+
+}  // extern "C"
+
+// ---- DLPack adapters ---------------------------------------------------------------
+namespace {
+
+int dl_check(const DLTensor* t, const char* name, uint8_t code, uint8_t bits, int ndim,
+             const long long* shape, int* memory, int* device)
+{
+    if (!t) return fail(MGD_ERR_INVALID_ARGUMENT, "%s is NULL", name);
+    if (t->dtype.code != code || t->dtype.bits != bits || t->dtype.lanes != 1)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "%s: wrong dtype (code %d bits %d)", name,
+                    (int)t->dtype.code, (int)t->dtype.bits);
+    if (t->ndim != ndim) return fail(MGD_ERR_INVALID_ARGUMENT, "%s: expected %d dims, got %d", name, ndim, t->ndim);
+    long long expect_stride = 1;
+    for (int i = ndim - 1; i >= 0; --i) {
+        if (shape[i] >= 0 && t->shape[i] != shape[i])
+            return fail(MGD_ERR_INVALID_ARGUMENT, "%s: dim %d is %lld, expected %lld", name, i,
+                        (long long)t->shape[i], shape[i]);
+        if (t->strides && t->shape[i] > 1 && t->strides[i] != expect_stride)
+            return fail(MGD_ERR_INVALID_ARGUMENT, "%s: tensor must be dense row-major", name);
+        expect_stride *= t->shape[i];
+    }
+    int mem, dev = 0;
+    if (t->device.device_type == kDLCPU || t->device.device_type == kDLCUDAHost) mem = MGD_MEM_HOST;
+    else if (t->device.device_type == kDLCUDA) { mem = MGD_MEM_DEVICE; dev = t->device.device_id; }
+    else return fail(MGD_ERR_INVALID_ARGUMENT, "%s: unsupported DLPack device type %d", name,
+                     (int)t->device.device_type);
+    if (*memory < 0) { *memory = mem; *device = dev; }
+    else if (*memory != mem || (mem == MGD_MEM_DEVICE && *device != dev))
+        return fail(MGD_ERR_INVALID_ARGUMENT, "%s: all tensors of a call must live in the same memory", name);
+    return MGD_OK;
+}
+
+template <typename T> T* dl_ptr(const DLTensor* t)
+{
+    return t ? reinterpret_cast<T*>(static_cast<char*>(t->data) + t->byte_offset) : nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgd_encode_targets_dlpack(const mgd_head_config* cfg, const DLTensor* boxes,
+                              DLTensor* const* y_true, void* stream, int flags, long long* stats)
+{
+    HeadGeom g;
+    int rc = build_geom(cfg, &g);
+    if (rc) return rc;
+    int memory = -1, device = 0;
+    const long long bshape[3] = {-1, -1, 5};
+    if ((rc = dl_check(boxes, "boxes", kDLFloat, 32, 3, bshape, &memory, &device))) return rc;
+    const long long B = boxes->shape[0], N = boxes->shape[1];
+    if (!y_true) return fail(MGD_ERR_INVALID_ARGUMENT, "y_true is NULL");
+    float* yp[MGD_MAX_LAYERS];
+    for (int l = 0; l < g.L; ++l) {
+        const long long s[4] = {B, g.gh[l], g.gw[l], g.D[l]};
+        char name[32];
+        snprintf(name, sizeof(name), "y_true[%d]", l);
+        if ((rc = dl_check(y_true[l], name, kDLFloat, 32, 4, s, &memory, &device))) return rc;
+        yp[l] = dl_ptr<float>(y_true[l]);
+    }
+    int cur = 0;
+    if (memory == MGD_MEM_HOST) { cudaGetDevice(&cur); cudaGetLastError(); device = cur; }
+    return mgd_encode_targets(cfg, dl_ptr<const float>(boxes), (int)B, (int)N, yp, memory, device,
+                              stream, flags, stats);
+}
+
+int mgd_decode_nms_dlpack(const mgd_head_config* cfg, const mgd_post_config* post,
+                          const DLTensor* const* preds, const DLTensor* image_hw,
+                          DLTensor* boxes_xywh, DLTensor* boxes_xyxy, DLTensor* scores,
+                          DLTensor* classes, DLTensor* index, DLTensor* counts, void* stream,
+                          int flags, long long* stats)
+{
+    HeadGeom g;
+    int rc = build_geom(cfg, &g);
+    if (rc) return rc;
+    if ((rc = check_post(post))) return rc;
+    if (!preds || !preds[0]) return fail(MGD_ERR_INVALID_ARGUMENT, "preds is NULL");
+    int memory = -1, device = 0;
+    const long long B = preds[0]->ndim == 4 ? preds[0]->shape[0] : -1;
+    const float* pp[MGD_MAX_LAYERS];
+    for (int l = 0; l < g.L; ++l) {
+        const long long s[4] = {B, g.gh[l], g.gw[l], g.D[l]};
+        char name[32];
+        snprintf(name, sizeof(name), "preds[%d]", l);
+        if ((rc = dl_check(preds[l], name, kDLFloat, 32, 4, s, &memory, &device))) return rc;
+        pp[l] = dl_ptr<const float>(preds[l]);
+    }
+    const long long M = post->max_boxes;
+    const long long s_hw[2] = {B, 2}, s_b4[3] = {B, M, 4}, s_b[2] = {B, M}, s_c[1] = {B};
+    if (image_hw && (rc = dl_check(image_hw, "image_hw", kDLInt, 32, 2, s_hw, &memory, &device))) return rc;
+    if (boxes_xywh && (rc = dl_check(boxes_xywh, "boxes_xywh", kDLFloat, 64, 3, s_b4, &memory, &device))) return rc;
+    if (boxes_xyxy && (rc = dl_check(boxes_xyxy, "boxes_xyxy", kDLInt, 32, 3, s_b4, &memory, &device))) return rc;
+    if (scores && (rc = dl_check(scores, "scores", kDLFloat, 64, 2, s_b, &memory, &device))) return rc;
+    if (classes && (rc = dl_check(classes, "classes", kDLInt, 32, 2, s_b, &memory, &device))) return rc;
+    if (index && (rc = dl_check(index, "index", kDLInt, 32, 2, s_b, &memory, &device))) return rc;
+    if ((rc = dl_check(counts, "counts", kDLInt, 32, 1, s_c, &memory, &device))) return rc;
+    int cur = 0;
+    if (memory == MGD_MEM_HOST) { cudaGetDevice(&cur); cudaGetLastError(); device = cur; }
+    return mgd_decode_nms(cfg, post, pp, (int)B, dl_ptr<const int>(image_hw),
+                          dl_ptr<double>(boxes_xywh), dl_ptr<int>(boxes_xyxy), dl_ptr<double>(scores),
+                          dl_ptr<int>(classes), dl_ptr<int>(index), dl_ptr<int>(counts), memory,
+                          device, stream, flags, stats);
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Shared declarations of libmgd's CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/mgd.h"
+
+#define MGD_MAX_TOTAL_ANCHORS (MGD_MAX_LAYERS * MGD_MAX_ANCHORS_PER_LAYER)
+
+// Device-side view of mgd_head_config plus derived constants.
+struct HeadGeom {
+    int L, C;
+    int in_h, in_w;
+    int gh[MGD_MAX_LAYERS], gw[MGD_MAX_LAYERS];
+    int na[MGD_MAX_LAYERS];            // anchors per layer
+    int D[MGD_MAX_LAYERS];             // channels per cell = 5 + A + C
+    int anchor_first[MGD_MAX_LAYERS];  // global index of the layer's first anchor
+    int K;                             // total anchors
+    int cell_off[MGD_MAX_LAYERS];      // first cell of the layer within one image
+    int cells;                         // cells per image over all layers
+    int anchors_f64;
+    float anc32[MGD_MAX_TOTAL_ANCHORS][2];
+    double anc64[MGD_MAX_TOTAL_ANCHORS][2];
+};
+
+// ---- encode ---------------------------------------------------------------
+// One record per valid ground-truth box, written by the assign kernel and read
+// by the fill kernel for the (few) cells the box owns.
+struct __align__(16) BoxRec {
+    double fx, fy;     // fractional centre offsets inside the centre cell (f64 like NumPy)
+    float tw, th;      // log size ratios to the matched anchor
+    int hot_anchor;    // channel 5 + k
+    int hot_class;     // channel 5 + A + class
+};
+
+struct EncodeArgs {
+    HeadGeom g;
+    int B, N;
+    const float* boxes;               // (B, N, 5)
+    float* y[MGD_MAX_LAYERS];         // (B, gh, gw, D)
+    int* table;                       // layer-major owner table: [l][b][cell]
+    BoxRec* recs;                     // (B, N)
+    int* status;                      // bit0: class >= C, bit1: negative class on a valid box
+    unsigned long long* stats;        // [valid boxes, skipped writes, positive cells, -]
+};
+
+// ---- decode / NMS ---------------------------------------------------------
+struct __align__(16) Cand {
+    double x, y, w, h;   // [x_min, y_min, w, h] in original-image pixels
+    double score;        // float32-valued in the decode path (the reference's op order)
+    int index;           // flat cell index (layer, row, col); position for mgd_nms
+    int cls;
+};
+
+struct DecodeArgs {
+    HeadGeom g;
+    int B;
+    const float* pred[MGD_MAX_LAYERS];
+    const int* image_hw;              // (B, 2) or nullptr
+    int use_softmax, rescore;
+    double confidence;
+    float obj_logit_min;              // conservative prefilter on the raw objectness logit
+    // tiling
+    int rows_per_tile;
+    long long tile_first[MGD_MAX_LAYERS + 1];   // prefix sum of tiles per layer
+    long long rows_in_layer[MGD_MAX_LAYERS];    // B * gh * gw
+    Cand* cand;                       // (B, cells)
+    int* counts;                      // (B,)
+};
+
+struct NmsArgs {
+    int B;
+    int cap;                          // candidate slots per image
+    const Cand* cand;
+    const int* counts;
+    const int* image_hw;              // (B,2) or nullptr (then in_h, in_w)
+    int in_h, in_w;
+    double thr;
+    int use_diou, per_class, max_boxes;
+    unsigned long long* sort_scratch; // (B, 2*pow2(cap)) u64, used when count > smem capacity
+    int sort_scratch_stride;          // elements (pairs) per image in sort_scratch
+    unsigned char* kept_scratch;      // kept-box list in global memory when max_boxes is large
+    size_t kept_scratch_stride;       // bytes per image
+    double* out_xywh; int* out_xyxy; double* out_scores; int* out_classes; int* out_index;
+    int* out_counts;
+    unsigned long long* stats;        // [candidates, detections]
+};
+
+// launchers (each enqueues on `stream` and returns the launch error, if any)
+cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_decode(const DecodeArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_nms(const NmsArgs& a, int num_sms, cudaStream_t stream);
+size_t encode_assign_smem_bytes(const HeadGeom& g, int N);
+int nms_smem_capacity();
+size_t nms_kept_bytes(int max_boxes);
+cudaError_t launch_decode_dense(const DecodeArgs& a, const int* image_hw, double* out,
+                                cudaStream_t stream);
+cudaError_t launch_pack_candidates(const double* boxes, const double* scores, const int* classes,
+                                   int n, Cand* cand, int* count, cudaStream_t stream);
+cudaError_t launch_keep_from_index(const int* index, const int* counts, int max_keep, int* keep,
+                                   int* n_keep, cudaStream_t stream);

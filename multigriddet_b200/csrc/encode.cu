@@ -1,0 +1,323 @@
+// Multi-grid y_true target encoder for sm_100a.
+//
+// Replaces the O(B*N*9) Python loop of preprocess_true_boxes
+// (reference multigriddet/data/generators.py:3393-3473) with two kernels:
+//
+//   encode_assign_kernel  one CTA per image, thread per ground-truth box.
+//       Anchor matching (generators.py:2486-2494, 2529-2532) and the 3x3 scatter
+//       with the reference's sequential overwrite rule (:3454-3472), resolved
+//       without any ordering between boxes:
+//         cover[cell] = min box index whose 3x3 block contains the cell
+//                       (== "cell occupied before box t"  <=>  cover[cell] < t,
+//                        because the first box covering a cell always writes it)
+//         a box skips a candidate iff cover[cell] < t and it has written >= 3
+//         owner[cell] = max box index among the boxes that write the cell
+//       Both tables live in shared memory (atomicMin / atomicMax); the result is
+//       a per-cell owner code (box record, neighbour id) written once, coalesced.
+//
+//   encode_fill_kernel    grid-wide streaming writer.  Every y_true row
+//       (5+A+C floats) is produced exactly once -- zeros, or the owner's values --
+//       with 16-byte streaming stores; the dense tensor is never memset first.
+//       HBM-bound: algorithmic bytes = cells*D*4 written + 20 B/box read.
+//
+// All arithmetic that decides an integer (anchor, layer, cell, skip) uses IEEE
+// single/double operations in the reference's order; the file is compiled with
+// -fmad=false so nothing is contracted.
+#include <limits.h>
+#include <math.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kAssignThreads = 256;
+constexpr int kFillThreads = 256;
+constexpr int kFillBatch = 4;           // independent row groups in flight per warp
+
+// generators.py:2486-2494 + np.round(iol, 3) + first maximum (lowest global index)
+__device__ __forceinline__ int match_anchor(const HeadGeom& g, float bw, float bh)
+{
+    int best = 0;
+    if (!g.anchors_f64) {
+        float top = -INFINITY;
+        const float box_area = __fmul_rn(bw, bh);
+        for (int i = 0; i < g.K; ++i) {
+            const float aw = g.anc32[i][0], ah = g.anc32[i][1];
+            const float inter = __fmul_rn(fminf(bw, aw), fminf(bh, ah));
+            const float iol = __fdiv_rn(inter, fmaxf(box_area, __fmul_rn(aw, ah)));
+            // round(x,3) = rint(x*1000)/1000; the division is monotone and injective
+            // on these integers, so the argmax can be taken on rint(x*1000)
+            const float r = rintf(__fmul_rn(iol, 1000.0f));
+            if (r > top) { top = r; best = i; }
+        }
+    } else {
+        double top = -INFINITY;
+        const double box_area = (double)__fmul_rn(bw, bh);   // float32 product, :2489
+        for (int i = 0; i < g.K; ++i) {
+            const double aw = g.anc64[i][0], ah = g.anc64[i][1];
+            const double inter = __dmul_rn(fmin((double)bw, aw), fmin((double)bh, ah));
+            const double iol = __ddiv_rn(inter, fmax(box_area, __dmul_rn(aw, ah)));
+            const double r = rint(__dmul_rn(iol, 1000.0));
+            if (r > top) { top = r; best = i; }
+        }
+    }
+    return best;
+}
+
+// packed per-box placement kept in shared memory between the phases
+__device__ __forceinline__ int pack_place(int layer, int col, int row)
+{
+    // anything further than one cell outside the grid has no in-bounds candidate
+    col = min(max(col, -2), 16380) + 2;
+    row = min(max(row, -2), 16380) + 2;
+    return (layer << 28) | (row << 14) | col;
+}
+
+__global__ void __launch_bounds__(kAssignThreads)
+encode_assign_kernel(const __grid_constant__ EncodeArgs a)
+{
+    extern __shared__ int sm[];
+    const HeadGeom& g = a.g;
+    int* cover = sm;                    // [cells]
+    int* owner = sm + g.cells;          // [cells]
+    int* place = owner + g.cells;       // [N]
+    __shared__ unsigned int s_stat[3];
+    __shared__ int s_status;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < g.cells; i += kAssignThreads) { cover[i] = INT_MAX; owner[i] = -1; }
+    if (tid < 3) s_stat[tid] = 0;
+    if (tid == 0) s_status = 0;
+    __syncthreads();
+
+    unsigned int n_valid = 0, n_skipped = 0, n_pos = 0;
+    int status = 0;
+
+    // ---- phase A: per-box record + cover table --------------------------------
+    for (int t = tid; t < a.N; t += kAssignThreads) {
+        const float* bx = a.boxes + ((size_t)b * a.N + t) * 5;
+        const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3], cf = bx[4];
+        if (!(cf < (float)g.C)) status |= 1;                         // :3409, every row
+        const float bw = __fsub_rn(x2, x1), bh = __fsub_rn(y2, y1);  // :3416
+        int pl = -1;
+        if (!(__fmul_rn(bw, bh) <= 0.0f)) {                          // :3431
+            ++n_valid;
+            const int cls = (int)cf;                                 // astype('int32')
+            if (cls < 0) status |= 2;
+            // (x1+x2)//2 on float32 == floor((x1+x2)/2): the halving is exact
+            const float cxp = floorf(__fmul_rn(__fadd_rn(x1, x2), 0.5f));   // :3415
+            const float cyp = floorf(__fmul_rn(__fadd_rn(y1, y2), 0.5f));
+            const int ga = match_anchor(g, bw, bh);
+            int layer = 0;
+            while (layer + 1 < g.L && ga >= g.anchor_first[layer + 1]) ++layer;
+            const int k = ga - g.anchor_first[layer];
+            // :3438-3439  f32 * (G/S as float64) -> float64 (NumPy 2 promotion)
+            const double gx = __dmul_rn((double)cxp, __ddiv_rn((double)g.gh[layer], (double)g.in_h));
+            const double gy = __dmul_rn((double)cyp, __ddiv_rn((double)g.gw[layer], (double)g.in_w));
+            const int col = (int)fmin(fmax(gx, -4.0), 1.0e6);        // int(): truncation
+            const int row = (int)fmin(fmax(gy, -4.0), 1.0e6);
+            BoxRec rec;
+            rec.fx = __dsub_rn(gx, (double)col);
+            rec.fy = __dsub_rn(gy, (double)row);
+            if (!g.anchors_f64) {                                    // :3446-3449
+                const float rw = __fdiv_rn(bw, g.anc32[ga][0]);
+                const float rh = __fdiv_rn(bh, g.anc32[ga][1]);
+                // NumPy's float32 log is libm logf there; log in double rounded once
+                // to float reproduces it (<= 1 ulp away in ~0.4% of inputs)
+                rec.tw = (float)log(rw < 1e-3f ? 1e-3 : (double)rw);
+                rec.th = (float)log(rh < 1e-3f ? 1e-3 : (double)rh);
+            } else {
+                const double rw = __ddiv_rn((double)bw, g.anc64[ga][0]);
+                const double rh = __ddiv_rn((double)bh, g.anc64[ga][1]);
+                rec.tw = (float)log(rw < 1e-3 ? 1e-3 : rw);
+                rec.th = (float)log(rh < 1e-3 ? 1e-3 : rh);
+            }
+            rec.hot_anchor = 5 + k;
+            rec.hot_class = 5 + g.na[layer] + max(cls, 0);
+            a.recs[(size_t)b * a.N + t] = rec;
+            pl = pack_place(layer, col, row);
+            const int g0 = g.gh[layer], g1 = g.gw[layer];
+            const int c0 = (pl & 0x3fff) - 2, r0 = ((pl >> 14) & 0x3fff) - 2;
+            #pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                #pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int cc = c0 + dx, rr = r0 + dy;
+                    if (cc >= 0 && cc < g0 && rr >= 0 && rr < g1)
+                        atomicMin(&cover[g.cell_off[layer] + rr * g1 + cc], t);
+                }
+            }
+        }
+        place[t] = pl;
+    }
+    __syncthreads();
+
+    // ---- phase B: sequential skip rule per box, owner = last writer -----------
+    for (int t = tid; t < a.N; t += kAssignThreads) {
+        const int pl = place[t];
+        if (pl < 0) continue;
+        const int layer = pl >> 28;
+        const int c0 = (pl & 0x3fff) - 2, r0 = ((pl >> 14) & 0x3fff) - 2;
+        const int g0 = g.gh[layer], g1 = g.gw[layer];
+        int written = 0;
+        #pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {                           // :3454 x outer
+            #pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {                       // :3456 y inner
+                const int cc = c0 + dx, rr = r0 + dy;
+                if (cc < 0 || cc >= g0 || rr < 0 || rr >= g1) continue;   // :3459-3462
+                const int cell = g.cell_off[layer] + rr * g1 + cc;
+                if (cover[cell] < t && written >= 3) { ++n_skipped; continue; }   // :3463
+                ++written;
+                atomicMax(&owner[cell], t * 16 + (dx + 1) * 3 + (dy + 1));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase C: publish the owner codes, layer-major ------------------------
+    const int rec_base = b * a.N * 16;
+    for (int l = 0; l < g.L; ++l) {
+        const int n = g.gh[l] * g.gw[l];
+        int* dst = a.table + (size_t)a.B * g.cell_off[l] + (size_t)b * n;
+        const int* src = owner + g.cell_off[l];
+        for (int i = tid; i < n; i += kAssignThreads) {
+            const int v = src[i];
+            dst[i] = v < 0 ? -1 : v + rec_base;
+            n_pos += (v >= 0);
+        }
+    }
+    if (n_valid) atomicAdd(&s_stat[0], n_valid);
+    if (n_skipped) atomicAdd(&s_stat[1], n_skipped);
+    if (n_pos) atomicAdd(&s_stat[2], n_pos);
+    if (status) atomicOr(&s_status, status);
+    __syncthreads();
+    if (tid < 3 && a.stats && s_stat[tid]) atomicAdd(&a.stats[tid], (unsigned long long)s_stat[tid]);
+    if (tid == 0 && s_status) atomicOr(a.status, s_status);
+}
+
+// Per-layer plan of the streaming writer.
+struct FillPlan {
+    int dv[MGD_MAX_LAYERS];                 // vector units per row = D / VEC
+    int rpw[MGD_MAX_LAYERS];                // rows one warp covers per step
+    long long group_first[MGD_MAX_LAYERS + 1];
+    long long rows[MGD_MAX_LAYERS];
+};
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC>
+__device__ __forceinline__ typename VecT<VEC>::type
+make_units(const BoxRec& r, int code, int ch0)
+{
+    float v[VEC];
+    const int nb = code & 15;
+    #pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int ch = ch0 + j;
+        float x;
+        if (ch == 0)      x = (float)__dadd_rn((double)(1 - nb / 3), r.fx);   // -dx + fx, :3467
+        else if (ch == 1) x = (float)__dadd_rn((double)(1 - nb % 3), r.fy);   // -dy + fy
+        else if (ch == 2) x = r.tw;
+        else if (ch == 3) x = r.th;
+        else x = (ch == 4 || ch == r.hot_anchor || ch == r.hot_class) ? 1.0f : 0.0f;
+        v[j] = x;
+    }
+    if constexpr (VEC == 4) return make_float4(v[0], v[1], v[2], v[3]);
+    else return v[0];
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kFillThreads)
+encode_fill_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ FillPlan p)
+{
+    using V = typename VecT<VEC>::type;
+    const HeadGeom& g = a.g;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * kFillThreads + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * kFillThreads) >> 5;
+    const long long total = p.group_first[g.L];
+
+    for (long long base = warp; base < total; base += n_warps * kFillBatch) {
+        int code[kFillBatch];
+        long long row[kFillBatch];
+        int lay[kFillBatch], part[kFillBatch];
+        #pragma unroll
+        for (int u = 0; u < kFillBatch; ++u) {
+            const long long grp = base + (long long)u * n_warps;
+            code[u] = -2;                                   // -2: nothing to do
+            if (grp < total) {
+                int l = 0;
+                while (l + 1 < g.L && grp >= p.group_first[l + 1]) ++l;
+                const int dv = p.dv[l];
+                const int sub = dv <= 32 ? lane / dv : 0;
+                const long long r = (grp - p.group_first[l]) * p.rpw[l] + sub;
+                lay[u] = l;
+                part[u] = dv <= 32 ? lane - sub * dv : lane;
+                row[u] = r;
+                if (sub < p.rpw[l] && r < p.rows[l])
+                    code[u] = __ldg(a.table + (size_t)a.B * g.cell_off[l] + r);
+            }
+        }
+        #pragma unroll
+        for (int u = 0; u < kFillBatch; ++u) {
+            if (code[u] == -2) continue;
+            const int l = lay[u];
+            const int dv = p.dv[l];
+            V* dst = reinterpret_cast<V*>(a.y[l]) + row[u] * dv;
+            if (code[u] < 0) {
+                V z;
+                if constexpr (VEC == 4) z = make_float4(0.f, 0.f, 0.f, 0.f); else z = 0.f;
+                for (int q = part[u]; q < dv; q += 32) __stcs(dst + q, z);
+            } else {
+                const BoxRec rec = a.recs[code[u] >> 4];
+                for (int q = part[u]; q < dv; q += 32)
+                    __stcs(dst + q, make_units<VEC>(rec, code[u], q * VEC));
+            }
+        }
+    }
+}
+
+}  // namespace
+
+size_t encode_assign_smem_bytes(const HeadGeom& g, int N)
+{
+    return (size_t)(2 * g.cells + N) * sizeof(int);
+}
+
+cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
+{
+    const HeadGeom& g = a.g;
+    const size_t smem = encode_assign_smem_bytes(g, a.N);
+    cudaError_t err = cudaFuncSetAttribute(encode_assign_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    encode_assign_kernel<<<a.B, kAssignThreads, smem, stream>>>(a);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+
+    bool vec4 = true;
+    for (int l = 0; l < g.L; ++l)
+        vec4 = vec4 && (g.D[l] % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y[l]) & 15) == 0);
+    const int vec = vec4 ? 4 : 1;
+    FillPlan p;
+    long long groups = 0;
+    for (int l = 0; l < g.L; ++l) {
+        p.dv[l] = g.D[l] / vec;
+        p.rpw[l] = p.dv[l] <= 32 ? 32 / p.dv[l] : 1;
+        p.rows[l] = (long long)a.B * g.gh[l] * g.gw[l];
+        p.group_first[l] = groups;
+        groups += (p.rows[l] + p.rpw[l] - 1) / p.rpw[l];
+    }
+    p.group_first[g.L] = groups;
+    const long long warps_needed = (groups + kFillBatch - 1) / kFillBatch;
+    long long blocks = (warps_needed * 32 + kFillThreads - 1) / kFillThreads;
+    const long long max_blocks = (long long)num_sms * (2048 / kFillThreads);   // one full wave
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    if (vec4) encode_fill_kernel<4><<<(unsigned)blocks, kFillThreads, 0, stream>>>(a, p);
+    else      encode_fill_kernel<1><<<(unsigned)blocks, kFillThreads, 0, stream>>>(a, p);
+    return cudaGetLastError();
+}

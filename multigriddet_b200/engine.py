@@ -1,0 +1,266 @@
+"""Array-level entry points over the C ABI.
+
+Accepts NumPy arrays (host memory: the library stages through the GPU), torch
+CUDA tensors (device memory, zero-copy, enqueued on the current torch stream)
+and any other object exporting ``__dlpack__`` (e.g. TensorFlow tensors via
+``tf.experimental.dlpack``), which goes through the ``*_dlpack`` entry points.
+Outputs are allocated here, in the same memory space as the inputs, and handed
+to the library: the library never owns tensor memory.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_NMS_METHODS = {"diou": _lib.NMS_DIOU, "standard": _lib.NMS_IOU, "iou": _lib.NMS_IOU,
+                "cluster": _lib.NMS_IOU}
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def _torch_stream(device_index: int) -> int:
+    import torch
+    return int(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+def _current_device() -> int:
+    # host-memory calls run on the caller's current CUDA device when torch is in the
+    # process (one rank per GPU under torchrun), else on device 0
+    import sys
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available():
+        return int(torch.cuda.current_device())
+    return 0
+
+
+def device_count() -> int:
+    return int(_lib.load().mgd_device_count())
+
+
+def post_config(max_boxes=100, confidence=0.1, nms_threshold=0.5, nms_method="diou",
+                per_class=False, use_softmax=True, rescore_confidence=True) -> _lib.PostConfig:
+    if nms_method not in _NMS_METHODS:
+        raise NotImplementedError(
+            f"nms_method={nms_method!r}: the CUDA path implements 'diou', 'standard' and "
+            "'cluster' (greedy hard NMS); 'soft' / WBF are not built yet")
+    pc = _lib.PostConfig()
+    pc.use_softmax = int(bool(use_softmax))
+    pc.rescore_confidence = int(bool(rescore_confidence))
+    pc.confidence = float(confidence)
+    pc.nms_threshold = float(nms_threshold)
+    pc.nms_method = _NMS_METHODS[nms_method]
+    pc.per_class = int(bool(per_class))
+    pc.max_boxes = int(max_boxes)
+    return pc
+
+
+# ------------------------------------------------------------------------------
+# encode
+# ------------------------------------------------------------------------------
+
+def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=None,
+                   out=None, sync=True, return_stats=False):
+    """Multi-grid y_true encoder (reference ``preprocess_true_boxes`` semantics).
+
+    true_boxes: (B, N, 5) NumPy array (any dtype) or torch CUDA float32 tensor.
+    Returns a list of L arrays/tensors (B, Gh, Gw, 5+A+C) float32 in the same
+    memory space.  ``sync=False`` (device tensors only) returns right after the
+    kernels are enqueued on the current stream; class-range errors then surface
+    at the next ``poll_status``.
+    """
+    lib = _lib.load()
+    cfg = _lib.make_head_config(anchors, num_classes, input_shape, grid_shapes)
+    L = cfg.num_layers
+    stats = (ctypes.c_longlong * 4)()
+    if _is_torch(true_boxes):
+        import torch
+        if not true_boxes.is_cuda:
+            raise ValueError("torch tensors must live on a CUDA device (pass NumPy for host data)")
+        boxes = true_boxes.to(torch.float32).contiguous()
+        if boxes.dim() != 3 or boxes.shape[2] != 5:
+            raise ValueError(f"true_boxes must be (B, N, 5), got {tuple(boxes.shape)}")
+        B, N = int(boxes.shape[0]), int(boxes.shape[1])
+        dev = boxes.device.index or 0
+        if out is None:
+            out = [torch.empty((B, cfg.grid_h[l], cfg.grid_w[l], 5 + cfg.num_anchors[l] + cfg.num_classes),
+                               dtype=torch.float32, device=boxes.device) for l in range(L)]
+        ptrs = _lib.ptr_array([o.data_ptr() for o in out])
+        rc = lib.mgd_encode_targets(ctypes.byref(cfg), ctypes.c_void_p(boxes.data_ptr()), B, N,
+                                    ptrs, _lib.MEM_DEVICE, dev,
+                                    ctypes.c_void_p(_torch_stream(dev)),
+                                    _lib.FLAG_SYNC if sync else 0, stats)
+    else:
+        boxes = np.ascontiguousarray(np.asarray(true_boxes), dtype=np.float32)
+        if boxes.ndim != 3 or boxes.shape[2] != 5:
+            raise ValueError(f"true_boxes must be (B, N, 5), got {boxes.shape}")
+        B, N = boxes.shape[0], boxes.shape[1]
+        if out is None:
+            out = [np.empty((B, cfg.grid_h[l], cfg.grid_w[l], 5 + cfg.num_anchors[l] + cfg.num_classes),
+                            dtype=np.float32) for l in range(L)]
+        ptrs = _lib.ptr_array([o.ctypes.data for o in out])
+        rc = lib.mgd_encode_targets(ctypes.byref(cfg), ctypes.c_void_p(boxes.ctypes.data), B, N,
+                                    ptrs, _lib.MEM_HOST, _current_device(), None,
+                                    _lib.FLAG_SYNC, stats)
+    _lib.raise_for_status(rc)
+    if return_stats:
+        return out, {"n_valid_boxes": int(stats[0]), "n_skipped_writes": int(stats[1]),
+                     "n_positive_cells": int(stats[2])}
+    return out
+
+
+def poll_status(device=None, stream=None):
+    """Synchronise and raise any deferred device-side error of async calls."""
+    lib = _lib.load()
+    dev = _current_device() if device is None else int(device)
+    st = _torch_stream(dev) if stream is None else int(stream)
+    _lib.raise_for_status(lib.mgd_poll_status(dev, ctypes.c_void_p(st)))
+
+
+# ------------------------------------------------------------------------------
+# decode + NMS
+# ------------------------------------------------------------------------------
+
+def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_boxes=100,
+               confidence=0.1, nms_threshold=0.5, nms_method="diou", per_class=False,
+               use_softmax=True, rescore_confidence=True, sync=True, return_stats=False,
+               want=("boxes_xywh", "boxes_xyxy", "scores", "classes", "index")):
+    """Batched decode -> threshold -> NMS -> top-k (B independent reference calls).
+
+    preds: list of L (B, Gh, Gw, 5+A+C) float32 NumPy arrays or torch CUDA tensors.
+    image_shapes: None (model input size), one (h, w), or (B, 2).
+    Returns a dict of padded arrays/tensors + 'counts' (B,).
+    """
+    lib = _lib.load()
+    L = len(preds)
+    if L != len(anchors):
+        raise ValueError(f"Expected {len(anchors)} predictions, got {L}")   # multigrid_decode.py:62-63
+    grid_shapes = [(int(p.shape[1]), int(p.shape[2])) for p in preds]
+    cfg = _lib.make_head_config(anchors, num_classes, model_image_size, grid_shapes)
+    pc = post_config(max_boxes, confidence, nms_threshold, nms_method, per_class, use_softmax,
+                     rescore_confidence)
+    B = int(preds[0].shape[0])
+    for l, p in enumerate(preds):
+        exp = (B, cfg.grid_h[l], cfg.grid_w[l], 5 + cfg.num_anchors[l] + cfg.num_classes)
+        if tuple(int(v) for v in p.shape) != exp:
+            raise ValueError(f"preds[{l}] has shape {tuple(p.shape)}, expected {exp}")
+    M = int(max_boxes)
+    stats = (ctypes.c_longlong * 4)()
+    hw = None
+    if image_shapes is not None:
+        hw = np.asarray(image_shapes, dtype=np.int32).reshape(-1, 2)
+        if hw.shape[0] == 1 and B != 1:
+            hw = np.tile(hw, (B, 1))
+        if hw.shape[0] != B:
+            raise ValueError(f"image_shapes must be (h, w) or (B, 2); got {hw.shape} for B={B}")
+        hw = np.ascontiguousarray(hw)
+    spec = {"boxes_xywh": ((B, M, 4), "float64"), "boxes_xyxy": ((B, M, 4), "int32"),
+            "scores": ((B, M), "float64"), "classes": ((B, M), "int32"),
+            "index": ((B, M), "int32")}
+    out = {}
+    if _is_torch(preds[0]):
+        import torch
+        dev = preds[0].device.index or 0
+        tp = [p.to(torch.float32).contiguous() for p in preds]
+        for k in want:
+            out[k] = torch.empty(spec[k][0], dtype=getattr(torch, spec[k][1]), device=tp[0].device)
+        out["counts"] = torch.empty((B,), dtype=torch.int32, device=tp[0].device)
+        d_hw = torch.from_numpy(hw).to(tp[0].device, non_blocking=False) if hw is not None else None
+        addr = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else None
+        rc = lib.mgd_decode_nms(
+            ctypes.byref(cfg), ctypes.byref(pc), _lib.ptr_array([p.data_ptr() for p in tp]), B,
+            ctypes.c_void_p(d_hw.data_ptr()) if d_hw is not None else None,
+            addr("boxes_xywh"), addr("boxes_xyxy"), addr("scores"), addr("classes"),
+            addr("index"), addr("counts"), _lib.MEM_DEVICE, dev,
+            ctypes.c_void_p(_torch_stream(dev)), _lib.FLAG_SYNC if sync else 0, stats)
+        out["_keepalive"] = (tp, d_hw)
+    else:
+        npreds = [np.ascontiguousarray(np.asarray(p), dtype=np.float32) for p in preds]
+        for k in want:
+            out[k] = np.empty(spec[k][0], dtype=spec[k][1])
+        out["counts"] = np.empty((B,), dtype=np.int32)
+        addr = lambda k: ctypes.c_void_p(out[k].ctypes.data) if k in out else None
+        rc = lib.mgd_decode_nms(
+            ctypes.byref(cfg), ctypes.byref(pc), _lib.ptr_array([p.ctypes.data for p in npreds]), B,
+            ctypes.c_void_p(hw.ctypes.data) if hw is not None else None,
+            addr("boxes_xywh"), addr("boxes_xyxy"), addr("scores"), addr("classes"),
+            addr("index"), addr("counts"), _lib.MEM_HOST, _current_device(), None,
+            _lib.FLAG_SYNC, stats)
+    _lib.raise_for_status(rc)
+    if not sync:
+        return out
+    out.pop("_keepalive", None)
+    if return_stats:
+        out["stats"] = {"n_candidates": int(stats[0]), "n_detections": int(stats[1])}
+    return out
+
+
+def decode_dense(preds, anchors, num_classes, model_image_size, image_shapes=None,
+                 use_softmax=True, rescore_confidence=True):
+    """Dense decode (reference ``decode_predictions`` [+ ``correct_boxes``]):
+    (B, cells, 5+C) float64."""
+    lib = _lib.load()
+    if len(preds) != len(anchors):
+        raise ValueError(f"Expected {len(anchors)} predictions, got {len(preds)}")
+    grid_shapes = [(int(p.shape[1]), int(p.shape[2])) for p in preds]
+    cfg = _lib.make_head_config(anchors, num_classes, model_image_size, grid_shapes)
+    pc = post_config(use_softmax=use_softmax, rescore_confidence=rescore_confidence)
+    B = int(preds[0].shape[0])
+    cells = sum(g[0] * g[1] for g in grid_shapes)
+    hw = None
+    if image_shapes is not None:
+        hw = np.asarray(image_shapes, dtype=np.int32).reshape(-1, 2)
+        if hw.shape[0] == 1 and B != 1:
+            hw = np.tile(hw, (B, 1))
+        hw = np.ascontiguousarray(hw)
+    if _is_torch(preds[0]):
+        import torch
+        dev = preds[0].device.index or 0
+        tp = [p.to(torch.float32).contiguous() for p in preds]
+        out = torch.empty((B, cells, 5 + int(num_classes)), dtype=torch.float64, device=tp[0].device)
+        d_hw = torch.from_numpy(hw).to(tp[0].device) if hw is not None else None
+        rc = lib.mgd_decode_dense(ctypes.byref(cfg), ctypes.byref(pc),
+                                  _lib.ptr_array([p.data_ptr() for p in tp]), B,
+                                  ctypes.c_void_p(d_hw.data_ptr()) if d_hw is not None else None,
+                                  ctypes.c_void_p(out.data_ptr()), _lib.MEM_DEVICE, dev,
+                                  ctypes.c_void_p(_torch_stream(dev)), _lib.FLAG_SYNC)
+    else:
+        npreds = [np.ascontiguousarray(np.asarray(p), dtype=np.float32) for p in preds]
+        out = np.empty((B, cells, 5 + int(num_classes)), dtype=np.float64)
+        rc = lib.mgd_decode_dense(ctypes.byref(cfg), ctypes.byref(pc),
+                                  _lib.ptr_array([p.ctypes.data for p in npreds]), B,
+                                  ctypes.c_void_p(hw.ctypes.data) if hw is not None else None,
+                                  ctypes.c_void_p(out.ctypes.data), _lib.MEM_HOST,
+                                  _current_device(), None, _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    return out
+
+
+def nms(boxes, scores, classes=None, nms_threshold=0.5, nms_method="diou", per_class=False,
+        max_keep=0):
+    """Greedy NMS on (n,4) xywh float64 boxes; returns kept positions (descending score)."""
+    lib = _lib.load()
+    if nms_method not in _NMS_METHODS:
+        raise NotImplementedError(f"nms_method={nms_method!r} is not built")
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
+    s = np.ascontiguousarray(np.asarray(scores, dtype=np.float64).reshape(-1))
+    n = b.shape[0]
+    if s.shape[0] != n:
+        raise ValueError("boxes and scores disagree on n")
+    c = None
+    if classes is not None:
+        c = np.ascontiguousarray(np.asarray(classes).astype(np.int32).reshape(-1))
+    keep = np.empty((max(n, 1),), dtype=np.int32)
+    n_keep = ctypes.c_int(0)
+    rc = lib.mgd_nms(ctypes.c_void_p(b.ctypes.data), ctypes.c_void_p(s.ctypes.data),
+                     ctypes.c_void_p(c.ctypes.data) if c is not None else None, n,
+                     float(nms_threshold), _NMS_METHODS[nms_method], int(bool(per_class)),
+                     int(max_keep), ctypes.c_void_p(keep.ctypes.data),
+                     ctypes.cast(ctypes.byref(n_keep), ctypes.c_void_p), _lib.MEM_HOST,
+                     _current_device(), None, _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    return keep[:n_keep.value].astype(np.int64)

@@ -1,0 +1,355 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): bit-exact cell / anchor / class indices, masks and
+NMS keep sets; float targets and decoded boxes within 1e-5 relative.  The oracle
+here is ``oracle/mgd_oracle.c`` (pinned to the NumPy oracle and through it to the
+reference, see tests/test_oracle_*.py), fast enough for full-size batches.
+"""
+import numpy as np
+import pytest
+
+from multigriddet_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5          # north_star tolerance for float targets / decoded boxes
+
+
+def _assert_encode_equal(got, ref, n_anchor=3):
+    exact_float = 0
+    total_float = 0
+    for g, r in zip(got, ref):
+        assert g.shape == r.shape and g.dtype == np.float32
+        # integer content: objectness mask, anchor one-hot, class one-hot -> bit-exact
+        assert np.array_equal(g[..., 4:], r[..., 4:])
+        # offsets are exact binary fractions -> bit-exact
+        assert np.array_equal(g[..., 0:2], r[..., 0:2])
+        # log size ratios: 1e-5 relative (expected: equal in almost every cell)
+        np.testing.assert_allclose(g[..., 2:4], r[..., 2:4], rtol=RTOL, atol=1e-6)
+        exact_float += int(np.sum(g[..., 2:4] == r[..., 2:4]))
+        total_float += g[..., 2:4].size
+    return exact_float / max(total_float, 1)
+
+
+ENCODE_CASES = [
+    # S, C, N, B, layout, corners, padding, anchor dtype
+    (608, 80, 100, 16, "uniform", "int", "tail", np.float32),
+    (608, 80, 100, 8, "uniform", "frac", "interleaved", np.float64),
+    (416, 20, 20, 8, "uniform", "int", "tail", np.float32),       # BASELINE configs[0]
+    (320, 80, 300, 4, "mosaic", "frac", "tail", np.float32),      # configs[3] stress
+    (480, 80, 300, 4, "mosaic", "int", "tail", np.float64),
+    (608, 80, 300, 4, "mosaic", "frac", "interleaved", np.float32),
+    (352, 1, 50, 3, "uniform", "frac", "tail", np.float32),       # D = 9: scalar store path
+    (608, 7, 40, 3, "mosaic", "int", "tail", np.float32),         # D = 15
+]
+
+
+@pytest.mark.parametrize("S,C,N,B,layout,corners,padding,dt", ENCODE_CASES)
+def test_encode_matches_oracle(c_oracle, S, C, N, B, layout, corners, padding, dt):
+    anchors = synth.coco_anchors(dt)
+    boxes = synth.synth_boxes(11, B, N, S, C, corners=corners, layout=layout, padding=padding)
+    ref, rstats = c_oracle.encode_targets(boxes, (S, S), anchors, C, return_stats=True)
+    got, gstats = engine.encode_targets(boxes, (S, S), anchors, C, return_stats=True)
+    frac = _assert_encode_equal(got, ref)
+    assert frac > 0.999
+    assert gstats["n_valid_boxes"] == rstats["n_valid_boxes"]
+    assert gstats["n_skipped_writes"] == rstats["n_skipped_writes"]
+    assert gstats["n_positive_cells"] == int(sum(r[..., 4].sum() for r in ref))
+
+
+def test_encode_config1_batch64(c_oracle):
+    """BASELINE configs[1]: COCO 80c 608, batch 64, up to 100 boxes."""
+    S, C, N, B = 608, 80, 100, 64
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(3, B, N, S, C)
+    ref = c_oracle.encode_targets(boxes, (S, S), anchors, C)
+    got = engine.encode_targets(boxes, (S, S), anchors, C)
+    _assert_encode_equal(got, ref)
+
+
+def test_encode_device_tensors_match_host_path():
+    import torch
+    S, C, N, B = 608, 80, 100, 8
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(5, B, N, S, C)
+    host = engine.encode_targets(boxes, (S, S), anchors, C)
+    dev = engine.encode_targets(torch.from_numpy(boxes).cuda(), (S, S), anchors, C)
+    for h, d in zip(host, dev):
+        assert d.is_cuda
+        assert np.array_equal(h, d.cpu().numpy())
+
+
+def test_encode_edge_cases(c_oracle):
+    S, C = 608, 80
+    anchors = synth.coco_anchors(np.float32)
+    # all padding, boxes on the border, degenerate and negative-extent boxes, one box
+    boxes = np.zeros((4, 6, 5), dtype=np.float32)
+    boxes[1, 0] = [0, 0, 20, 30, 3]            # top-left corner: neighbours out of bounds
+    boxes[1, 1] = [590, 590, 608, 608, 4]      # bottom-right corner
+    boxes[1, 2] = [100, 100, 100, 180, 5]      # zero width -> skipped
+    boxes[1, 3] = [200, 200, 150, 260, 6]      # negative width -> skipped (area < 0)
+    boxes[1, 4] = [300, 300, 250, 240, 7]      # both negative -> area > 0, encoded (reference quirk)
+    boxes[2, 5] = [10.5, 20.25, 300.75, 400.5, 79]
+    boxes[3, :, :] = [50, 60, 90, 120, 1]      # six identical boxes
+    ref = c_oracle.encode_targets(boxes, (S, S), anchors, C)
+    got = engine.encode_targets(boxes, (S, S), anchors, C)
+    _assert_encode_equal(got, ref)
+    # empty batch and zero boxes per image
+    out = engine.encode_targets(np.zeros((0, 5, 5), np.float32), (S, S), anchors, C)
+    assert [o.shape[0] for o in out] == [0, 0, 0]
+    out = engine.encode_targets(np.zeros((2, 0, 5), np.float32), (S, S), anchors, C)
+    assert all(not o.any() for o in out)
+
+
+def test_encode_errors():
+    S, C = 608, 80
+    anchors = synth.coco_anchors(np.float32)
+    boxes = np.zeros((1, 2, 5), dtype=np.float32)
+    boxes[0, 0] = [10, 10, 50, 50, 80]          # class id == num_classes
+    with pytest.raises(AssertionError):
+        engine.encode_targets(boxes, (S, S), anchors, C)
+    boxes[0, 0, 4] = -1
+    with pytest.raises(ValueError):
+        engine.encode_targets(boxes, (S, S), anchors, C)
+    with pytest.raises(NotImplementedError):
+        engine.encode_targets(np.zeros((1, 1, 5), np.float32), (608, 416), anchors, C)
+
+
+def test_known_answer_single_box():
+    """SURVEY 8c known-answer vectors (from the reference's own tests' inputs)."""
+    small_first = [np.array(a, dtype=np.float32) for a in
+                   (((10, 13), (16, 30), (33, 23)), ((30, 61), (62, 45), (59, 119)),
+                    ((116, 90), (156, 198), (373, 326)))]
+    boxes = np.array([[[254, 264, 354, 344, 0]]], dtype=np.float32)   # centre (304,304) 100x80
+    y = engine.encode_targets(boxes, (608, 608), small_first, 1)
+    assert not y[0].any() and not y[1].any()
+    pos = np.argwhere(y[2][0, :, :, 4] == 1)
+    assert sorted(map(tuple, pos)) == [(r, c) for r in (37, 38, 39) for c in (37, 38, 39)]
+    np.testing.assert_allclose(y[2][0, 38, 38, :4], [0, 0, -0.14842002, -0.11778303], rtol=1e-6)
+    assert y[2][0, 38, 38, 5] == 1 and y[2][0, 38, 38, 8] == 1
+    for r in (37, 38, 39):
+        for c in (37, 38, 39):
+            assert tuple(y[2][0, r, c, :2]) == (38 - c, 38 - r)
+    anchors = synth.coco_anchors(np.float32)
+    boxes = np.array([[[100, 200, 180, 260, 2]]], dtype=np.float32)
+    y = engine.encode_targets(boxes, (608, 608), anchors, 80)
+    np.testing.assert_allclose(y[1][0, 14, 8, :4], [0.75, 0.375, 0.25489223, 0.28768212], rtol=1e-6)
+    assert y[1][0, 14, 8, 5 + 1] == 1 and y[1][0, 14, 8, 5 + 3 + 2] == 1
+
+
+# ------------------------------------------------------------------------------
+# decode + NMS
+# ------------------------------------------------------------------------------
+
+def _planted(seed, B, S, C, N, anchors, c_oracle, layout="uniform"):
+    import torch
+    boxes = synth.synth_boxes(seed, B, N, S, C, layout=layout)
+    yt = c_oracle.encode_targets(boxes, (S, S), anchors, C)
+    preds = synth.planted_head_outputs([torch.from_numpy(y) for y in yt], len(anchors[0]), seed)
+    return [p.numpy() for p in preds]
+
+
+def _compare_detections(got, ref, B):
+    """Returns (#images whose keep index list is identical, #score-bit mismatches)."""
+    same = 0
+    score_bits_off = 0
+    for b in range(B):
+        k = int(ref["counts"][b])
+        if int(got["counts"][b]) == k and np.array_equal(got["index"][b, :k], ref["index"][b, :k]):
+            same += 1
+            score_bits_off += int(np.sum(got["scores"][b, :k] != ref["scores"][b, :k]))
+            assert np.array_equal(got["classes"][b, :k], ref["classes"][b, :k])
+            np.testing.assert_allclose(got["scores"][b, :k], ref["scores"][b, :k], rtol=RTOL)
+            np.testing.assert_allclose(got["boxes_xywh"][b, :k], ref["boxes_xywh"][b, :k],
+                                       rtol=RTOL, atol=1e-4)
+            # int32 xyxy: exact except values within 1e-4 px of a .5 rounding boundary
+            diff = got["boxes_xyxy"][b, :k] != ref["boxes_xyxy"][b, :k]
+            if diff.any():
+                xy = ref["boxes_xywh"][b, :k].copy()
+                xy[:, 2:] += xy[:, :2]
+                frac = np.abs((xy + 0.5) - np.round(xy + 0.5))
+                assert np.all(frac[diff] < 1e-4)
+            # padding convention
+            assert np.all(got["classes"][b, k:] == -1) and np.all(got["index"][b, k:] == -1)
+    return same, score_bits_off
+
+
+DECODE_CASES = [
+    # S, C, B, N, anchor dtype, method, per_class, confidence, thr, mixed shapes
+    (608, 80, 12, 100, np.float32, "diou", False, 0.001, 0.45, False),
+    (608, 80, 12, 100, np.float64, "diou", False, 0.001, 0.45, True),
+    (608, 80, 8, 100, np.float32, "diou", True, 0.001, 0.45, True),
+    (608, 80, 8, 60, np.float32, "standard", False, 0.1, 0.5, True),
+    (416, 20, 8, 20, np.float32, "diou", False, 0.1, 0.45, False),   # configs[0]
+    (320, 80, 4, 300, np.float32, "cluster", False, 0.001, 0.45, False),
+]
+
+
+@pytest.mark.parametrize("S,C,B,N,dt,method,per_class,conf,thr,mixed", DECODE_CASES)
+def test_decode_nms_matches_oracle(c_oracle, S, C, B, N, dt, method, per_class, conf, thr, mixed):
+    anchors = synth.coco_anchors(dt)
+    preds = _planted(21, B, S, C, N, anchors, c_oracle)
+    shapes = synth.image_shapes(4, B, mixed=mixed, square=(S, S))
+    kw = dict(max_boxes=100, confidence=conf, nms_threshold=thr, nms_method=method,
+              per_class=per_class)
+    ref = c_oracle.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+    got = engine.decode_nms(preds, shapes, (S, S), anchors, C, return_stats=True, **kw)
+    same, bits_off = _compare_detections(got, ref, B)
+    # scores are reproduced bit-for-bit (glibc expf restated on the device), so the
+    # keep sets must be identical on every image
+    assert same == B
+    assert bits_off == 0
+    assert got["stats"]["n_candidates"] == int(ref["n_candidates"].sum())
+    assert got["stats"]["n_detections"] == int(ref["counts"].sum())
+
+
+def test_decode_sigmoid_mode_and_no_rescore(c_oracle):
+    S, C, B = 608, 80, 6
+    anchors = synth.coco_anchors(np.float32)
+    preds = _planted(8, B, S, C, 80, anchors, c_oracle)
+    for use_softmax, rescore, conf in ((False, True, 0.3), (True, False, 0.5), (False, False, 0.9)):
+        kw = dict(max_boxes=100, confidence=conf, nms_threshold=0.45, nms_method="diou",
+                  use_softmax=use_softmax, rescore_confidence=rescore)
+        ref = c_oracle.decode_nms(preds, [(S, S)], (S, S), anchors, C, **kw)
+        got = engine.decode_nms(preds, (S, S), (S, S), anchors, C, **kw)
+        same, bits_off = _compare_detections(got, ref, B)
+        assert same == B and bits_off == 0
+
+
+def test_decode_dense_random_worst_case(c_oracle):
+    """Every cell is a candidate (7581 per image): global-memory sort path, early exit."""
+    S, C, B = 608, 80, 3
+    anchors = synth.coco_anchors(np.float32)
+    preds = [p.numpy() for p in synth.dense_random_head_outputs(B, S, 3, C, seed=2)]
+    kw = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method="diou")
+    ref = c_oracle.decode_nms(preds, [(480, 640)], (S, S), anchors, C, **kw)
+    got = engine.decode_nms(preds, (480, 640), (S, S), anchors, C, **kw)
+    assert int(ref["n_candidates"].min()) > 7000
+    same, bits_off = _compare_detections(got, ref, B)
+    assert same == B and bits_off == 0
+
+
+def test_decode_generic_path_odd_channels(c_oracle):
+    """D = 5+3+6 = 14 floats per cell: rows are not 16-byte multiples -> non-TMA path."""
+    S, C, B = 320, 6, 5
+    anchors = synth.coco_anchors(np.float32)
+    preds = _planted(5, B, S, C, 30, anchors, c_oracle)
+    kw = dict(max_boxes=50, confidence=0.05, nms_threshold=0.45, nms_method="diou")
+    ref = c_oracle.decode_nms(preds, [(S, S)], (S, S), anchors, C, **kw)
+    got = engine.decode_nms(preds, (S, S), (S, S), anchors, C, **kw)
+    same, bits_off = _compare_detections(got, ref, B)
+    assert same == B and bits_off == 0
+
+
+def test_decode_empty_and_threshold_edges(c_oracle):
+    S, C, B = 608, 80, 2
+    anchors = synth.coco_anchors(np.float32)
+    preds = _planted(9, B, S, C, 10, anchors, c_oracle)
+    got = engine.decode_nms(preds, (S, S), (S, S), anchors, C, confidence=1.5)
+    assert np.all(got["counts"] == 0) and np.all(got["index"] == -1)
+    got = engine.decode_nms(preds, (S, S), (S, S), anchors, C, confidence=0.0, max_boxes=7)
+    ref = c_oracle.decode_nms(preds, [(S, S)], (S, S), anchors, C, confidence=0.0, max_boxes=7)
+    assert np.array_equal(got["index"], ref["index"])
+    with pytest.raises(ValueError):
+        engine.decode_nms(preds[:2], (S, S), (S, S), anchors, C)
+    with pytest.raises(NotImplementedError):
+        engine.decode_nms(preds, (S, S), (S, S), anchors, C, nms_method="soft")
+
+
+def test_decode_device_tensors_match_host_path(c_oracle):
+    import torch
+    S, C, B = 608, 80, 6
+    anchors = synth.coco_anchors(np.float32)
+    preds = _planted(13, B, S, C, 100, anchors, c_oracle)
+    shapes = synth.image_shapes(1, B)
+    host = engine.decode_nms(preds, shapes, (S, S), anchors, C, confidence=0.001, nms_threshold=0.45)
+    dev = engine.decode_nms([torch.from_numpy(p).cuda() for p in preds], shapes, (S, S), anchors, C,
+                            confidence=0.001, nms_threshold=0.45)
+    for k in ("boxes_xywh", "boxes_xyxy", "scores", "classes", "index", "counts"):
+        assert np.array_equal(host[k], dev[k].cpu().numpy()), k
+
+
+def test_decode_dense_api(c_oracle):
+    from oracle import mgd_oracle as O
+    S, C, B = 416, 20, 2
+    anchors = synth.coco_anchors(np.float32)
+    preds = _planted(2, B, S, C, 20, anchors, c_oracle)
+    ref = O.decode_predictions(preds, anchors, (S, S), C)
+    got = engine.decode_dense(preds, anchors, C, (S, S))
+    assert got.shape == ref.shape and got.dtype == np.float64
+    np.testing.assert_allclose(got[..., 4:], ref[..., 4:], rtol=RTOL, atol=1e-30)
+    np.testing.assert_allclose(got[..., :4], ref[..., :4], rtol=RTOL, atol=1e-7)
+    assert np.array_equal(got[..., 5:].argmax(-1), ref[..., 5:].argmax(-1))
+    ref2 = O.correct_boxes(ref, (480, 640), (S, S))
+    got2 = engine.decode_dense(preds, anchors, C, (S, S), image_shapes=(480, 640))
+    np.testing.assert_allclose(got2[..., :4], ref2[..., :4], rtol=RTOL, atol=1e-4)
+
+
+def test_nms_only_api():
+    from oracle import mgd_oracle as O
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 5, 300, 3000):
+        xy = rng.uniform(0, 500, size=(n, 2))
+        wh = rng.uniform(5, 120, size=(n, 2))
+        boxes = np.concatenate([xy, wh], 1)
+        scores = rng.uniform(0, 1, size=n)
+        if n >= 5:
+            scores[3] = scores[1]                 # an exact tie
+        classes = rng.integers(0, 5, size=n)
+        for method, diou in (("diou", True), ("standard", False)):
+            for per_class in (False, True):
+                ref = O.greedy_nms(boxes, scores, 0.45, diou, classes=classes, per_class=per_class)
+                got = engine.nms(boxes, scores, classes, 0.45, method, per_class)
+                assert np.array_equal(got, ref), (n, method, per_class)
+
+
+# ------------------------------------------------------------------------------
+# full-size properties (BASELINE sizes; no element-wise oracle needed)
+# ------------------------------------------------------------------------------
+
+def test_full_size_encode_decode_round_trip(c_oracle):
+    """configs[2]-sized batch on device: encode 256 images, plant, decode+NMS; every
+    detection must sit on a positive cell of the encoder's own y_true and carry its
+    class; batch results must equal the same images processed in two halves."""
+    import torch
+    S, C, B, N = 608, 80, 256, 100
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(17, B, N, S, C)
+    d_boxes = torch.from_numpy(boxes).cuda()
+    yt = engine.encode_targets(d_boxes, (S, S), anchors, C)
+    # idempotence / determinism
+    yt2 = engine.encode_targets(d_boxes, (S, S), anchors, C)
+    assert all(torch.equal(a, b) for a, b in zip(yt, yt2))
+    # a checksum of checksums against the C oracle on the full batch
+    ref = c_oracle.encode_targets(boxes, (S, S), anchors, C)
+    for a, r in zip(yt, ref):
+        assert int(a[..., 4].sum().item()) == int(r[..., 4].sum())
+        assert np.array_equal(a[..., 4:].cpu().numpy(), r[..., 4:])
+    preds = synth.planted_head_outputs(yt, 3, seed=1)
+    kw = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method="diou")
+    det = engine.decode_nms(preds, None, (S, S), anchors, C, **kw)
+    counts = det["counts"].cpu().numpy()
+    index = det["index"].cpu().numpy()
+    classes = det["classes"].cpu().numpy()
+    scores = det["scores"].cpu().numpy()
+    assert counts.min() >= 1 and counts.max() <= 100
+    flat_obj = torch.cat([y[..., 4].reshape(B, -1) for y in yt], 1).cpu().numpy()
+    flat_cls = torch.cat([y[..., 8:].argmax(-1).reshape(B, -1) for y in yt], 1).cpu().numpy()
+    hits = 0
+    total = 0
+    for b in range(B):
+        k = counts[b]
+        assert np.all(np.diff(scores[b, :k]) <= 0)                # sorted by score
+        assert len(set(index[b, :k].tolist())) == k               # no duplicates
+        on_pos = flat_obj[b, index[b, :k]] == 1
+        hits += int(on_pos.sum())
+        total += int(k)
+        assert np.all(classes[b, :k][on_pos] == flat_cls[b, index[b, :k]][on_pos])
+    assert hits / total > 0.97
+    # batch independence: halves give the same answer
+    half = engine.decode_nms([p[:B // 2] for p in preds], None, (S, S), anchors, C, **kw)
+    assert np.array_equal(half["index"].cpu().numpy(), index[:B // 2])
+    # and the C oracle agrees on the first 32 images of the full batch
+    ref = c_oracle.decode_nms([p[:32].cpu().numpy() for p in preds], [(S, S)], (S, S), anchors, C, **kw)
+    assert np.array_equal(ref["index"], index[:32])
+    assert np.array_equal(ref["scores"], scores[:32])
