@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Headline benchmark: encode + decode/NMS images/sec on COCO-shaped synthetic data.
+
+    python bench.py --gpus N --steps K --warmup W              (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...    (reference CPU path)
+
+One *step* = one pass of the hot path over one batch: `mgd_encode_targets` on B
+images' ground-truth boxes (B x 3 grids of y_true written) followed by
+`mgd_decode_nms` on B images of raw head outputs (decode, threshold, NMS, top-k),
+both through the C ABI.  Workload (BASELINE.json configs[4], the configuration the
+metric is quoted on): COCO 80 classes, 608x608, grids 19/38/76, up to 100
+boxes/image, planted head outputs, confidence 0.001, DIoU-NMS 0.45, max 100
+detections.  Images are independent, so N GPUs shard by image with no collective
+(weak scaling: every rank processes its own batch).
+
+`value` is measured with inputs and outputs resident in HBM (CUDA events on the
+launching stream, max over ranks); `e2e` is the same step through the same C ABI
+with pinned HOST buffers, so host<->device copies are inside the timed region.
+The batch is far larger than L2 (2 x 2.67 MB per image), so no L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "encode+decode/NMS images/sec, COCO 608x608"
+UNIT = "images/s"
+S, C, A, NBOX = 608, 80, 3, 100
+CELLS = 19 * 19 + 38 * 38 + 76 * 76                    # 7581
+D = 5 + A + C                                           # 88
+BYTES_ENCODE = CELLS * D * 4 + NBOX * 5 * 4             # y_true written + boxes read
+BYTES_DECODE = CELLS * D * 4 + 100 * (32 + 16 + 8 + 4 + 4) + 4
+POST = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method="diou")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="images per rank per step")
+    ap.add_argument("--e2e-batch", type=int, default=512)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dram_traffic(kernel):
+    """Per-image DRAM bytes of a kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference, timed on host cores
+# ------------------------------------------------------------------------------
+
+def _cpu_inputs(n_images, seed=0):
+    import numpy as np
+    import torch
+    from multigriddet_b200 import synth
+    from oracle import c_oracle
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(seed, n_images, NBOX, S, C)
+    yt = c_oracle.encode_targets(boxes, (S, S), anchors, C)       # input prep, not timed
+    preds = [p.numpy() for p in
+             synth.planted_head_outputs([torch.from_numpy(y) for y in yt], A, seed)]
+    return anchors, boxes, preds
+
+
+def _cpu_worker(args):
+    boxes, preds = args
+    import numpy as np
+    from multigriddet_b200 import synth
+    from oracle import mgd_oracle as O
+    anchors = synth.coco_anchors(np.float32)
+    t0 = time.perf_counter()
+    O.encode_targets(boxes, (S, S), anchors, C)
+    t1 = time.perf_counter()
+    O.postprocess_batch(preds, np.tile(np.array([[S, S]]), (boxes.shape[0], 1)), (S, S),
+                        anchors, C, **POST)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_baseline_single(n_images=192):
+    """Oracle port (NumPy restatement of the reference), one core."""
+    _, boxes, preds = _cpu_inputs(n_images)
+    te, td = _cpu_worker((boxes, preds))
+    return {"value": n_images / (te + td), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_images} images (same COCO-608 workload): encode {n_images / te:.1f} img/s, "
+                      f"decode+DIoU-NMS {n_images / td:.1f} img/s, oracle/mgd_oracle.py on 1 host core",
+            "encode_images_per_s": n_images / te, "decode_nms_images_per_s": n_images / td}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_worker = 4
+    n_images = cores * per_worker
+    _, boxes, preds = _cpu_inputs(n_images)
+    shards = [(boxes[i * per_worker:(i + 1) * per_worker],
+               [p[i * per_worker:(i + 1) * per_worker] for p in preds]) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_worker, shards)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_worker, shards)
+        dt = time.perf_counter() - t0
+    value = n_images * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "COCO 80c 608x608 encode (<=100 boxes/img) + decode/DIoU-NMS "
+                               "(conf 0.001, thr 0.45, max 100), planted head outputs",
+                   "images_per_step": n_images},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n_images} images/step sharded over {cores} processes "
+                                   "(oracle/mgd_oracle.py: NumPy port of the reference path; the "
+                                   "reference itself is Python and cannot travel to the GPU box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------
+
+def make_device_inputs(batch, device, seed):
+    import numpy as np
+    import torch
+    from multigriddet_b200 import engine, synth
+    anchors = synth.coco_anchors(np.float32)
+    unique = min(batch, 512)
+    base = synth.synth_boxes(seed, unique, NBOX, S, C)
+    reps = (batch + unique - 1) // unique
+    boxes = np.tile(base, (reps, 1, 1))[:batch]
+    d_boxes = torch.from_numpy(boxes).to(device)
+    preds = [torch.empty((batch, g, g, D), dtype=torch.float32, device=device)
+             for g in (19, 38, 76)]
+    chunk = 256
+    for b0 in range(0, batch, chunk):
+        yt = engine.encode_targets(d_boxes[b0:b0 + chunk], (S, S), anchors, C)
+        pl = synth.planted_head_outputs(yt, A, seed * 1000 + b0)
+        for dst, src in zip(preds, pl):
+            dst[b0:b0 + chunk].copy_(src)
+        del yt, pl
+    torch.cuda.synchronize()
+    return anchors, boxes, d_boxes, preds
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from multigriddet_b200 import engine, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: multigriddet_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    anchors, boxes_np, d_boxes, preds = make_device_inputs(B, device, seed=1 + rank)
+    y_out = [torch.empty((B, g, g, D), dtype=torch.float32, device=device) for g in (19, 38, 76)]
+    d_hw = torch.from_numpy(synth.image_shapes(rank, B, mixed=True)).to(device)
+
+    def step():
+        engine.encode_targets(d_boxes, (S, S), anchors, C, out=y_out, sync=False)
+        return engine.decode_nms(preds, d_hw, (S, S), anchors, C, sync=False,
+                                 want=("boxes_xyxy", "scores", "classes"), **POST)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        engine.profile_begin()
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step()
+        ev1.record()
+        barrier()
+        prof = engine.profile_end()
+    engine.poll_status(local)
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_images = B * world * args.steps
+    value = total_images / (ms_max / 1e3)
+    n_det = int(out["counts"].sum().item())
+
+    # ---- roofline of the dominant kernel (per-launch CUDA events on the launching stream)
+    peak, peak_src = measured_peak()
+    kernels = {}
+    for kind, nbytes in (("encode_fill", BYTES_ENCODE), ("decode_compact", BYTES_DECODE)):
+        tot_ms, launches = prof[kind]
+        if launches:
+            per_launch_images = B * args.steps / launches
+            gbs = per_launch_images * nbytes / (tot_ms / launches / 1e3) / 1e9
+            kernels[kind] = {"ms_total": tot_ms, "launches": launches,
+                             "avg_launch_ms": tot_ms / launches,
+                             "images_per_launch": per_launch_images,
+                             "achieved_gbs": gbs, "frac": gbs / peak}
+    for kind in ("encode_assign", "nms"):
+        tot_ms, launches = prof[kind]
+        kernels[kind] = {"ms_total": tot_ms, "launches": launches,
+                         "avg_launch_ms": tot_ms / max(launches, 1)}
+    dominant = max(("encode_fill", "decode_compact"), key=lambda k: prof[k][0])
+    dk = kernels[dominant]
+    traffic = dram_traffic(dominant)
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": dk["frac"],
+                "traffic": traffic * dk["images_per_launch"] if traffic else None,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_image": BYTES_ENCODE if dominant == "encode_fill" else BYTES_DECODE,
+                "step_frac_of_hbm_peak": (BYTES_ENCODE + BYTES_DECODE) * B * args.steps
+                                         / (ms / 1e3) / 1e9 / peak}
+    gpu_launches = sum(v[1] for v in prof.values())
+
+    # ---- end to end through the C ABI with pinned host buffers ------------------------
+    e2e = None
+    if not args.no_e2e:
+        Be = min(args.e2e_batch, B)
+        h_boxes = torch.from_numpy(boxes_np[:Be].copy()).pin_memory()
+        h_preds = [p[:Be].cpu().pin_memory() for p in preds]
+        h_y = [torch.empty((Be, g, g, D), dtype=torch.float32).pin_memory() for g in (19, 38, 76)]
+        hw_np = d_hw[:Be].cpu().numpy()
+        np_preds = [p.numpy() for p in h_preds]
+        np_y = [y.numpy() for y in h_y]
+
+        def e2e_step():
+            engine.encode_targets(h_boxes.numpy(), (S, S), anchors, C, out=np_y)
+            return engine.decode_nms(np_preds, hw_np, (S, S), anchors, C,
+                                     want=("boxes_xyxy", "scores", "classes"), **POST)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        h2d = Be * NBOX * 5 * 4 + sum(p.numel() * 4 for p in h_preds) + Be * 8
+        d2h = sum(y.numel() * 4 for y in h_y) + Be * (100 * (16 + 8 + 4) + 4)
+        e2e = {"value": Be * world * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "batch": Be, "steps": args.e2e_steps,
+               "detections_last_step": int(res["counts"].sum())}
+        del h_preds, h_y, np_preds, np_y
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_single()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "COCO 80c 608x608 (grids 19/38/76, 88 ch): encode <=100 boxes/img "
+                                   "+ decode/DIoU-NMS (conf 0.001, thr 0.45, max 100), planted head "
+                                   "outputs, mixed letterbox shapes",
+                       "images_per_rank_per_step": B, "sharding": f"image-sharded x{world}, no collective",
+                       "l2": "inputs larger than L2 (2 x 2.67 MB/image x batch), no flush needed"},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+            "clocks": clocks.summary(), "gpu_launches": gpu_launches,
+            "detections_last_step": n_det,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

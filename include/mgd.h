@@ -182,6 +182,18 @@ MGD_API int mgd_nms(const double *boxes, const double *scores, const int *classe
  */
 MGD_API int mgd_poll_status(int device, void *stream);
 
+/*
+ * Per-kernel timing for the calling thread (observability; the reference only has
+ * wall-clock prints, evaluator.py:496-525).  Between begin and end every kernel
+ * the library launches for this thread is bracketed by CUDA events on the
+ * launching stream.  mgd_profile_end synchronises those events and returns, per
+ * kernel kind, the summed device time in ms and the number of launches:
+ *   [0] encode_assign  [1] encode_fill  [2] decode_compact  [3] nms  [4] other
+ */
+#define MGD_PROFILE_KINDS 5
+MGD_API int mgd_profile_begin(void);
+MGD_API int mgd_profile_end(double *ms, long long *launches);
+
 /* ---- DLPack zero-copy variants -------------------------------------------------
  * The tensors arrive as DLTensor* (dlpack.h ABI, v0.8+): dtype, shape, strides and
  * device are validated and the call forwards to the pointer entry point above.

@@ -64,7 +64,8 @@ _LLP = ctypes.POINTER(ctypes.c_longlong)
 
 EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targets",
            "mgd_decode_nms", "mgd_decode_dense", "mgd_nms", "mgd_poll_status",
-           "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack")
+           "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack", "mgd_profile_begin",
+           "mgd_profile_end")
 
 
 def load():
@@ -113,6 +114,9 @@ def load():
         ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_int, _LLP]
+    lib.mgd_profile_begin.restype = ctypes.c_int
+    lib.mgd_profile_end.restype = ctypes.c_int
+    lib.mgd_profile_end.argtypes = [_DP, _LLP]
     _lib = lib
     return lib
 

@@ -35,6 +35,35 @@ int fail(int code, const char* fmt, ...)
             return fail(MGD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// ---- per-kernel event timing (observability; off unless mgd_profile_begin) -------
+struct ProfSpan { int kind; cudaEvent_t t0, t1; };
+thread_local bool t_prof_on = false;
+thread_local std::vector<ProfSpan> t_prof_spans;
+thread_local cudaEvent_t t_prof_open = nullptr;
+
+}  // namespace
+
+void prof_mark_begin(int, cudaStream_t stream)
+{
+    if (!t_prof_on) return;
+    cudaEventCreate(&t_prof_open);
+    cudaEventRecord(t_prof_open, stream);
+}
+
+void prof_mark_end(int kind, cudaStream_t stream)
+{
+    if (!t_prof_on || !t_prof_open) return;
+    ProfSpan s;
+    s.kind = kind;
+    s.t0 = t_prof_open;
+    cudaEventCreate(&s.t1);
+    cudaEventRecord(s.t1, stream);
+    t_prof_spans.push_back(s);
+    t_prof_open = nullptr;
+}
+
+namespace {
+
 // ---- per-device state -----------------------------------------------------------
 struct DeviceInfo {
     bool ready = false;
@@ -326,6 +355,32 @@ int mgd_version(void) { return MGD_VERSION; }
 const char* mgd_last_error(void) { return t_error.c_str(); }
 
 int mgd_device_count(void) { return device_count_quiet(); }
+
+int mgd_profile_begin(void)
+{
+    for (ProfSpan& s : t_prof_spans) { cudaEventDestroy(s.t0); cudaEventDestroy(s.t1); }
+    t_prof_spans.clear();
+    t_prof_on = true;
+    return MGD_OK;
+}
+
+int mgd_profile_end(double* ms, long long* launches)
+{
+    t_prof_on = false;
+    for (int k = 0; k < PROF_KINDS; ++k) { if (ms) ms[k] = 0.0; if (launches) launches[k] = 0; }
+    int rc = MGD_OK;
+    for (ProfSpan& s : t_prof_spans) {
+        float t = 0.f;
+        cudaError_t e = cudaEventSynchronize(s.t1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, s.t0, s.t1);
+        if (e != cudaSuccess) rc = fail(MGD_ERR_CUDA, "profile: %s", cudaGetErrorString(e));
+        else { if (ms) ms[s.kind] += t; if (launches) launches[s.kind] += 1; }
+        cudaEventDestroy(s.t0);
+        cudaEventDestroy(s.t1);
+    }
+    t_prof_spans.clear();
+    return rc;
+}
 
 int mgd_poll_status(int device, void* stream)
 {

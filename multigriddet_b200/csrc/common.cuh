@@ -85,6 +85,12 @@ struct NmsArgs {
     unsigned long long* stats;        // [candidates, detections]
 };
 
+// per-kernel CUDA-event timing (mgd_profile_begin / mgd_profile_end)
+enum ProfKind { PROF_ENCODE_ASSIGN = 0, PROF_ENCODE_FILL = 1, PROF_DECODE_COMPACT = 2,
+                PROF_NMS = 3, PROF_OTHER = 4, PROF_KINDS = 5 };
+void prof_mark_begin(int kind, cudaStream_t stream);
+void prof_mark_end(int kind, cudaStream_t stream);
+
 // launchers (each enqueues on `stream` and returns the launch error, if any)
 cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_decode(const DecodeArgs& a, int num_sms, cudaStream_t stream);

@@ -414,6 +414,7 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
     if (grid > tiles) grid = tiles;
     if (grid < 1) grid = 1;
     cudaError_t err;
+    prof_mark_begin(PROF_DECODE_COMPACT, stream);
     if (tma_ok) {
         err = cudaFuncSetAttribute(decode_compact_kernel<true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -425,6 +426,7 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
         if (err != cudaSuccess) return err;
         decode_compact_kernel<false><<<(unsigned)grid, kThreads, smem, stream>>>(a, n_stages, stage_floats);
     }
+    prof_mark_end(PROF_DECODE_COMPACT, stream);
     return cudaGetLastError();
 }
 
@@ -443,6 +445,8 @@ cudaError_t launch_decode_dense(const DecodeArgs& a, const int* image_hw, double
     long long grid = (rows + kThreads / 8 - 1) / (kThreads / 8);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
+    prof_mark_begin(PROF_OTHER, stream);
     decode_dense_kernel<<<(unsigned)grid, kThreads, smem, stream>>>(a, image_hw, out, row_floats);
+    prof_mark_end(PROF_OTHER, stream);
     return cudaGetLastError();
 }

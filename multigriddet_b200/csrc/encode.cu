@@ -294,7 +294,9 @@ cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
     cudaError_t err = cudaFuncSetAttribute(encode_assign_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
+    prof_mark_begin(PROF_ENCODE_ASSIGN, stream);
     encode_assign_kernel<<<a.B, kAssignThreads, smem, stream>>>(a);
+    prof_mark_end(PROF_ENCODE_ASSIGN, stream);
     err = cudaGetLastError();
     if (err != cudaSuccess) return err;
 
@@ -317,7 +319,9 @@ cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
     const long long max_blocks = (long long)num_sms * (2048 / kFillThreads);   // one full wave
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
+    prof_mark_begin(PROF_ENCODE_FILL, stream);
     if (vec4) encode_fill_kernel<4><<<(unsigned)blocks, kFillThreads, 0, stream>>>(a, p);
     else      encode_fill_kernel<1><<<(unsigned)blocks, kFillThreads, 0, stream>>>(a, p);
+    prof_mark_end(PROF_ENCODE_FILL, stream);
     return cudaGetLastError();
 }

@@ -262,7 +262,9 @@ cudaError_t launch_nms(const NmsArgs& a, int, cudaStream_t stream)
     cudaError_t err = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)dyn);
     if (err != cudaSuccess) return err;
+    prof_mark_begin(PROF_NMS, stream);
     nms_kernel<<<a.B, kThreads, dyn, stream>>>(a);
+    prof_mark_end(PROF_NMS, stream);
     return cudaGetLastError();
 }
 

@@ -151,7 +151,13 @@ def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_
     M = int(max_boxes)
     stats = (ctypes.c_longlong * 4)()
     hw = None
-    if image_shapes is not None:
+    d_hw = None
+    if image_shapes is not None and _is_torch(image_shapes):
+        import torch
+        d_hw = image_shapes.to(torch.int32).contiguous()
+        if tuple(d_hw.shape) != (B, 2) or not d_hw.is_cuda:
+            raise ValueError("a tensor image_shapes must be a CUDA (B, 2) tensor")
+    elif image_shapes is not None:
         hw = np.asarray(image_shapes, dtype=np.int32).reshape(-1, 2)
         if hw.shape[0] == 1 and B != 1:
             hw = np.tile(hw, (B, 1))
@@ -169,7 +175,8 @@ def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_
         for k in want:
             out[k] = torch.empty(spec[k][0], dtype=getattr(torch, spec[k][1]), device=tp[0].device)
         out["counts"] = torch.empty((B,), dtype=torch.int32, device=tp[0].device)
-        d_hw = torch.from_numpy(hw).to(tp[0].device, non_blocking=False) if hw is not None else None
+        if d_hw is None and hw is not None:
+            d_hw = torch.from_numpy(hw).to(tp[0].device, non_blocking=False)
         addr = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else None
         rc = lib.mgd_decode_nms(
             ctypes.byref(cfg), ctypes.byref(pc), _lib.ptr_array([p.data_ptr() for p in tp]), B,
@@ -264,3 +271,19 @@ def nms(boxes, scores, classes=None, nms_threshold=0.5, nms_method="diou", per_c
                      _current_device(), None, _lib.FLAG_SYNC)
     _lib.raise_for_status(rc)
     return keep[:n_keep.value].astype(np.int64)
+
+
+PROFILE_KINDS = ("encode_assign", "encode_fill", "decode_compact", "nms", "other")
+
+
+def profile_begin():
+    """Start per-kernel CUDA-event timing of this thread's library calls."""
+    _lib.raise_for_status(_lib.load().mgd_profile_begin())
+
+
+def profile_end():
+    """Stop timing; returns {kernel kind: (total ms, launches)}."""
+    ms = (ctypes.c_double * len(PROFILE_KINDS))()
+    n = (ctypes.c_longlong * len(PROFILE_KINDS))()
+    _lib.raise_for_status(_lib.load().mgd_profile_end(ms, n))
+    return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(PROFILE_KINDS)}
