@@ -267,6 +267,7 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         d.rescore = post.rescore_confidence;
         d.confidence = post.confidence;
         d.obj_logit_min = objectness_prefilter(post);
+        d.score_lo = post.confidence > 0.0 ? (float)(post.confidence * (1.0 - 1e-3)) : -1.0f;
         CUDA_TRY(cudaMallocAsync(&d.cand, (size_t)nb * g.cells * sizeof(Cand), stream));
         CUDA_TRY(cudaMallocAsync(&d.counts, (size_t)nb * sizeof(int), stream));
         CUDA_TRY(cudaMemsetAsync(d.counts, 0, (size_t)nb * sizeof(int), stream));
@@ -274,9 +275,11 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
 
         NmsArgs n;
         memset(&n, 0, sizeof(n));
+        n.g = g;
         n.B = nb;
         n.cap = g.cells;
         n.cand = d.cand;
+        CUDA_TRY(cudaMallocAsync(&n.boxes, (size_t)nb * g.cells * sizeof(BoxD), stream));
         n.counts = d.counts;
         n.image_hw = d.image_hw;
         n.in_h = g.in_h; n.in_w = g.in_w;
@@ -302,6 +305,7 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         CUDA_TRY(launch_nms(n, num_sms, stream));
         if (n.sort_scratch) CUDA_TRY(cudaFreeAsync(n.sort_scratch, stream));
         if (n.kept_scratch) CUDA_TRY(cudaFreeAsync(n.kept_scratch, stream));
+        CUDA_TRY(cudaFreeAsync(n.boxes, stream));
         CUDA_TRY(cudaFreeAsync(d.cand, stream));
         CUDA_TRY(cudaFreeAsync(d.counts, stream));
     }
@@ -711,15 +715,15 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
         d_boxes = p; d_scores = p + 4 * (size_t)n; d_classes = classes ? q : nullptr;
         d_keep = q + n; d_nkeep = q + 2 * (size_t)n;
     }
-    Cand* cand; int* count; int* d_index; int* d_counts;
-    CUDA_TRY(cudaMallocAsync(&cand, (size_t)n * sizeof(Cand), st));
+    int* count; int* d_index; int* d_counts;
     CUDA_TRY(cudaMallocAsync(&count, 2 * sizeof(int) + (size_t)max_keep * sizeof(int), st));
     d_counts = count + 1;
     d_index = count + 2;
-    CUDA_TRY(launch_pack_candidates(d_boxes, d_scores, d_classes, n, cand, count, st));
+    CUDA_TRY(cudaMemcpyAsync(count, &n, sizeof(int), cudaMemcpyHostToDevice, st));
     NmsArgs a;
     memset(&a, 0, sizeof(a));
-    a.B = 1; a.cap = n; a.cand = cand; a.counts = count;
+    a.B = 1; a.cap = n; a.counts = count;
+    a.in_boxes = d_boxes; a.in_scores = d_scores; a.in_classes = d_classes;
     a.thr = nms_threshold; a.use_diou = nms_method == MGD_NMS_DIOU; a.per_class = per_class;
     a.max_boxes = max_keep;
     int pow2 = 2;
@@ -742,7 +746,6 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
     }
     if (a.sort_scratch) CUDA_TRY(cudaFreeAsync(a.sort_scratch, st));
     if (a.kept_scratch) CUDA_TRY(cudaFreeAsync(a.kept_scratch, st));
-    CUDA_TRY(cudaFreeAsync(cand, st));
     CUDA_TRY(cudaFreeAsync(count, st));
     if (staged) CUDA_TRY(cudaFreeAsync(staged, st));
     if (host || (flags & MGD_FLAG_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));

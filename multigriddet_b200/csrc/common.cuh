@@ -44,12 +44,17 @@ struct EncodeArgs {
 };
 
 // ---- decode / NMS ---------------------------------------------------------
+// One candidate (score >= confidence) as the decode kernel emits it: 32 bytes.
+// The box is reconstructed from the raw logits by the NMS kernel.
 struct __align__(16) Cand {
-    double x, y, w, h;   // [x_min, y_min, w, h] in original-image pixels
-    double score;        // float32-valued in the decode path (the reference's op order)
-    int index;           // flat cell index (layer, row, col); position for mgd_nms
-    int cls;
+    float score;         // float32 score in the reference's operation order
+    int index;           // flat cell index (layer, row, col)
+    float t[4];          // raw tx, ty, tw, th
+    int cls;             // argmax class
+    int anchor;          // global index of the argmax anchor
 };
+
+struct __align__(16) BoxD { double x, y, w, h; };   // [x_min, y_min, w, h], image pixels
 
 struct DecodeArgs {
     HeadGeom g;
@@ -59,18 +64,21 @@ struct DecodeArgs {
     int use_softmax, rescore;
     double confidence;
     float obj_logit_min;              // conservative prefilter on the raw objectness logit
-    // tiling
-    int rows_per_tile;
-    long long tile_first[MGD_MAX_LAYERS + 1];   // prefix sum of tiles per layer
+    float score_lo;                   // confidence * (1 - 1e-3): bound for the fast prefilters
     long long rows_in_layer[MGD_MAX_LAYERS];    // B * gh * gw
     Cand* cand;                       // (B, cells)
     int* counts;                      // (B,)
 };
 
 struct NmsArgs {
+    HeadGeom g;                       // decode mode: geometry for the box reconstruction
     int B;
     int cap;                          // candidate slots per image
-    const Cand* cand;
+    const Cand* cand;                 // decode mode: (B, cap) records; nullptr in explicit mode
+    const double* in_boxes;           // explicit mode (mgd_nms, B == 1): (n,4) xywh
+    const double* in_scores;          //   (n,)
+    const int* in_classes;            //   (n,) or nullptr
+    BoxD* boxes;                      // decode mode scratch: (B, cap) reconstructed boxes
     const int* counts;
     const int* image_hw;              // (B,2) or nullptr (then in_h, in_w)
     int in_h, in_w;
@@ -100,7 +108,5 @@ int nms_smem_capacity();
 size_t nms_kept_bytes(int max_boxes);
 cudaError_t launch_decode_dense(const DecodeArgs& a, const int* image_hw, double* out,
                                 cudaStream_t stream);
-cudaError_t launch_pack_candidates(const double* boxes, const double* scores, const int* classes,
-                                   int n, Cand* cand, int* count, cudaStream_t stream);
 cudaError_t launch_keep_from_index(const int* index, const int* counts, int max_keep, int* keep,
                                    int* n_keep, cudaStream_t stream);

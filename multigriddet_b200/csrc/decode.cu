@@ -1,34 +1,44 @@
 // Dense head decode + score threshold + candidate compaction for sm_100a.
 //
-// Replaces MultiGridDecoder.decode_predictions / correct_boxes and the threshold
-// step of handle_predictions (reference multigriddet/postprocess/
-// multigrid_decode.py:100-183, 185-235, 262-278) without ever materialising the
-// reference's (B, 7581, 85) float64 tensor.
+// Replaces MultiGridDecoder.decode_predictions and the threshold step of
+// handle_predictions (reference multigriddet/postprocess/multigrid_decode.py:
+// 100-183, 262-278) without ever materialising the reference's (B, 7581, 85)
+// float64 tensor.  Box reconstruction of the few candidates (:151-163, 185-235)
+// happens in the NMS kernel, one thread per candidate.
 //
-// decode_compact_kernel -- persistent CTAs, HBM-bound (reads cells*D*4 bytes):
-//   * the head tensor streams through shared memory in tiles of whole cell rows,
-//     moved by the TMA bulk-copy engine (cp.async.bulk + mbarrier, multi-stage
-//     ring), so no thread spends registers or issue slots on loads;
-//   * phase 1: one compare per row on the raw objectness logit.  score <=
-//     sigmoid(obj) because both softmax maxima are <= 1, so a row whose logit is
-//     below logit(confidence) minus a margin cannot become a candidate;
-//   * phase 2: the survivors (about 10% of rows on a trained head) are evaluated
-//     exactly, eight lanes per row, in the reference's float32 operation order:
-//     softmax as exp(x - max) / sum with NumPy's pairwise 8-accumulator summation
-//     order (the eight lanes ARE the eight accumulators), glibc-equivalent expf
-//     (libm_emul.h), first-maximum argmax on the probabilities, score =
-//     (obj * anchor) * class, threshold in float64 like `score >= confidence`;
-//   * candidates get their box in float64 ((xy + cell) / grid, anchor * exp(wh),
-//     letterbox correction with float32 constants) and are appended to the
-//     per-image candidate list with one atomic per candidate.
+// decode_compact_kernel -- persistent CTAs of independent warps.  A warp walks the
+// head tensor in blocks of 32 cell rows and filters them in three levels; only the
+// bytes a level needs are ever requested from HBM:
+//   1. lane per row, one 16-byte load (objectness + anchor logits): an upper bound
+//      of the score.  score <= sigmoid(obj) * max_anchor_prob because the class
+//      maximum is <= 1, so a row below confidence*(1-1e-3) can never be a candidate
+//      (fast intrinsics, relative error ~1e-6 << the 1e-3 margin).  On a trained
+//      head ~85% of the rows end here having cost 32 of their 352 bytes;
+//   2. the surviving rows are appended to the warp's pool in shared memory with
+//      one TMA bulk copy each (cp.async.bulk + mbarrier, whole 352-byte rows, pool
+//      stride padded to 23 float4 so lane-per-row 16-byte reads are conflict-free).
+//      When the pool fills, all 32 lanes evaluate the same bound including the
+//      class softmax, one row per lane;
+//   3. rows still alive are evaluated exactly, eight lanes per row, in the
+//      reference's float32 operation order: softmax as exp(x - max) / sum with
+//      NumPy's pairwise 8-accumulator summation (the eight lanes ARE the eight
+//      accumulators), glibc-equivalent expf (libm_emul.h), first-maximum argmax on
+//      the probabilities, score = (obj * anchor) * class, threshold in float64 like
+//      `score >= confidence`.  Candidates are appended to the per-image list (one
+//      atomic each) as 32-byte records: score, cell, class, anchor, raw box logits.
+// Algorithmic bytes (what the reference reads) are cells*D*4 per image; the DRAM
+// traffic of this kernel is lower and data-dependent.  No CTA barrier, no
+// inter-warp dependency.
 #include <math.h>
 #include "common.cuh"
-#include "libm_emul.h"
+#include "decode_math.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kMaxStages = 8;
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kDenseThreads = 256;
+constexpr int kPoolRows = 32;
 
 // ---- PTX: mbarrier + TMA bulk copy -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -48,6 +58,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                  ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
 {
     asm volatile(
@@ -66,253 +85,240 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     } while (!done);
 }
 
-// ---- NumPy float32 add.reduce order, one octet of lanes = the 8 accumulators --
-// x: shared-memory array of n floats; j = lane within the octet (0..7).
-__device__ float np_sum_octet(const float* x, int n, int j)
-{
-    if (n < 8) {
-        float res = 0.f;
-        for (int i = 0; i < n; ++i) res = __fadd_rn(res, x[i]);
-        return res;
-    }
-    if (n <= 128) {
-        float r = x[j];
-        const int body = n - (n & 7);
-        for (int i = 8 + j; i < body; i += 8) r = __fadd_rn(r, x[i]);
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));   // (r0+r1) (r2+r3) ...
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));   // ((r0+r1)+(r2+r3)) ...
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-        for (int i = body; i < n; ++i) r = __fadd_rn(r, x[i]);
-        return r;
-    }
-    int n2 = n / 2;
-    n2 -= n2 & 7;
-    const float lo = np_sum_octet(x, n2, j);
-    const float hi = np_sum_octet(x + n2, n - n2, j);
-    return __fadd_rn(lo, hi);
-}
+struct WarpPool {
+    float* rows;          // [kPoolRows][stride] floats
+    int* cell;            // [kPoolRows] row index within the layer
+    float* bound;         // [kPoolRows] level-1 bound
+    uint64_t* bar;        // bulk-copy completion
+    int stride;           // floats per pool row (16-byte multiple when TMA is used)
+};
 
-// Max probability and its first index over x[0..n): softmax (scipy: exp(x-max)/sum)
-// or element-wise expit.  Overwrites x with the exponentials / probabilities.
-// All 32 lanes of the warp must call this together (full-mask shuffles).
-__device__ void octet_probs(float* x, int n, int j, bool use_softmax, const uint64_t* tab,
-                            float& pmax, int& arg)
+// Level 2 + 3 on the `count` rows currently in the warp's pool (all of one layer).
+// Called by all 32 lanes.
+template <bool kFast>
+__device__ __noinline__ void flush_pool(const DecodeArgs& a, const WarpPool& pool, int count,
+                                        int layer, const uint64_t* s_tab)
 {
-    if (use_softmax) {
-        float m = -INFINITY;
-        for (int i = j; i < n; i += 8) m = fmaxf(m, x[i]);
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-        for (int i = j; i < n; i += 8) x[i] = mgd_expf_tab(__fsub_rn(x[i], m), tab);
+    const HeadGeom& g = a.g;
+    const int lane = threadIdx.x & 31;
+    const int A = g.na[layer], C = g.C;
+    const bool softmax = a.use_softmax != 0;
+    const bool rescore = a.rescore != 0;
+
+    // ---- level 2: lane per pooled row, bound including the class maximum --------------
+    bool pass = lane < count;
+    if (pass && rescore) {
+        const float* c = pool.rows + lane * pool.stride + 5 + A;
+        float mc = -INFINITY, sum = 0.f;
+        if (kFast) {                            // A == 3: classes start at float 8, C % 4 == 0
+            const float4* c4 = reinterpret_cast<const float4*>(c);
+            #pragma unroll 4
+            for (int i = 0; i < C / 4; ++i) {
+                const float4 v = c4[i];
+                mc = fmaxf(fmaxf(mc, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                if (softmax) sum += (__expf(v.x) + __expf(v.y)) + (__expf(v.z) + __expf(v.w));
+            }
+        } else {
+            for (int i = 0; i < C; ++i) {
+                mc = fmaxf(mc, c[i]);
+                if (softmax) sum += __expf(c[i]);
+            }
+        }
+        float ub;
+        if (softmax) {
+            // max softmax = exp(mc) / sum; no max subtraction in the fast bound: if it
+            // overflows (logits > 88) the row is simply kept for the exact evaluation
+            ub = __fdividef(pool.bound[lane] * __expf(mc), sum);
+            if (!(sum < 3.0e38f) || !(ub == ub)) ub = 3.0e38f;
+        } else {
+            ub = pool.bound[lane] * fast_sigmoid(mc);
+        }
+        pass = ub >= a.score_lo;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, pass);
+
+    // ---- level 3: exact evaluation, octet per row --------------------------------------
+    const int j = lane & 7;
+    const int oct = lane >> 3;
+    const unsigned omask = 0xffu << (oct * 8);
+    const int cells_l = g.gh[layer] * g.gw[layer];
+    while (todo) {
+        const unsigned pos = nth_set_bit(todo, oct);
+        if (pos < 32u) {
+            float* x = pool.rows + pos * pool.stride;
+            float pa, pc; int ka, kc;
+            octet_probs(x + 5, A, j, omask, softmax, s_tab, pa, ka);
+            octet_probs(x + 5 + A, C, j, omask, softmax, s_tab, pc, kc);
+            float score = mgd_expitf_tab(x[4], s_tab);                       // :147
+            if (rescore) score = __fmul_rn(__fmul_rn(score, pa), pc);        // :170
+            if (j == 0 && (double)score >= a.confidence) {                   // :271
+                const int grow = pool.cell[pos];
+                const int b = grow / cells_l;
+                const int cell = grow - b * cells_l;
+                Cand cd;
+                cd.score = score;
+                cd.index = g.cell_off[layer] + cell;
+                cd.t[0] = x[0]; cd.t[1] = x[1]; cd.t[2] = x[2]; cd.t[3] = x[3];
+                cd.cls = kc;
+                cd.anchor = g.anchor_first[layer] + ka;
+                const int slot = atomicAdd(a.counts + b, 1);
+                a.cand[(size_t)b * g.cells + slot] = cd;
+            }
+        }
         __syncwarp();
-        const float s = np_sum_octet(x, n, j);
-        pmax = __fdiv_rn(1.0f, s);              // the maximum's exponential is exactly 1
-        int first = INT_MAX;
-        for (int i = j; i < n; i += 8) {
-            const float e = x[i];
-            if (e >= 0.99999f && __fdiv_rn(e, s) == pmax) { first = i; break; }
-        }
-        first = min(first, __shfl_xor_sync(0xffffffffu, first, 1));
-        first = min(first, __shfl_xor_sync(0xffffffffu, first, 2));
-        first = min(first, __shfl_xor_sync(0xffffffffu, first, 4));
-        arg = first;
-    } else {
-        float best = -INFINITY;
-        int first = INT_MAX;
-        for (int i = j; i < n; i += 8) {
-            const float q = mgd_expitf_tab(x[i], tab);
-            x[i] = q;
-            if (q > best) { best = q; first = i; }
-        }
         #pragma unroll
-        for (int d = 1; d <= 4; d <<= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, d);
-            const int oi = __shfl_xor_sync(0xffffffffu, first, d);
-            if (ob > best || (ob == best && oi < first)) { best = ob; first = oi; }
-        }
-        pmax = best;
-        arg = first;
+        for (int q = 0; q < 4; ++q) todo &= todo - 1;
     }
+    // pool rows were rewritten in place through the generic proxy; order those writes
+    // before the bulk copies (async proxy) that will refill the slots
+    if (kFast) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
 }
 
-struct Letterbox { float off_w, off_h, sc_w, sc_h, img_w, img_h; };
-
-// multigrid_decode.py:205-216 in float32
-__device__ __forceinline__ Letterbox letterbox_consts(int in_h, int in_w, int ih_i, int iw_i)
-{
-    const float mh = (float)in_h, mw = (float)in_w, ih = (float)ih_i, iw = (float)iw_i;
-    const float ratio = fminf(__fdiv_rn(mh, ih), __fdiv_rn(mw, iw));
-    const float nh = rintf(__fmul_rn(ih, ratio)), nw = rintf(__fmul_rn(iw, ratio));
-    Letterbox lb;
-    lb.off_h = __fdiv_rn(__fdiv_rn(__fsub_rn(mh, nh), 2.0f), mh);
-    lb.off_w = __fdiv_rn(__fdiv_rn(__fsub_rn(mw, nw), 2.0f), mw);
-    lb.sc_h = __fdiv_rn(mh, nh);
-    lb.sc_w = __fdiv_rn(mw, nw);
-    lb.img_w = iw;
-    lb.img_h = ih;
-    return lb;
-}
-
-// Box of one cell in float64: multigrid_decode.py:151-163 then :219-228.
-// x: the raw row (channels 0..3 untouched), ga: global anchor index.
-__device__ __forceinline__ void decode_box(const HeadGeom& g, const float* x, int layer, int ga,
-                                           int r, int c, const Letterbox* lb,
-                                           const uint64_t* tab, double out[4])
-{
-    const float ux = __fmul_rn(0.15f, x[0]), uy = __fmul_rn(0.15f, x[1]);
-    // np.tanh float32: correctly rounded here (libm tanhf is within 2 ulp of this)
-    const float ax = __fadd_rn((float)tanh((double)ux), mgd_expitf_tab(ux, tab));
-    const float ay = __fadd_rn((float)tanh((double)uy), mgd_expitf_tab(uy, tab));
-    double bx = __ddiv_rn(__dadd_rn((double)ax, (double)c), (double)g.gh[layer]);   // :154-155
-    double by = __ddiv_rn(__dadd_rn((double)ay, (double)r), (double)g.gw[layer]);
-    double bw, bh;
-    const float ew = mgd_expf_tab(x[2], tab), eh = mgd_expf_tab(x[3], tab);
-    if (!g.anchors_f64) {
-        const float w32 = __fmul_rn(g.anc32[ga][0], ew), h32 = __fmul_rn(g.anc32[ga][1], eh);
-        bw = (double)(float)__ddiv_rn((double)w32, (double)g.in_h);    // :163 in-place on f32
-        bh = (double)(float)__ddiv_rn((double)h32, (double)g.in_w);
-    } else {
-        bw = __ddiv_rn(__dmul_rn(g.anc64[ga][0], (double)ew), (double)g.in_h);
-        bh = __ddiv_rn(__dmul_rn(g.anc64[ga][1], (double)eh), (double)g.in_w);
-    }
-    if (lb) {
-        bx = __dmul_rn(__dsub_rn(bx, (double)lb->off_w), (double)lb->sc_w);        // :219
-        by = __dmul_rn(__dsub_rn(by, (double)lb->off_h), (double)lb->sc_h);
-        bw = __dmul_rn(bw, (double)lb->sc_w);                                      // :220
-        bh = __dmul_rn(bh, (double)lb->sc_h);
-        bx = __dsub_rn(bx, __ddiv_rn(bw, 2.0));                                    // :223
-        by = __dsub_rn(by, __ddiv_rn(bh, 2.0));
-        bx = __dmul_rn(bx, (double)lb->img_w);                                     // :227-228
-        by = __dmul_rn(by, (double)lb->img_h);
-        bw = __dmul_rn(bw, (double)lb->img_w);
-        bh = __dmul_rn(bh, (double)lb->img_h);
-    }
-    out[0] = bx; out[1] = by; out[2] = bw; out[3] = bh;
-}
-
-// Dynamic shared memory layout: [stages][rows_per_tile * Dmax] floats, then the
-// survivor list.  kUseTma=false copies tiles with ordinary loads (any D / alignment).
-template <bool kUseTma>
+// kFast: every layer has A == 3 anchors, D % 4 == 0 and 16-byte aligned tensors:
+// 16-byte loads for level 1, TMA bulk copies into the pool, float4 pool reads.
+template <bool kFast>
 __global__ void __launch_bounds__(kThreads)
-decode_compact_kernel(const __grid_constant__ DecodeArgs a, int n_stages, int stage_floats)
+decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar[kMaxStages];
+    __shared__ uint64_t s_bar[kWarpsPerCta];
     __shared__ uint64_t s_tab[MGD_EXP2F_N];
-    __shared__ int s_count[2];
+    __shared__ int s_cell[kWarpsPerCta][kPoolRows];
+    __shared__ float s_bound[kWarpsPerCta][kPoolRows];
 
     const HeadGeom& g = a.g;
-    float* stage0 = reinterpret_cast<float*>(smem_raw);
-    int* s_list = reinterpret_cast<int*>(smem_raw + (size_t)n_stages * stage_floats * sizeof(float));
-    float* s_dummy = reinterpret_cast<float*>(s_list + a.rows_per_tile);
-
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int j = tid & 7;                    // lane within the octet
-    const int oct = lane >> 3;                // octet within the warp
     const int warp = tid >> 5;
-    const long long total_tiles = a.tile_first[g.L];
+    WarpPool pool;
+    pool.rows = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kPoolRows * pool_stride;
+    pool.cell = s_cell[warp];
+    pool.bound = s_bound[warp];
+    pool.bar = &s_bar[warp];
+    pool.stride = pool_stride;
 
     if (tid < MGD_EXP2F_N) s_tab[tid] = mgd_exp2f_tab[tid];
-    for (int i = tid; i < stage_floats / a.rows_per_tile; i += kThreads) s_dummy[i] = 0.f;
-    if (tid == 0) {
-        s_count[0] = 0; s_count[1] = 0;
-        if (kUseTma) {
-            for (int s = 0; s < n_stages; ++s) mbar_init(&full_bar[s], 1);
-            fence_mbar_init();
-        }
+    if (kFast && lane == 0) {
+        mbar_init(pool.bar, 1);
+        fence_mbar_init();
     }
     __syncthreads();
 
-    auto tile_geom = [&](long long tile, int& layer, long long& row0, int& rows) {
-        int l = 0;
-        while (l + 1 < g.L && tile >= a.tile_first[l + 1]) ++l;
-        layer = l;
-        row0 = (tile - a.tile_first[l]) * a.rows_per_tile;
-        const long long left = a.rows_in_layer[l] - row0;
-        rows = (int)(left < a.rows_per_tile ? left : a.rows_per_tile);
-    };
-    auto issue = [&](long long seq) {          // thread 0 only
-        const long long tile = blockIdx.x + seq * gridDim.x;
-        if (tile >= total_tiles) return;
-        int layer, rows; long long row0;
-        tile_geom(tile, layer, row0, rows);
-        const int s = (int)(seq % n_stages);
-        const uint32_t bytes = (uint32_t)rows * g.D[layer] * sizeof(float);
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        bulk_g2s(stage0 + (size_t)s * stage_floats, a.pred[layer] + row0 * g.D[layer], bytes,
-                 &full_bar[s]);
-    };
-    if (kUseTma && tid == 0)
-        for (int s = 0; s < n_stages; ++s) issue(s);
+    const int gwarp = blockIdx.x * kWarpsPerCta + warp;
+    const int n_warps = gridDim.x * kWarpsPerCta;
+    const bool softmax = a.use_softmax != 0;
+    const bool rescore = a.rescore != 0;
+    uint32_t bar_phase = 0;
 
-    for (long long seq = 0;; ++seq) {
-        const long long tile = blockIdx.x + seq * gridDim.x;
-        if (tile >= total_tiles) break;
-        int layer, rows; long long row0;
-        tile_geom(tile, layer, row0, rows);
+    for (int layer = 0; layer < g.L; ++layer) {
         const int D = g.D[layer];
         const int A = g.na[layer];
-        const int s = (int)(seq % n_stages);
-        float* buf = stage0 + (size_t)s * stage_floats;
-        int* cnt = &s_count[seq & 1];
+        const int n_rows = (int)a.rows_in_layer[layer];
+        const int n_blocks = (n_rows + 31) >> 5;
+        const float* base = a.pred[layer];
+        int count = 0;                              // rows in the pool (all of this layer)
 
-        if (kUseTma) {
-            mbar_wait(&full_bar[s], (uint32_t)((seq / n_stages) & 1));
-        } else {
-            const float* src = a.pred[layer] + row0 * D;
-            for (int i = tid; i < rows * D; i += kThreads) buf[i] = __ldg(src + i);
-            __syncthreads();
-        }
-
-        // ---- phase 1: objectness prefilter, one compare per row ----------------
-        for (int r = tid; r < rows; r += kThreads)
-            if (buf[r * D + 4] >= a.obj_logit_min) s_list[atomicAdd(cnt, 1)] = r;
-        __syncthreads();
-        const int n_surv = *cnt;
-        if (tid == 0) s_count[(seq + 1) & 1] = 0;
-
-        // ---- phase 2: exact evaluation, one octet of lanes per surviving row ---
-        for (int base = warp * 4; base < n_surv; base += (kThreads / 32) * 4) {
-            const int slot = base + oct;
-            const bool live = slot < n_surv;
-            const int r = live ? s_list[slot] : 0;
-            // Octets without a row still run the (full-mask) shuffles below; they
-            // work on a scratch row so they never touch a row another octet rewrites.
-            float* x = live ? buf + r * D : s_dummy;
-            float pa, pc; int ka, kc;
-            octet_probs(x + 5, A, j, a.use_softmax != 0, s_tab, pa, ka);
-            octet_probs(x + 5 + A, g.C, j, a.use_softmax != 0, s_tab, pc, kc);
-            float score = mgd_expitf_tab(x[4], s_tab);                       // :147
-            if (a.rescore) score = __fmul_rn(__fmul_rn(score, pa), pc);      // :170
-            if (live && j == 0 && (double)score >= a.confidence) {           // :271
-                const long long grow = row0 + r;
-                const int cells_l = g.gh[layer] * g.gw[layer];
-                const int b = (int)(grow / cells_l);
-                const int cell = (int)(grow - (long long)b * cells_l);
-                const int rr = cell / g.gw[layer], cc = cell - rr * g.gw[layer];
-                const int ih = a.image_hw ? a.image_hw[2 * b] : g.in_h;
-                const int iw = a.image_hw ? a.image_hw[2 * b + 1] : g.in_w;
-                const Letterbox lb = letterbox_consts(g.in_h, g.in_w, ih, iw);
-                double box[4];
-                decode_box(g, x, layer, g.anchor_first[layer] + ka, rr, cc, &lb, s_tab, box);
-                Cand cd;
-                cd.x = box[0]; cd.y = box[1]; cd.w = box[2]; cd.h = box[3];
-                cd.score = (double)score;
-                cd.index = g.cell_off[layer] + cell;
-                cd.cls = kc;
-                const int pos = atomicAdd(a.counts + b, 1);
-                a.cand[(size_t)b * g.cells + pos] = cd;
+        // level-1 inputs of a block: [obj, anchor logits]; prefetched one block ahead
+        auto load_head = [&](int blk, float4& q) {
+            const int row = blk * 32 + lane;
+            q = make_float4(NAN, 0.f, 0.f, 0.f);          // NaN never passes a >= test
+            if (blk < n_blocks && row < n_rows) {
+                if (kFast) q = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * D + 4));
+                else q.x = __ldg(base + (size_t)row * D + 4);
             }
+        };
+        float4 q_next;
+        load_head(gwarp, q_next);
+        for (int blk = gwarp; blk < n_blocks; blk += n_warps) {
+            const float4 q = q_next;
+            load_head(blk + n_warps, q_next);
+            const int row = blk * 32 + lane;
+
+            // ---- level 1: lane per row ---------------------------------------------------
+            float bound = 0.f;
+            bool pass = false;
+            if (q.x >= a.obj_logit_min) {           // rows beyond the layer carry NaN
+                bound = fast_sigmoid(q.x);
+                if (rescore) {
+                    if (kFast) {
+                        const float ma = fmaxf(q.y, fmaxf(q.z, q.w));
+                        if (softmax)
+                            bound = __fdividef(bound, (__expf(q.y - ma) + __expf(q.z - ma)) + __expf(q.w - ma));
+                        else
+                            bound *= fast_sigmoid(ma);
+                    } else {
+                        const float* an = base + (size_t)row * D + 5;
+                        float ma = __ldg(an);
+                        for (int i = 1; i < A; ++i) ma = fmaxf(ma, __ldg(an + i));
+                        if (softmax) {
+                            float sa = 0.f;
+                            for (int i = 0; i < A; ++i) sa += __expf(__ldg(an + i) - ma);
+                            bound = __fdividef(bound, sa);
+                        } else {
+                            bound *= fast_sigmoid(ma);
+                        }
+                    }
+                }
+                pass = bound >= a.score_lo;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, pass);
+            if (!todo) continue;
+
+            // ---- append the survivors' rows to the pool ------------------------------------
+            int n_new = __popc(todo);
+            if (count + n_new > kPoolRows) {
+                if (kFast) {
+                    if (lane == 0) mbar_arrive(pool.bar);
+                    mbar_wait(pool.bar, bar_phase);
+                    bar_phase ^= 1u;
+                }
+                flush_pool<kFast>(a, pool, count, layer, s_tab);
+                count = 0;
+            }
+            // lane i of the survivors (in row order) takes pool slot count + rank
+            const int rank = __popc(todo & ((1u << lane) - 1u));
+            if (pass) {
+                pool.cell[count + rank] = row;
+                pool.bound[count + rank] = bound;
+            }
+            if (kFast) {
+                // one bulk copy per surviving row, issued by the row's own lane; the copies
+                // stay in flight while the warp moves on -- they are awaited at the flush
+                if (lane == 0) mbar_expect_tx(pool.bar, (uint32_t)n_new * D * sizeof(float));
+                __syncwarp();
+                if (pass)
+                    bulk_g2s(pool.rows + (size_t)(count + rank) * pool.stride,
+                             base + (size_t)row * D, (uint32_t)D * sizeof(float), pool.bar);
+            } else {
+                unsigned rest = todo;
+                int slot = count;
+                while (rest) {
+                    const int src_lane = __ffs((int)rest) - 1;
+                    rest &= rest - 1;
+                    const float* src = base + ((size_t)blk * 32 + src_lane) * D;
+                    float* dst = pool.rows + (size_t)slot * pool.stride;
+                    for (int i = lane; i < D; i += 32) dst[i] = __ldg(src + i);
+                    ++slot;
+                }
+                __syncwarp();
+            }
+            count += n_new;
         }
-        __syncthreads();                       // stage s and the list are free again
-        if (kUseTma && tid == 0) issue(seq + n_stages);
+        if (count) {
+            if (kFast) {
+                if (lane == 0) mbar_arrive(pool.bar);
+                mbar_wait(pool.bar, bar_phase);
+                bar_phase ^= 1u;
+            }
+            flush_pool<kFast>(a, pool, count, layer, s_tab);
+        }
+        __syncwarp();
     }
 }
 
 // ---- dense decode (decode_predictions API), one octet per row, not a hot path --
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kDenseThreads)
 decode_dense_kernel(const __grid_constant__ DecodeArgs a, const int* image_hw, double* out,
                     int row_floats)
 {
@@ -320,15 +326,16 @@ decode_dense_kernel(const __grid_constant__ DecodeArgs a, const int* image_hw, d
     __shared__ uint64_t s_tab[MGD_EXP2F_N];
     const HeadGeom& g = a.g;
     const int tid = threadIdx.x, j = tid & 7;
+    const unsigned omask = 0xffu << (((tid & 31) >> 3) * 8);
     float* x = reinterpret_cast<float*>(smem_raw) + (size_t)(tid >> 3) * row_floats;
     if (tid < MGD_EXP2F_N) s_tab[tid] = mgd_exp2f_tab[tid];
     __syncthreads();
     const long long total_rows = (long long)a.B * g.cells;
-    const long long octs = (long long)gridDim.x * (kThreads / 8);
+    const long long octs = (long long)gridDim.x * (kDenseThreads / 8);
     // uniform trip count per warp: every lane iterates while ANY octet of the grid might
     const long long iters = (total_rows + octs - 1) / octs;
     for (long long it = 0; it < iters; ++it) {
-        long long q = it * octs + (long long)blockIdx.x * (kThreads / 8) + (tid >> 3);
+        long long q = it * octs + (long long)blockIdx.x * (kDenseThreads / 8) + (tid >> 3);
         const bool live = q < total_rows;
         if (!live) q = total_rows - 1;
         const int b = (int)(q / g.cells);
@@ -339,33 +346,35 @@ decode_dense_kernel(const __grid_constant__ DecodeArgs a, const int* image_hw, d
         const int D = g.D[layer], A = g.na[layer];
         const float* src = a.pred[layer] + ((size_t)b * g.gh[layer] * g.gw[layer] + cell) * D;
         for (int i = j; i < D; i += 8) x[i] = __ldg(src + i);
-        __syncwarp();
+        __syncwarp(omask);
         float pa, pc; int ka, kc;
-        octet_probs(x + 5, A, j, a.use_softmax != 0, s_tab, pa, ka);
-        octet_probs(x + 5 + A, g.C, j, a.use_softmax != 0, s_tab, pc, kc);
-        __syncwarp();
+        octet_probs(x + 5, A, j, omask, a.use_softmax != 0, s_tab, pa, ka);
+        octet_probs(x + 5 + A, g.C, j, omask, a.use_softmax != 0, s_tab, pc, kc);
+        __syncwarp(omask);
         float score = mgd_expitf_tab(x[4], s_tab);
         if (a.rescore) score = __fmul_rn(__fmul_rn(score, pa), pc);
         const int rr = cell / g.gw[layer], cc = cell - rr * g.gw[layer];
         double box[4];
         Letterbox lb;
         if (image_hw) lb = letterbox_consts(g.in_h, g.in_w, image_hw[2 * b], image_hw[2 * b + 1]);
-        decode_box(g, x, layer, g.anchor_first[layer] + ka, rr, cc, image_hw ? &lb : nullptr,
-                   s_tab, box);
+        decode_axis_of(g, x, layer, g.anchor_first[layer] + ka, rr, cc, image_hw ? &lb : nullptr, 0,
+                       s_tab, box[0], box[2]);
+        decode_axis_of(g, x, layer, g.anchor_first[layer] + ka, rr, cc, image_hw ? &lb : nullptr, 1,
+                       s_tab, box[1], box[3]);
         if (live) {
             double* o = out + (size_t)q * (5 + g.C);
             if (j < 4) o[j] = box[j];
             if (j == 4) o[4] = (double)score;
             float s = 1.0f;
-            if (a.use_softmax) s = np_sum_octet(x + 5 + A, g.C, j);
+            if (a.use_softmax) s = np_sum_octet(x + 5 + A, g.C, j, omask);
             for (int i = j; i < g.C; i += 8) {
                 const float e = x[5 + A + i];
                 o[5 + i] = (double)(a.use_softmax ? __fdiv_rn(e, s) : e);
             }
         } else if (a.use_softmax) {
-            (void)np_sum_octet(x + 5 + A, g.C, j);
+            (void)np_sum_octet(x + 5 + A, g.C, j, omask);
         }
-        __syncwarp();
+        __syncwarp(omask);
     }
 }
 
@@ -376,55 +385,44 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
     DecodeArgs a = a_in;
     const HeadGeom& g = a.g;
     int dmax = 0;
-    bool tma_ok = true;
+    bool fast = true;
     for (int l = 0; l < g.L; ++l) {
         dmax = g.D[l] > dmax ? g.D[l] : dmax;
-        tma_ok = tma_ok && (g.D[l] % 4 == 0) &&
-                 ((reinterpret_cast<uintptr_t>(a.pred[l]) & 15) == 0);
-    }
-    // tile = whole rows; a stage holds up to rows_per_tile rows of the widest layer
-    static int env_rows = -1, env_stages = -1, env_ctas = -1;
-    if (env_rows < 0) {
-        const char* e;
-        env_rows = (e = getenv("MGD_DECODE_TILE_ROWS")) ? atoi(e) : 0;
-        env_stages = (e = getenv("MGD_DECODE_STAGES")) ? atoi(e) : 0;
-        env_ctas = (e = getenv("MGD_DECODE_CTAS_PER_SM")) ? atoi(e) : 0;
-    }
-    int ctas_per_sm = env_ctas > 0 ? env_ctas : 2;
-    int n_stages = env_stages > 0 ? env_stages : 3;
-    if (n_stages > kMaxStages) n_stages = kMaxStages;
-    const size_t budget = (size_t)(220 * 1024) / ctas_per_sm - 2048;
-    int rows = env_rows > 0 ? env_rows : 64;
-    while (rows > 8 && (size_t)n_stages * rows * dmax * 4 + (size_t)(rows + dmax + 32) * 4 > budget) rows /= 2;
-    if ((size_t)n_stages * rows * dmax * 4 + (size_t)(rows + dmax + 32) * 4 > 220 * 1024) return cudaErrorInvalidValue;
-    if (!tma_ok) n_stages = 1;
-    a.rows_per_tile = rows;
-    long long tiles = 0;
-    for (int l = 0; l < g.L; ++l) {
+        fast = fast && g.na[l] == 3 && (g.D[l] % 4 == 0) &&
+               ((reinterpret_cast<uintptr_t>(a.pred[l]) & 15) == 0);
         a.rows_in_layer[l] = (long long)a.B * g.gh[l] * g.gw[l];
-        a.tile_first[l] = tiles;
-        tiles += (a.rows_in_layer[l] + rows - 1) / rows;
+        if (a.rows_in_layer[l] >= 0x7fffffffll - 64) return cudaErrorInvalidValue;
     }
-    a.tile_first[g.L] = tiles;
-    // rows is a power of two >= 8 here, so every stage stays 32-byte aligned;
-    // stage_floats / rows == dmax is the scratch-row length the kernel derives
-    const int stage_floats = rows * dmax;
-    const size_t smem = (size_t)n_stages * stage_floats * 4 + (size_t)(rows + dmax + 32) * 4;
+    // pool row stride: an odd number of float4 (fast path) / an odd number of floats
+    // (generic path) so that lane-per-row reads hit distinct banks
+    int stride = fast ? (dmax / 4 | 1) * 4 : (dmax | 1);
+    if (fast && stride < dmax) stride += 8;
+    const size_t smem = (size_t)kWarpsPerCta * kPoolRows * stride * sizeof(float);
+    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    static int env_ctas = -1;
+    if (env_ctas < 0) { const char* e = getenv("MGD_DECODE_CTAS_PER_SM"); env_ctas = e ? atoi(e) : 0; }
+    int ctas_per_sm = (int)((224 * 1024) / (smem + 2048));
+    if (ctas_per_sm > 2048 / kThreads) ctas_per_sm = 2048 / kThreads;
+    if (env_ctas > 0 && env_ctas < ctas_per_sm) ctas_per_sm = env_ctas;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    long long blocks = 0;
+    for (int l = 0; l < g.L; ++l) blocks += (a.rows_in_layer[l] + 31) / 32;
     long long grid = (long long)num_sms * ctas_per_sm;
-    if (grid > tiles) grid = tiles;
+    const long long needed = (blocks + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid > needed) grid = needed;
     if (grid < 1) grid = 1;
     cudaError_t err;
     prof_mark_begin(PROF_DECODE_COMPACT, stream);
-    if (tma_ok) {
+    if (fast) {
         err = cudaFuncSetAttribute(decode_compact_kernel<true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        decode_compact_kernel<true><<<(unsigned)grid, kThreads, smem, stream>>>(a, n_stages, stage_floats);
+        decode_compact_kernel<true><<<(unsigned)grid, kThreads, smem, stream>>>(a, stride);
     } else {
         err = cudaFuncSetAttribute(decode_compact_kernel<false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        decode_compact_kernel<false><<<(unsigned)grid, kThreads, smem, stream>>>(a, n_stages, stage_floats);
+        decode_compact_kernel<false><<<(unsigned)grid, kThreads, smem, stream>>>(a, stride);
     }
     prof_mark_end(PROF_DECODE_COMPACT, stream);
     return cudaGetLastError();
@@ -437,16 +435,16 @@ cudaError_t launch_decode_dense(const DecodeArgs& a, const int* image_hw, double
     int dmax = 0;
     for (int l = 0; l < g.L; ++l) dmax = g.D[l] > dmax ? g.D[l] : dmax;
     const int row_floats = (dmax + 3) & ~3;
-    const size_t smem = (size_t)(kThreads / 8) * row_floats * 4;
+    const size_t smem = (size_t)(kDenseThreads / 8) * row_floats * 4;
     cudaError_t err = cudaFuncSetAttribute(decode_dense_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     const long long rows = (long long)a.B * g.cells;
-    long long grid = (rows + kThreads / 8 - 1) / (kThreads / 8);
+    long long grid = (rows + kDenseThreads / 8 - 1) / (kDenseThreads / 8);
     if (grid > 148 * 8) grid = 148 * 8;
     if (grid < 1) grid = 1;
     prof_mark_begin(PROF_OTHER, stream);
-    decode_dense_kernel<<<(unsigned)grid, kThreads, smem, stream>>>(a, image_hw, out, row_floats);
+    decode_dense_kernel<<<(unsigned)grid, kDenseThreads, smem, stream>>>(a, image_hw, out, row_floats);
     prof_mark_end(PROF_OTHER, stream);
     return cudaGetLastError();
 }

@@ -17,8 +17,12 @@
 //
 //   encode_fill_kernel    grid-wide streaming writer.  Every y_true row
 //       (5+A+C floats) is produced exactly once -- zeros, or the owner's values --
-//       with 16-byte streaming stores; the dense tensor is never memset first.
-//       HBM-bound: algorithmic bytes = cells*D*4 written + 20 B/box read.
+//       the dense tensor is never memset first.  A warp owns tiles of whole rows
+//       whose size is a multiple of 512 B, so each warp store is 32 consecutive
+//       float4 = four full 128-byte lines (streaming, evict-first); the per-row
+//       owner codes of a tile arrive in one coalesced load, prefetched a tile ahead,
+//       and are broadcast by shuffle.  HBM-bound: algorithmic bytes =
+//       cells*D*4 written + 20 B/box read.
 //
 // All arithmetic that decides an integer (anchor, layer, cell, skip) uses IEEE
 // single/double operations in the reference's order; the file is compiled with
@@ -31,7 +35,6 @@ namespace {
 
 constexpr int kAssignThreads = 256;
 constexpr int kFillThreads = 256;
-constexpr int kFillBatch = 4;           // independent row groups in flight per warp
 
 // generators.py:2486-2494 + np.round(iol, 3) + first maximum (lowest global index)
 __device__ __forceinline__ int match_anchor(const HeadGeom& g, float bw, float bh)
@@ -196,11 +199,13 @@ encode_assign_kernel(const __grid_constant__ EncodeArgs a)
     if (tid == 0 && s_status) atomicOr(a.status, s_status);
 }
 
-// Per-layer plan of the streaming writer.
+// Per-layer plan of the streaming writer.  A warp tile is R whole rows with
+// R * dv a multiple of 32 vector units, so every warp store covers 32 consecutive
+// units (512 B with float4: four full 128-byte lines) and tiles never share a line.
 struct FillPlan {
     int dv[MGD_MAX_LAYERS];                 // vector units per row = D / VEC
-    int rpw[MGD_MAX_LAYERS];                // rows one warp covers per step
-    long long group_first[MGD_MAX_LAYERS + 1];
+    int R[MGD_MAX_LAYERS];                  // rows per warp tile = 32 / gcd(dv, 32)
+    long long tile_first[MGD_MAX_LAYERS + 1];
     long long rows[MGD_MAX_LAYERS];
 };
 
@@ -238,44 +243,48 @@ encode_fill_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * kFillThreads + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * kFillThreads) >> 5;
-    const long long total = p.group_first[g.L];
+    const long long total = p.tile_first[g.L];
+    V zero;
+    if constexpr (VEC == 4) zero = make_float4(0.f, 0.f, 0.f, 0.f); else zero = 0.f;
 
-    for (long long base = warp; base < total; base += n_warps * kFillBatch) {
-        int code[kFillBatch];
-        long long row[kFillBatch];
-        int lay[kFillBatch], part[kFillBatch];
-        #pragma unroll
-        for (int u = 0; u < kFillBatch; ++u) {
-            const long long grp = base + (long long)u * n_warps;
-            code[u] = -2;                                   // -2: nothing to do
-            if (grp < total) {
-                int l = 0;
-                while (l + 1 < g.L && grp >= p.group_first[l + 1]) ++l;
-                const int dv = p.dv[l];
-                const int sub = dv <= 32 ? lane / dv : 0;
-                const long long r = (grp - p.group_first[l]) * p.rpw[l] + sub;
-                lay[u] = l;
-                part[u] = dv <= 32 ? lane - sub * dv : lane;
-                row[u] = r;
-                if (sub < p.rpw[l] && r < p.rows[l])
-                    code[u] = __ldg(a.table + (size_t)a.B * g.cell_off[l] + r);
+    auto tile_layer = [&](long long tile) {
+        int l = 0;
+        while (l + 1 < g.L && tile >= p.tile_first[l + 1]) ++l;
+        return l;
+    };
+    // owner code of row `lane` of a tile (-1 beyond the layer's last row)
+    auto load_codes = [&](long long tile) {
+        if (tile >= total) return -1;
+        const int l = tile_layer(tile);
+        const long long row = (tile - p.tile_first[l]) * p.R[l] + lane;
+        if (lane >= p.R[l] || row >= p.rows[l]) return -1;
+        return __ldg(a.table + (size_t)a.B * g.cell_off[l] + row);
+    };
+
+    int next_codes = load_codes(warp);
+    for (long long tile = warp; tile < total; tile += n_warps) {
+        const int codes = next_codes;
+        next_codes = load_codes(tile + n_warps);          // prefetch: hides the only load
+        const int l = tile_layer(tile);
+        const int dv = p.dv[l];
+        const long long row0 = (tile - p.tile_first[l]) * p.R[l];
+        const long long left = p.rows[l] - row0;
+        const int n_rows = (int)(left < p.R[l] ? left : p.R[l]);
+        const int n_units = n_rows * dv;
+        V* dst = reinterpret_cast<V*>(a.y[l]) + row0 * dv;
+        // unit f = lane + 32*step lies in row r, column `part`; both advance without a division
+        int r = lane / dv, part = lane - r * dv;
+        const int inc_r = 32 / dv, inc_p = 32 - inc_r * dv;
+        const int steps = (n_units + 31) >> 5;
+        for (int st = 0, f = lane; st < steps; ++st, f += 32) {
+            const int code = __shfl_sync(0xffffffffu, codes, r & 31);
+            if (f < n_units) {
+                V v = zero;
+                if (code >= 0) v = make_units<VEC>(a.recs[code >> 4], code, part * VEC);
+                __stcs(dst + f, v);
             }
-        }
-        #pragma unroll
-        for (int u = 0; u < kFillBatch; ++u) {
-            if (code[u] == -2) continue;
-            const int l = lay[u];
-            const int dv = p.dv[l];
-            V* dst = reinterpret_cast<V*>(a.y[l]) + row[u] * dv;
-            if (code[u] < 0) {
-                V z;
-                if constexpr (VEC == 4) z = make_float4(0.f, 0.f, 0.f, 0.f); else z = 0.f;
-                for (int q = part[u]; q < dv; q += 32) __stcs(dst + q, z);
-            } else {
-                const BoxRec rec = a.recs[code[u] >> 4];
-                for (int q = part[u]; q < dv; q += 32)
-                    __stcs(dst + q, make_units<VEC>(rec, code[u], q * VEC));
-            }
+            part += inc_p; r += inc_r;
+            if (part >= dv) { part -= dv; ++r; }
         }
     }
 }
@@ -305,17 +314,18 @@ cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
         vec4 = vec4 && (g.D[l] % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y[l]) & 15) == 0);
     const int vec = vec4 ? 4 : 1;
     FillPlan p;
-    long long groups = 0;
+    long long tiles = 0;
     for (int l = 0; l < g.L; ++l) {
         p.dv[l] = g.D[l] / vec;
-        p.rpw[l] = p.dv[l] <= 32 ? 32 / p.dv[l] : 1;
+        int gcd = p.dv[l], t = 32;
+        while (t) { const int m = gcd % t; gcd = t; t = m; }
+        p.R[l] = 32 / gcd;
         p.rows[l] = (long long)a.B * g.gh[l] * g.gw[l];
-        p.group_first[l] = groups;
-        groups += (p.rows[l] + p.rpw[l] - 1) / p.rpw[l];
+        p.tile_first[l] = tiles;
+        tiles += (p.rows[l] + p.R[l] - 1) / p.R[l];
     }
-    p.group_first[g.L] = groups;
-    const long long warps_needed = (groups + kFillBatch - 1) / kFillBatch;
-    long long blocks = (warps_needed * 32 + kFillThreads - 1) / kFillThreads;
+    p.tile_first[g.L] = tiles;
+    long long blocks = (tiles * 32 + kFillThreads - 1) / kFillThreads;
     const long long max_blocks = (long long)num_sms * (2048 / kFillThreads);   // one full wave
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;

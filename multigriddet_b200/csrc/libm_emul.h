@@ -58,15 +58,10 @@ MGD_HD uint64_t mgd_double_as_u64(double d)
 #endif
 }
 
+// Core of the routine for finite |x| < ~104 (no overflow / NaN handling).
 // `tab` lets device code pass a shared-memory copy of the table.
-MGD_HD float mgd_expf_tab(float x, const uint64_t *tab)
+MGD_HD float mgd_expf_core(float x, const uint64_t *tab)
 {
-    // |x| >= 88 or NaN: glibc's special-case block
-    if (!(x < 88.0f && x > -88.0f)) {
-        if (x != x) return x + x;
-        if (x > 88.72283172607421875f) return __builtin_huge_valf();   // 0x1.62e42ep6f
-        if (x < -103.972076416015625f) return 0.0f;                    // -0x1.9fe368p6f
-    }
     const double inv_ln2_n = 0x1.71547652b82fep+0 * MGD_EXP2F_N;
     const double shift = 0x1.8p+52;
     const double c0 = 0x1.c6af84b912394p-5 / MGD_EXP2F_N / MGD_EXP2F_N / MGD_EXP2F_N;
@@ -90,6 +85,17 @@ MGD_HD float mgd_expf_tab(float x, const uint64_t *tab)
     y = fma(q, r2, y);
     y = y * s;
     return (float)y;
+}
+
+MGD_HD float mgd_expf_tab(float x, const uint64_t *tab)
+{
+    // |x| >= 88 or NaN: glibc's special-case block
+    if (!(x < 88.0f && x > -88.0f)) {
+        if (x != x) return x + x;
+        if (x > 88.72283172607421875f) return __builtin_huge_valf();   // 0x1.62e42ep6f
+        if (x < -103.972076416015625f) return 0.0f;                    // -0x1.9fe368p6f
+    }
+    return mgd_expf_core(x, tab);
 }
 
 MGD_HD float mgd_expf(float x) { return mgd_expf_tab(x, mgd_exp2f_tab); }

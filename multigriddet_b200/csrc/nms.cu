@@ -6,6 +6,9 @@
 // (multigrid_decode.py:322-345, 397-422).
 //
 // One CTA per image, everything after the candidate gather stays in shared memory:
+//   0. one thread per candidate rebuilds its box in float64 from the raw logits the
+//      decode kernel recorded ((xy + cell) / grid, anchor * exp(wh), letterbox
+//      correction with float32 constants: multigrid_decode.py:151-163, 205-228);
 //   1. bitonic sort of (score desc, cell index asc) keys -- the deterministic
 //      version of the reference's argsort(scores)[::-1];
 //   2. the sorted list is walked in chunks of 64.  For each chunk
@@ -23,14 +26,13 @@
 // traffic is the candidate records only (48 B each, normally L2-resident).
 #include <math.h>
 #include "common.cuh"
+#include "decode_math.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 64;
 constexpr int kSortSmem = 2048;   // (key, value) pairs sorted in shared memory
-
-struct BoxD { double x, y, w, h; };
 
 // nms.py:121-148 (IoU) and :189-231 (DIoU); true when b must be suppressed by a,
 // i.e. when NOT (metric < threshold)  (nms.py:112,180 keep `metric < threshold`).
@@ -92,10 +94,12 @@ nms_kernel(const __grid_constant__ NmsArgs a)
 
     const int tid = threadIdx.x;
     const int M = a.counts[b];
-    const Cand* cand = a.cand + (size_t)b * a.cap;
+    const Cand* cand = a.cand ? a.cand + (size_t)b * a.cap : nullptr;
+    const BoxD* boxes = a.cand ? a.boxes + (size_t)b * a.cap
+                               : reinterpret_cast<const BoxD*>(a.in_boxes);
     const bool diou = a.use_diou != 0;
 
-    // ---- 1. sort ---------------------------------------------------------------
+    // ---- 0. boxes + sort keys, one thread per candidate -----------------------------
     int mpad = 2;
     while (mpad < M) mpad <<= 1;
     unsigned long long* key = s_key;
@@ -104,14 +108,38 @@ nms_kernel(const __grid_constant__ NmsArgs a)
         key = a.sort_scratch + (size_t)b * 2 * a.sort_scratch_stride;
         val = key + a.sort_scratch_stride;
     }
+    if (cand) {
+        __shared__ uint64_t s_tab[MGD_EXP2F_N];
+        if (tid < MGD_EXP2F_N) s_tab[tid] = mgd_exp2f_tab[tid];
+        __syncthreads();
+        const HeadGeom& g = a.g;
+        const int ih = a.image_hw ? a.image_hw[2 * b] : a.in_h;
+        const int iw = a.image_hw ? a.image_hw[2 * b + 1] : a.in_w;
+        const Letterbox lb = letterbox_consts(g.in_h, g.in_w, ih, iw);
+        BoxD* out = a.boxes + (size_t)b * a.cap;
+        for (int i = tid; i < M; i += kThreads) {
+            const Cand cd = cand[i];
+            int layer = 0;
+            while (layer + 1 < g.L && cd.index >= g.cell_off[layer + 1]) ++layer;
+            const int cell = cd.index - g.cell_off[layer];
+            const int rr = cell / g.gw[layer], cc = cell - rr * g.gw[layer];
+            BoxD bx;
+            decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 0, s_tab, bx.x, bx.w);
+            decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 1, s_tab, bx.y, bx.h);
+            out[i] = bx;
+        }
+    }
     for (int i = tid; i < mpad; i += kThreads) {
         if (i < M) {
-            key[i] = score_key(cand[i].score);
-            val[i] = ((unsigned long long)(unsigned)cand[i].index << 32) | (unsigned)i;
+            const double sc = cand ? (double)cand[i].score : a.in_scores[i];
+            const unsigned idx = cand ? (unsigned)cand[i].index : (unsigned)i;
+            key[i] = score_key(sc);
+            val[i] = ((unsigned long long)idx << 32) | (unsigned)i;
         } else {
             key[i] = ~0ull; val[i] = ~0ull;
         }
     }
+    // ---- 1. sort ---------------------------------------------------------------
     if (tid == 0) { s_kept = 0; s_new = 0; }
     __syncthreads();
     for (int k = 2; k <= mpad; k <<= 1) {
@@ -139,9 +167,8 @@ nms_kernel(const __grid_constant__ NmsArgs a)
             c_alive[tid] = tid < n;
             if (tid < n) {
                 const int pos = (int)(val[c0 + tid] & 0xffffffffu);
-                const Cand cd = cand[pos];
-                c_box[tid].x = cd.x; c_box[tid].y = cd.y; c_box[tid].w = cd.w; c_box[tid].h = cd.h;
-                c_cls[tid] = cd.cls;
+                c_box[tid] = boxes[pos];
+                c_cls[tid] = cand ? cand[pos].cls : (a.in_classes ? a.in_classes[pos] : 0);
                 c_pos[tid] = pos;
             }
         }
@@ -187,7 +214,8 @@ nms_kernel(const __grid_constant__ NmsArgs a)
             const int slot = kept + tid;
             k_box[slot] = c_box[i];
             k_cls[slot] = c_cls[i];
-            const Cand cd = cand[c_pos[i]];
+            const BoxD cd = c_box[i];
+            const int pos = c_pos[i];
             const size_t o = (size_t)b * a.max_boxes + slot;
             if (a.out_xywh) {
                 a.out_xywh[o * 4 + 0] = cd.x; a.out_xywh[o * 4 + 1] = cd.y;
@@ -201,9 +229,9 @@ nms_kernel(const __grid_constant__ NmsArgs a)
                 a.out_xyxy[o * 4 + 2] = (int)floor(__dadd_rn(clipd(__dadd_rn(cd.x, cd.w), 0.0, W), 0.5));
                 a.out_xyxy[o * 4 + 3] = (int)floor(__dadd_rn(clipd(__dadd_rn(cd.y, cd.h), 0.0, H), 0.5));
             }
-            if (a.out_scores) a.out_scores[o] = cd.score;
-            if (a.out_classes) a.out_classes[o] = cd.cls;
-            if (a.out_index) a.out_index[o] = cd.index;
+            if (a.out_scores) a.out_scores[o] = cand ? (double)cand[pos].score : a.in_scores[pos];
+            if (a.out_classes) a.out_classes[o] = c_cls[i];
+            if (a.out_index) a.out_index[o] = cand ? cand[pos].index : pos;
         }
         __syncthreads();
     }
@@ -225,21 +253,6 @@ nms_kernel(const __grid_constant__ NmsArgs a)
             atomicAdd(&a.stats[1], (unsigned long long)kept);
         }
     }
-}
-
-// nms-only API: caller arrays -> candidate records (index = position)
-__global__ void pack_candidates_kernel(const double* boxes, const double* scores,
-                                       const int* classes, int n, Cand* cand, int* count)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *count = n;
-    if (i >= n) return;
-    Cand cd;
-    cd.x = boxes[4 * i]; cd.y = boxes[4 * i + 1]; cd.w = boxes[4 * i + 2]; cd.h = boxes[4 * i + 3];
-    cd.score = scores[i];
-    cd.index = i;
-    cd.cls = classes ? classes[i] : 0;
-    cand[i] = cd;
 }
 
 __global__ void keep_from_index_kernel(const int* index, const int* counts, int max_keep,
@@ -265,14 +278,6 @@ cudaError_t launch_nms(const NmsArgs& a, int, cudaStream_t stream)
     prof_mark_begin(PROF_NMS, stream);
     nms_kernel<<<a.B, kThreads, dyn, stream>>>(a);
     prof_mark_end(PROF_NMS, stream);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_pack_candidates(const double* boxes, const double* scores, const int* classes,
-                                   int n, Cand* cand, int* count, cudaStream_t stream)
-{
-    const int blocks = n > 0 ? (n + 255) / 256 : 1;
-    pack_candidates_kernel<<<blocks, 256, 0, stream>>>(boxes, scores, classes, n, cand, count);
     return cudaGetLastError();
 }
 
