@@ -1,0 +1,82 @@
+"""Drop-in for the target-encoding entry points of the reference's
+``multigriddet/data/generators.py``.
+
+Same names, argument meaning, return containers and error behaviour as the
+reference; the work happens in ``libmgd.so`` (``mgd_encode_targets``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import engine
+
+
+def get_anchor_mask(anchors):
+    """Global anchor indices grouped per layer (reference generators.py:2473-2483)."""
+    mask, start = [], 0
+    for layer in anchors:
+        mask.append(list(range(start, start + len(layer))))
+        start += len(layer)
+    return mask
+
+
+def _as_host_anchors(anchors):
+    out = []
+    for a in anchors:
+        if hasattr(a, "numpy") and not isinstance(a, np.ndarray):
+            a = a.numpy()                       # tf.constant / torch tensor
+        out.append(np.asarray(a))
+    return out
+
+
+def preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, multi_anchor_assign,
+                          grid_shapes=None, iou_thresh=0.2):
+    """Multi-grid ``y_true`` targets (reference generators.py:3393-3473).
+
+    true_boxes: (B, N, 5) ``[x1, y1, x2, y2, class]`` in pixels, zero rows = padding.
+    Returns a list of ``float32`` arrays ``(B, Gh, Gw, 5 + A + C)``, one per layer.
+    ``AssertionError`` if a class id is >= ``num_classes`` (generators.py:3409).
+    ``multi_anchor_assign`` and ``iou_thresh`` are accepted and ignored exactly as in
+    the reference (it always calls ``best_fit_and_layer(..., False)``, :3435).
+
+    NumPy in -> NumPy out (the library stages through the GPU); torch CUDA tensor
+    in -> torch CUDA tensors out (zero-copy).
+    """
+    del multi_anchor_assign, iou_thresh
+    anchors = _as_host_anchors(anchors)
+    if grid_shapes is not None:
+        grid_shapes = [(int(g[0]), int(g[1])) for g in grid_shapes]
+    input_shape = (int(input_shape[0]), int(input_shape[1]))
+    return engine.encode_targets(true_boxes, input_shape, anchors, int(num_classes), grid_shapes)
+
+
+def tf_preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, multi_anchor_assign,
+                             grid_shapes, debug_aug_pipeline=False):
+    """Signature-compatible stand-in for the reference's ``@tf.function`` encoder
+    (generators.py:2696-3390).
+
+    It computes the *NumPy-path* semantics (the runnable, self-consistent encoder,
+    SURVEY.md section 0): floor-divided centres, rounded-IoL anchor choice and the
+    sequential occupancy rule.  The TF path differs from that in known ways (exact
+    centres, no IoL rounding, last box wins every contested cell, x/y fractions
+    swapped -- SURVEY.md 8a-3); those are NOT reproduced and parity against real
+    TensorFlow is unpinned (TF is not installed here).
+
+    A ctypes library cannot be traced into a TF graph: inside ``dataset.map`` call
+    it through ``tf.py_function`` / ``tf.numpy_function``.  TensorFlow tensors are
+    accepted eagerly via DLPack when TF is present; NumPy and torch CUDA tensors
+    always work.  Returns the same container type it was given.
+    """
+    del debug_aug_pipeline
+    tf_mod = type(true_boxes).__module__.split(".")[0] == "tensorflow"
+    if tf_mod:
+        import tensorflow as tf            # only reachable where TF exists
+        boxes = np.from_dlpack(tf.experimental.dlpack.to_dlpack(true_boxes)) \
+            if hasattr(np, "from_dlpack") else true_boxes.numpy()
+        shape = tuple(int(v) for v in np.asarray(input_shape).reshape(-1)[:2])
+        y = preprocess_true_boxes(boxes, shape, anchors, num_classes, multi_anchor_assign,
+                                  grid_shapes)
+        return [tf.convert_to_tensor(t) for t in y]
+    shape = tuple(int(v) for v in np.asarray(input_shape).reshape(-1)[:2])
+    return preprocess_true_boxes(true_boxes, shape, anchors, num_classes, multi_anchor_assign,
+                                 grid_shapes)

@@ -1,0 +1,168 @@
+"""Generate ``tests/golden/*.npz`` by running the REAL reference from /root/reference.
+
+    python -m oracle.gen_golden          (build container only; needs /root/reference)
+
+Test infrastructure (see ``oracle/__init__.py``).  The fixtures pin the oracle
+(``tests/test_oracle_golden.py``) and, on the GPU box where the reference does not
+exist, the CUDA path (``tests/test_gpu_golden.py``).  NumPy runs with its AVX
+dispatch disabled (``ref_loader.pin_numpy_env``) so ``argsort`` ties and the float32
+transcendentals are the portable libm ones.
+
+Fixtures are kept small: y_true is stored sparsely (positive cells only), head
+outputs are quantised to float16-representable values so they store in half the
+space while every consumer sees the identical float32 tensor.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+ref_loader.pin_numpy_env()
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from multigriddet_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+SMALL_FIRST = (((10, 13), (16, 30), (33, 23)), ((30, 61), (62, 45), (59, 119)),
+               ((116, 90), (156, 198), (373, 326)))
+
+
+def sparse(y_true):
+    """positive-cell coordinates and rows of each layer"""
+    out = {}
+    for l, y in enumerate(y_true):
+        nz = np.argwhere(np.any(y != 0, axis=-1))
+        out[f"idx{l}"] = nz.astype(np.int32)
+        out[f"val{l}"] = y[nz[:, 0], nz[:, 1], nz[:, 2]].astype(np.float32)
+        out[f"shape{l}"] = np.array(y.shape, dtype=np.int32)
+    return out
+
+
+def encode_cases():
+    enc = ref_loader.load_encoder()
+    cases = [
+        # name, S, C, N, B, layout, corners, padding, anchor dtype, anchor set
+        ("voc416", 416, 20, 20, 8, "uniform", "int", "tail", np.float32, "coco"),
+        ("coco608", 608, 80, 100, 3, "uniform", "int", "tail", np.float32, "coco"),
+        ("coco608_f64", 608, 80, 100, 2, "uniform", "frac", "interleaved", np.float64, "coco"),
+        ("mosaic320", 320, 80, 300, 2, "mosaic", "frac", "tail", np.float32, "coco"),
+        ("mosaic512_f64", 512, 80, 300, 2, "mosaic", "int", "tail", np.float64, "coco"),
+        ("oneclass352", 352, 1, 40, 2, "uniform", "frac", "tail", np.float32, "small_first"),
+    ]
+    for i, (name, S, C, N, B, layout, corners, padding, dt, aset) in enumerate(cases):
+        anchors = (synth.coco_anchors(dt) if aset == "coco"
+                   else [np.array(a, dtype=dt) for a in SMALL_FIRST])
+        boxes = synth.synth_boxes(100 + i, B, N, S, C, corners=corners, layout=layout,
+                                  padding=padding, anchors=anchors)
+        y = enc(boxes.copy(), (S, S), anchors, C, False)
+        np.savez_compressed(os.path.join(OUT, f"encode_{name}.npz"), boxes=boxes,
+                            anchors=np.stack(anchors).astype(np.float64),
+                            anchors_f64=np.array(dt == np.float64), S=S, C=C, **sparse(y))
+        print("encode", name, [int(a[..., 4].sum()) for a in y])
+    # known-answer single boxes (the inputs of the reference's own two hot-path tests)
+    small_first = [np.array(a, dtype=np.float32) for a in SMALL_FIRST]
+    ka = []
+    for box, C in (([254, 264, 354, 344, 0], 1), ([100, 200, 180, 260, 2], 80),
+                   ([271.999, 271.999, 351.999, 351.999, 0], 1)):
+        b = np.array([[box]], dtype=np.float32)
+        y = enc(b.copy(), (608, 608), small_first, C, False)
+        ka.append((b, C, y))
+    np.savez_compressed(os.path.join(OUT, "encode_known_answer.npz"),
+                        anchors=np.stack(small_first).astype(np.float64),
+                        **{f"box{i}": k[0] for i, k in enumerate(ka)},
+                        **{f"C{i}": np.array(k[1]) for i, k in enumerate(ka)},
+                        **{f"c{i}_{key}": v for i, k in enumerate(ka) for key, v in sparse(k[2]).items()})
+
+
+def decode_cases():
+    post = ref_loader.load_postprocess()
+    enc = ref_loader.load_encoder()
+    cases = [
+        # name, S, C, B, N, anchor dtype
+        ("voc416", 416, 20, 2, 20, np.float32),
+        ("coco160", 160, 80, 3, 12, np.float32),
+        ("coco160_f64", 160, 80, 2, 12, np.float64),
+    ]
+    knobs = [
+        dict(image_shape=None, confidence=0.001, nms_threshold=0.45, nms_method="diou", max_boxes=100),
+        dict(image_shape=(480, 640), confidence=0.1, nms_threshold=0.45, nms_method="diou", max_boxes=100),
+        dict(image_shape=(1080, 1920), confidence=0.001, nms_threshold=0.5, nms_method="cluster", max_boxes=5),
+        dict(image_shape=(375, 500), confidence=0.3, nms_threshold=0.3, nms_method="diou", max_boxes=100),
+    ]
+    for i, (name, S, C, B, N, dt) in enumerate(cases):
+        anchors = synth.coco_anchors(dt)
+        boxes = synth.synth_boxes(200 + i, B, N, S, C, anchors=anchors)
+        y = enc(boxes.copy(), (S, S), anchors, C, False)
+        preds = synth.planted_head_outputs([torch.from_numpy(a) for a in y], 3, seed=300 + i)
+        preds16 = [p.numpy().astype(np.float16) for p in preds]
+        preds = [p.astype(np.float32) for p in preds16]
+        dec = post.MultiGridDecoder(anchors, C, input_shape=(S, S))
+        store = {"anchors": np.stack(anchors).astype(np.float64),
+                 "anchors_f64": np.array(dt == np.float64), "S": S, "C": C,
+                 "n_knobs": len(knobs)}
+        for l, p in enumerate(preds16):
+            store[f"pred{l}"] = p
+        dense = dec.decode_predictions([p.copy() for p in preds])
+        store["dense_sample_rows"] = np.arange(0, dense.shape[1], 37)
+        store["dense_sample"] = dense[:, ::37, :]
+        for k, kn in enumerate(knobs):
+            ishape = kn["image_shape"] or (S, S)
+            store[f"k{k}_image_shape"] = np.array(ishape)
+            store[f"k{k}_conf"] = np.array(kn["confidence"])
+            store[f"k{k}_thr"] = np.array(kn["nms_threshold"])
+            store[f"k{k}_method"] = np.array(kn["nms_method"])
+            store[f"k{k}_max"] = np.array(kn["max_boxes"])
+            ties = 0
+            for b in range(B):
+                one = [p[b:b + 1].copy() for p in preds]
+                for xyxy in (True, False):
+                    bx, cl, sc = dec.postprocess(one, ishape, (S, S), max_boxes=kn["max_boxes"],
+                                                 confidence=kn["confidence"],
+                                                 nms_threshold=kn["nms_threshold"],
+                                                 nms_method=kn["nms_method"], return_xyxy=xyxy)
+                    tag = "xyxy" if xyxy else "xywh"
+                    store[f"k{k}_b{b}_{tag}"] = np.asarray(bx)
+                store[f"k{k}_b{b}_classes"] = np.asarray(cl)
+                store[f"k{k}_b{b}_scores"] = np.asarray(sc)
+                ties += int(len(sc) - len(np.unique(sc)))
+            print("decode", name, "knob", k, "dets", [len(store[f"k{k}_b{b}_scores"]) for b in range(B)],
+                  "equal-score detections", ties)
+        np.savez_compressed(os.path.join(OUT, f"decode_{name}.npz"), **store)
+
+
+def nms_cases():
+    post = ref_loader.load_postprocess()
+    rng = np.random.default_rng(7)
+    store = {}
+    for i, n in enumerate((1, 7, 120, 900)):
+        xy = rng.uniform(0, 400, size=(n, 2))
+        wh = rng.uniform(4, 150, size=(n, 2))
+        boxes = np.concatenate([xy, wh], 1)
+        scores = rng.uniform(0.01, 1, size=n)          # distinct with probability 1
+        classes = rng.integers(0, 6, size=n)
+        store[f"n{i}_boxes"], store[f"n{i}_scores"], store[f"n{i}_classes"] = boxes, scores, classes
+        for name, cls in (("diou", post.DIoUNMS), ("standard", post.StandardNMS), ("cluster", post.ClusterNMS)):
+            for thr in (0.3, 0.5):
+                kb, kc, ks = cls().apply_nms(boxes, classes, scores, thr, 0.0)
+                store[f"n{i}_{name}_{thr}_scores"] = ks[0]
+                store[f"n{i}_{name}_{thr}_boxes"] = kb[0]
+    np.savez_compressed(os.path.join(OUT, "nms_cases.npz"), **store)
+    print("nms cases written")
+
+
+if __name__ == "__main__":
+    if not ref_loader.available():
+        raise SystemExit("reference tree not found at " + ref_loader.REFERENCE_ROOT)
+    os.makedirs(OUT, exist_ok=True)
+    encode_cases()
+    decode_cases()
+    nms_cases()
+    total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print(f"golden fixtures: {total / 1e6:.2f} MB in {OUT}")

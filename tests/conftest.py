@@ -15,6 +15,10 @@ if ROOT not in sys.path:
 # Must happen before NumPy is first imported by the test process.
 from oracle import ref_loader  # noqa: E402
 
+# The pin only works if NumPy has not been imported yet (pytest.ini disables the
+# plugins that would import it first).  Tests that compare NumPy-oracle floats
+# bit-for-bit fall back to a 1e-6 tolerance when the pin could not take effect.
+os.environ["MGD_NUMPY_PIN_EFFECTIVE"] = "0" if "numpy" in sys.modules else "1"
 ref_loader.pin_numpy_env()
 
 import pytest  # noqa: E402

@@ -1,0 +1,98 @@
+"""The oracle (NumPy and C restatements) against the reference's golden vectors.
+
+tests/golden/*.npz were produced by running the reference itself
+(oracle/gen_golden.py); these tests run everywhere (no GPU, no reference tree).
+"""
+import numpy as np
+import pytest
+
+import golden_util as G
+from oracle import mgd_oracle as O
+
+
+@pytest.mark.parametrize("path", G.files("encode"))
+def test_encode_oracles_match_reference_golden(path, c_oracle):
+    z = np.load(path)
+    if "boxes" not in z:          # known-answer file, handled below
+        return
+    anchors = G.anchors_of(z)
+    S, C = int(z["S"]), int(z["C"])
+    ref = G.dense_y_true(z)
+    got = O.encode_targets(z["boxes"], (S, S), anchors, C)
+    G.assert_encode_matches(got, ref, exact_floats=G.numpy_pinned())
+    got = O.encode_targets_parallel_scheme(z["boxes"], (S, S), anchors, C)
+    G.assert_encode_matches(got, ref, exact_floats=G.numpy_pinned())
+    got = c_oracle.encode_targets(z["boxes"], (S, S), anchors, C)
+    G.assert_encode_matches(got, ref, exact_floats=True)
+
+
+def test_encode_known_answers(c_oracle):
+    z = np.load(G.GOLDEN + "/encode_known_answer.npz")
+    anchors = [np.array(a, dtype=np.float32) for a in z["anchors"]]
+    for i in range(3):
+        ref = G.dense_y_true(z, prefix=f"c{i}_")
+        for impl in (O.encode_targets, c_oracle.encode_targets):
+            got = impl(z[f"box{i}"], (608, 608), anchors, int(z[f"C{i}"]))
+            G.assert_encode_matches(got, ref, exact_floats=G.numpy_pinned() or impl is c_oracle.encode_targets)
+    # the values SURVEY.md 8c quotes from the reference's own test inputs
+    y = G.dense_y_true(z, prefix="c0_")
+    np.testing.assert_allclose(y[2][0, 38, 38, :4], [0, 0, -0.14842002, -0.11778303], rtol=1e-6)
+    y = G.dense_y_true(z, prefix="c1_")
+    np.testing.assert_allclose(y[1][0, 14, 8, :4], [0.75, 0.375, 0.25489223, 0.28768212], rtol=1e-6)
+    # test_9cell_alignment.py's box: stored xy stays in [-1, 2)
+    y = G.dense_y_true(z, prefix="c2_")
+    pos = [l for l in range(3) if y[l].any()]
+    assert len(pos) == 1
+    cells = y[pos[0]][y[pos[0]][..., 4] == 1]
+    assert len(cells) == 9 and cells[:, :2].min() >= -1 and cells[:, :2].max() < 2
+
+
+@pytest.mark.parametrize("path", G.files("decode"))
+def test_decode_oracles_match_reference_golden(path, c_oracle):
+    z = np.load(path, allow_pickle=False)
+    anchors = G.anchors_of(z)
+    S, C = int(z["S"]), int(z["C"])
+    preds = G.preds_of(z)
+    B = preds[0].shape[0]
+    dense = O.decode_predictions(preds, anchors, (S, S), C)
+    if G.numpy_pinned():
+        assert np.array_equal(dense[:, ::37, :], z["dense_sample"])
+    else:
+        np.testing.assert_allclose(dense[:, ::37, :], z["dense_sample"], rtol=1e-6, atol=1e-30)
+    for k, kn in G.knobs_of(z):
+        ishape = kn.pop("image_shape")
+        py = O.postprocess_batch(preds, np.tile(np.array(ishape), (B, 1)), (S, S), anchors, C, **kn)
+        cc = c_oracle.decode_nms(preds, [ishape], (S, S), anchors, C, **kn)
+        for b in range(B):
+            ref_s = z[f"k{k}_b{b}_scores"]
+            n = len(ref_s)
+            assert len(py[b]["scores"]) == n and int(cc["counts"][b]) == n
+            if G.numpy_pinned():
+                assert np.array_equal(py[b]["scores"], ref_s)
+                assert np.array_equal(py[b]["boxes_xywh"], z[f"k{k}_b{b}_xywh"].reshape(-1, 4))
+            else:
+                np.testing.assert_allclose(py[b]["scores"], ref_s, rtol=1e-6)
+                np.testing.assert_allclose(py[b]["boxes_xywh"], z[f"k{k}_b{b}_xywh"].reshape(-1, 4),
+                                           rtol=1e-6, atol=1e-4)
+            assert np.array_equal(py[b]["boxes_xyxy"], z[f"k{k}_b{b}_xyxy"].reshape(-1, 4))
+            assert np.array_equal(py[b]["classes"], z[f"k{k}_b{b}_classes"])
+            # the C restatement: bit-exact too (NumPy pinned to libm in conftest.py)
+            assert np.array_equal(cc["scores"][b, :n], ref_s)
+            assert np.array_equal(cc["boxes_xywh"][b, :n], z[f"k{k}_b{b}_xywh"].reshape(-1, 4))
+            assert np.array_equal(cc["boxes_xyxy"][b, :n], z[f"k{k}_b{b}_xyxy"].reshape(-1, 4))
+            assert np.array_equal(cc["classes"][b, :n], z[f"k{k}_b{b}_classes"])
+            assert np.array_equal(cc["index"][b, :n], py[b]["index"])
+
+
+def test_nms_oracle_matches_reference_golden():
+    z = np.load(G.GOLDEN + "/nms_cases.npz")
+    i = 0
+    while f"n{i}_boxes" in z:
+        boxes, scores = z[f"n{i}_boxes"], z[f"n{i}_scores"]
+        for name, diou in (("diou", True), ("standard", False), ("cluster", False)):
+            for thr in (0.3, 0.5):
+                keep = O.greedy_nms(boxes, scores, thr, diou)
+                assert np.array_equal(scores[keep], z[f"n{i}_{name}_{thr}_scores"])
+                assert np.array_equal(boxes[keep], z[f"n{i}_{name}_{thr}_boxes"])
+        i += 1
+    assert i == 4

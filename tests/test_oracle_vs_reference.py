@@ -1,0 +1,80 @@
+"""The oracle against the reference executed from /root/reference on fresh seeds.
+
+Only runs in the build container (the reference tree does not exist on the GPU box);
+elsewhere the golden vectors (test_oracle_golden.py) carry the pin.
+"""
+import numpy as np
+import pytest
+
+from oracle import mgd_oracle as O
+from oracle import ref_loader
+from multigriddet_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(),
+                                reason="reference tree not present (GPU box)")
+
+
+@pytest.mark.parametrize("S,C,N,B,layout,corners,padding,dt", [
+    (608, 80, 100, 3, "uniform", "int", "tail", np.float32),
+    (608, 80, 100, 2, "uniform", "frac", "interleaved", np.float64),
+    (416, 20, 20, 8, "uniform", "int", "tail", np.float32),
+    (320, 80, 300, 2, "mosaic", "frac", "tail", np.float32),
+    (544, 80, 300, 2, "mosaic", "int", "interleaved", np.float64),
+    (672, 80, 800, 1, "mosaic", "frac", "tail", np.float32),
+])
+def test_encoder_restatements_equal_reference(S, C, N, B, layout, corners, padding, dt, c_oracle):
+    enc = ref_loader.load_encoder()
+    anchors = synth.coco_anchors(dt)
+    boxes = synth.synth_boxes(31, B, N, S, C, corners=corners, layout=layout, padding=padding)
+    ref = enc(boxes.copy(), (S, S), anchors, C, False)
+    for impl in (O.encode_targets, O.encode_targets_parallel_scheme, c_oracle.encode_targets):
+        got = impl(boxes, (S, S), anchors, C)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got)), impl.__name__
+    with pytest.raises(AssertionError):
+        bad = boxes.copy()
+        bad[0, 0, 4] = C
+        O.encode_targets(bad, (S, S), anchors, C)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_decoder_restatements_equal_reference(dt, c_oracle):
+    import torch
+    post = ref_loader.load_postprocess()
+    S, C, B = 608, 80, 3
+    anchors = synth.coco_anchors(dt)
+    boxes = synth.synth_boxes(5, B, 100, S, C)
+    yt = O.encode_targets(boxes, (S, S), anchors, C)
+    preds = [p.numpy() for p in synth.planted_head_outputs([torch.from_numpy(y) for y in yt], 3, 9)]
+    dec = post.MultiGridDecoder(anchors, C, input_shape=(S, S))
+    for ishape, method, conf, thr in (((608, 608), "diou", 0.001, 0.45), ((480, 640), "diou", 0.1, 0.45),
+                                      ((427, 640), "cluster", 0.001, 0.5)):
+        cc = c_oracle.decode_nms(preds, [ishape], (S, S), anchors, C, max_boxes=100, confidence=conf,
+                                 nms_threshold=thr, nms_method=method)
+        for b in range(B):
+            one = [p[b:b + 1] for p in preds]
+            rb, rc, rs = dec.postprocess([o.copy() for o in one], ishape, (S, S), max_boxes=100,
+                                         confidence=conf, nms_threshold=thr, nms_method=method)
+            m = O.postprocess_image(one, ishape, (S, S), anchors, C, max_boxes=100, confidence=conf,
+                                    nms_threshold=thr, nms_method=method)
+            assert np.array_equal(rb, m["boxes_xyxy"]) and np.array_equal(rc, m["classes"])
+            assert np.array_equal(rs, m["scores"])
+            n = len(rs)
+            assert int(cc["counts"][b]) == n
+            assert np.array_equal(cc["scores"][b, :n], rs)
+            assert np.array_equal(cc["boxes_xyxy"][b, :n], rb.reshape(-1, 4))
+    # sigmoid mode and the dense decode tensor
+    dec2 = post.MultiGridDecoder(anchors, C, input_shape=(S, S), use_softmax=False, rescore_confidence=False)
+    d_ref = dec2.decode_predictions([p.copy() for p in preds])
+    d_mine = O.decode_predictions(preds, anchors, (S, S), C, use_softmax=False, rescore_confidence=False)
+    assert np.array_equal(d_ref, d_mine)
+
+
+def test_reference_error_conventions():
+    post = ref_loader.load_postprocess()
+    anchors = synth.coco_anchors(np.float32)
+    dec = post.MultiGridDecoder(anchors, 80)
+    with pytest.raises(ValueError):
+        dec.decode_predictions([np.zeros((1, 19, 19, 88), np.float32)])
+    assert post.DIoUNMS().apply_nms(np.zeros((0, 4)), np.zeros(0), np.zeros(0), 0.5, 0.1) == ([], [], [])
+    with pytest.raises(NotImplementedError):      # 'standard' is not wired in the reference
+        dec.handle_predictions(np.ones((1, 3, 85)), (608, 608), nms_method="standard")
