@@ -181,6 +181,16 @@ int chunk_images(const HeadGeom& g, int batch)
     return (int)n;
 }
 
+// decode + NMS: one NMS launch should see thousands of images (a warp per image), so the
+// chunk is bounded by the candidate scratch (<= 1 GiB of 32-byte slots) instead
+int decode_chunk_images(const HeadGeom& g, int batch)
+{
+    long long n = (1ll << 30) / ((long long)g.cells * (long long)sizeof(Cand));
+    if (n < 1) n = 1;
+    if (n > batch) n = batch;
+    return (int)n;
+}
+
 // ---- deferred device-side status of asynchronous encode calls ---------------------
 struct Pending { int* host; int device; };
 thread_local std::vector<Pending> t_pending;
@@ -248,7 +258,7 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
                       int* classes, int* index, int* counts, int num_sms, cudaStream_t stream,
                       unsigned long long* d_stats)
 {
-    const int step = chunk_images(g, batch);
+    const int step = decode_chunk_images(g, batch);
     const int M = post.max_boxes;
     int pow2 = 2;
     while (pow2 < g.cells) pow2 <<= 1;
@@ -269,8 +279,9 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         d.obj_logit_min = objectness_prefilter(post);
         d.score_lo = post.confidence > 0.0 ? (float)(post.confidence * (1.0 - 1e-3)) : -1.0f;
         CUDA_TRY(cudaMallocAsync(&d.cand, (size_t)nb * g.cells * sizeof(Cand), stream));
-        CUDA_TRY(cudaMallocAsync(&d.counts, (size_t)nb * sizeof(int), stream));
-        CUDA_TRY(cudaMemsetAsync(d.counts, 0, (size_t)nb * sizeof(int), stream));
+        // counts[nb], counts[nb+1]: the work counters of the two warp-per-image NMS launches
+        CUDA_TRY(cudaMallocAsync(&d.counts, (size_t)(nb + 2) * sizeof(int), stream));
+        CUDA_TRY(cudaMemsetAsync(d.counts, 0, (size_t)(nb + 2) * sizeof(int), stream));
         CUDA_TRY(launch_decode(d, num_sms, stream));
 
         NmsArgs n;
@@ -281,6 +292,7 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         n.cand = d.cand;
         CUDA_TRY(cudaMallocAsync(&n.boxes, (size_t)nb * g.cells * sizeof(BoxD), stream));
         n.counts = d.counts;
+        n.next_image = d.counts + nb;
         n.image_hw = d.image_hw;
         n.in_h = g.in_h; n.in_w = g.in_w;
         n.thr = post.nms_threshold;

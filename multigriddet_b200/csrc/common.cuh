@@ -84,6 +84,8 @@ struct NmsArgs {
     int in_h, in_w;
     double thr;
     int use_diou, per_class, max_boxes;
+    int skip_small;                   // nms_kernel: skip images with <= this many candidates
+    int* next_image;                  // nms_warp_kernel: work counter (zeroed by the caller)
     unsigned long long* sort_scratch; // (B, 2*pow2(cap)) u64, used when count > smem capacity
     int sort_scratch_stride;          // elements (pairs) per image in sort_scratch
     unsigned char* kept_scratch;      // kept-box list in global memory when max_boxes is large

@@ -38,7 +38,6 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kDenseThreads = 256;
-constexpr int kPoolRows = 32;
 
 // ---- PTX: mbarrier + TMA bulk copy -------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -95,7 +94,7 @@ struct WarpPool {
 
 // Level 2 + 3 on the `count` rows currently in the warp's pool (all of one layer).
 // Called by all 32 lanes.
-template <bool kFast>
+template <bool kFast, int kPoolRows>
 __device__ __noinline__ void flush_pool(const DecodeArgs& a, const WarpPool& pool, int count,
                                         int layer, const uint64_t* s_tab)
 {
@@ -177,8 +176,8 @@ __device__ __noinline__ void flush_pool(const DecodeArgs& a, const WarpPool& poo
 
 // kFast: every layer has A == 3 anchors, D % 4 == 0 and 16-byte aligned tensors:
 // 16-byte loads for level 1, TMA bulk copies into the pool, float4 pool reads.
-template <bool kFast>
-__global__ void __launch_bounds__(kThreads)
+template <bool kFast, int kPoolRows>
+__global__ void __launch_bounds__(kThreads, kPoolRows >= 32 ? 2 : (kPoolRows >= 24 ? 3 : 4))
 decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -265,45 +264,50 @@ decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
             unsigned todo = __ballot_sync(0xffffffffu, pass);
             if (!todo) continue;
 
-            // ---- append the survivors' rows to the pool ------------------------------------
-            int n_new = __popc(todo);
-            if (count + n_new > kPoolRows) {
+            // ---- append the survivors' rows to the pool; flush whenever it is full ----------
+            while (todo) {
+                const int free_slots = kPoolRows - count;
+                const int rank = __popc(todo & ((1u << lane) - 1u));
+                const bool take = ((todo >> lane) & 1u) && rank < free_slots;
+                const unsigned taken = __ballot_sync(0xffffffffu, take);
+                const int n_new = __popc(taken);
+                if (take) {
+                    pool.cell[count + rank] = row;
+                    pool.bound[count + rank] = bound;
+                }
                 if (kFast) {
-                    if (lane == 0) mbar_arrive(pool.bar);
-                    mbar_wait(pool.bar, bar_phase);
-                    bar_phase ^= 1u;
+                    // one bulk copy per surviving row, issued by the row's own lane; the copies
+                    // stay in flight while the warp moves on -- they are awaited at the flush
+                    if (lane == 0) mbar_expect_tx(pool.bar, (uint32_t)n_new * D * sizeof(float));
+                    __syncwarp();
+                    if (take)
+                        bulk_g2s(pool.rows + (size_t)(count + rank) * pool.stride,
+                                 base + (size_t)row * D, (uint32_t)D * sizeof(float), pool.bar);
+                } else {
+                    unsigned rest = taken;
+                    int slot = count;
+                    while (rest) {
+                        const int src_lane = __ffs((int)rest) - 1;
+                        rest &= rest - 1;
+                        const float* src = base + ((size_t)blk * 32 + src_lane) * D;
+                        float* dst = pool.rows + (size_t)slot * pool.stride;
+                        for (int i = lane; i < D; i += 32) dst[i] = __ldg(src + i);
+                        ++slot;
+                    }
+                    __syncwarp();
                 }
-                flush_pool<kFast>(a, pool, count, layer, s_tab);
-                count = 0;
-            }
-            // lane i of the survivors (in row order) takes pool slot count + rank
-            const int rank = __popc(todo & ((1u << lane) - 1u));
-            if (pass) {
-                pool.cell[count + rank] = row;
-                pool.bound[count + rank] = bound;
-            }
-            if (kFast) {
-                // one bulk copy per surviving row, issued by the row's own lane; the copies
-                // stay in flight while the warp moves on -- they are awaited at the flush
-                if (lane == 0) mbar_expect_tx(pool.bar, (uint32_t)n_new * D * sizeof(float));
-                __syncwarp();
-                if (pass)
-                    bulk_g2s(pool.rows + (size_t)(count + rank) * pool.stride,
-                             base + (size_t)row * D, (uint32_t)D * sizeof(float), pool.bar);
-            } else {
-                unsigned rest = todo;
-                int slot = count;
-                while (rest) {
-                    const int src_lane = __ffs((int)rest) - 1;
-                    rest &= rest - 1;
-                    const float* src = base + ((size_t)blk * 32 + src_lane) * D;
-                    float* dst = pool.rows + (size_t)slot * pool.stride;
-                    for (int i = lane; i < D; i += 32) dst[i] = __ldg(src + i);
-                    ++slot;
+                count += n_new;
+                todo &= ~taken;
+                if (count == kPoolRows) {
+                    if (kFast) {
+                        if (lane == 0) mbar_arrive(pool.bar);
+                        mbar_wait(pool.bar, bar_phase);
+                        bar_phase ^= 1u;
+                    }
+                    flush_pool<kFast, kPoolRows>(a, pool, count, layer, s_tab);
+                    count = 0;
                 }
-                __syncwarp();
             }
-            count += n_new;
         }
         if (count) {
             if (kFast) {
@@ -311,7 +315,7 @@ decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
                 mbar_wait(pool.bar, bar_phase);
                 bar_phase ^= 1u;
             }
-            flush_pool<kFast>(a, pool, count, layer, s_tab);
+            flush_pool<kFast, kPoolRows>(a, pool, count, layer, s_tab);
         }
         __syncwarp();
     }
@@ -397,13 +401,15 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
     // (generic path) so that lane-per-row reads hit distinct banks
     int stride = fast ? (dmax / 4 | 1) * 4 : (dmax | 1);
     if (fast && stride < dmax) stride += 8;
-    const size_t smem = (size_t)kWarpsPerCta * kPoolRows * stride * sizeof(float);
+    static int env_pool = -1;
+    if (env_pool < 0) { const char* e = getenv("MGD_DECODE_POOL_ROWS"); env_pool = e ? atoi(e) : 0; }
+    int pool_rows = env_pool == 32 || env_pool == 24 || env_pool == 16 ? env_pool : 32;
+    while (pool_rows > 16 && (size_t)kWarpsPerCta * pool_rows * stride * sizeof(float) > 200 * 1024) pool_rows -= 8;
+    const size_t smem = (size_t)kWarpsPerCta * pool_rows * stride * sizeof(float);
     if (smem > 220 * 1024) return cudaErrorInvalidValue;
-    static int env_ctas = -1;
-    if (env_ctas < 0) { const char* e = getenv("MGD_DECODE_CTAS_PER_SM"); env_ctas = e ? atoi(e) : 0; }
     int ctas_per_sm = (int)((224 * 1024) / (smem + 2048));
-    if (ctas_per_sm > 2048 / kThreads) ctas_per_sm = 2048 / kThreads;
-    if (env_ctas > 0 && env_ctas < ctas_per_sm) ctas_per_sm = env_ctas;
+    const int reg_limit = pool_rows >= 32 ? 2 : (pool_rows >= 24 ? 3 : 4);
+    if (ctas_per_sm > reg_limit) ctas_per_sm = reg_limit;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     long long blocks = 0;
     for (int l = 0; l < g.L; ++l) blocks += (a.rows_in_layer[l] + 31) / 32;
@@ -413,17 +419,22 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
     if (grid < 1) grid = 1;
     cudaError_t err;
     prof_mark_begin(PROF_DECODE_COMPACT, stream);
+    auto run = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<(unsigned)grid, kThreads, smem, stream>>>(a, stride);
+        return cudaSuccess;
+    };
     if (fast) {
-        err = cudaFuncSetAttribute(decode_compact_kernel<true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        decode_compact_kernel<true><<<(unsigned)grid, kThreads, smem, stream>>>(a, stride);
+        if (pool_rows == 32) err = run(decode_compact_kernel<true, 32>);
+        else if (pool_rows == 24) err = run(decode_compact_kernel<true, 24>);
+        else err = run(decode_compact_kernel<true, 16>);
     } else {
-        err = cudaFuncSetAttribute(decode_compact_kernel<false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        decode_compact_kernel<false><<<(unsigned)grid, kThreads, smem, stream>>>(a, stride);
+        if (pool_rows == 32) err = run(decode_compact_kernel<false, 32>);
+        else if (pool_rows == 24) err = run(decode_compact_kernel<false, 24>);
+        else err = run(decode_compact_kernel<false, 16>);
     }
+    if (err != cudaSuccess) return err;
     prof_mark_end(PROF_DECODE_COMPACT, stream);
     return cudaGetLastError();
 }

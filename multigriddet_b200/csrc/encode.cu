@@ -15,13 +15,13 @@
 //       Both tables live in shared memory (atomicMin / atomicMax); the result is
 //       a per-cell owner code (box record, neighbour id) written once, coalesced.
 //
-//   encode_fill_kernel    grid-wide streaming writer.  Every y_true row
-//       (5+A+C floats) is produced exactly once -- zeros, or the owner's values --
-//       the dense tensor is never memset first.  A warp owns tiles of whole rows
-//       whose size is a multiple of 512 B, so each warp store is 32 consecutive
-//       float4 = four full 128-byte lines (streaming, evict-first); the per-row
-//       owner codes of a tile arrive in one coalesced load, prefetched a tile ahead,
-//       and are broadcast by shuffle.  HBM-bound: algorithmic bytes =
+//   encode_fill_kernel    grid-wide streaming writer.  A warp owns tiles of whole
+//       rows whose size is a multiple of 512 B: it stores the tile as zeros with 32
+//       consecutive float4 per instruction (four full 128-byte lines), then patches
+//       the seven non-zero channels of the rows that have an owner while the lines
+//       are still in L2 -- DRAM sees every byte exactly once, there is no separate
+//       memset pass over the tensor.  The per-row owner codes of a tile arrive in
+//       one coalesced load, prefetched a tile ahead.  HBM-bound: algorithmic bytes =
 //       cells*D*4 written + 20 B/box read.
 //
 // All arithmetic that decides an integer (anchor, layer, cell, skip) uses IEEE
@@ -213,25 +213,13 @@ template <int VEC> struct VecT;
 template <> struct VecT<4> { using type = float4; };
 template <> struct VecT<1> { using type = float; };
 
-template <int VEC>
-__device__ __forceinline__ typename VecT<VEC>::type
-make_units(const BoxRec& r, int code, int ch0)
+// n-th (0-based, n < 4) set bit of m, or 32 if m has fewer
+__device__ __forceinline__ unsigned nth_bit(unsigned m, int n)
 {
-    float v[VEC];
-    const int nb = code & 15;
     #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-        const int ch = ch0 + j;
-        float x;
-        if (ch == 0)      x = (float)__dadd_rn((double)(1 - nb / 3), r.fx);   // -dx + fx, :3467
-        else if (ch == 1) x = (float)__dadd_rn((double)(1 - nb % 3), r.fy);   // -dy + fy
-        else if (ch == 2) x = r.tw;
-        else if (ch == 3) x = r.th;
-        else x = (ch == 4 || ch == r.hot_anchor || ch == r.hot_class) ? 1.0f : 0.0f;
-        v[j] = x;
-    }
-    if constexpr (VEC == 4) return make_float4(v[0], v[1], v[2], v[3]);
-    else return v[0];
+    for (int q = 0; q < 3; ++q)
+        if (q < n) m &= m - 1;
+    return m ? (unsigned)(__ffs((int)m) - 1) : 32u;
 }
 
 template <int VEC>
@@ -252,7 +240,7 @@ encode_fill_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__
         while (l + 1 < g.L && tile >= p.tile_first[l + 1]) ++l;
         return l;
     };
-    // owner code of row `lane` of a tile (-1 beyond the layer's last row)
+    // owner code of row `lane` of a tile (-1 beyond the tile / the layer's last row)
     auto load_codes = [&](long long tile) {
         if (tile >= total) return -1;
         const int l = tile_layer(tile);
@@ -271,20 +259,39 @@ encode_fill_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__
         const long long left = p.rows[l] - row0;
         const int n_rows = (int)(left < p.R[l] ? left : p.R[l]);
         const int n_units = n_rows * dv;
+
+        // ---- pass 1: the whole tile as zeros, 32 consecutive units per warp store --------
         V* dst = reinterpret_cast<V*>(a.y[l]) + row0 * dv;
-        // unit f = lane + 32*step lies in row r, column `part`; both advance without a division
-        int r = lane / dv, part = lane - r * dv;
-        const int inc_r = 32 / dv, inc_p = 32 - inc_r * dv;
-        const int steps = (n_units + 31) >> 5;
-        for (int st = 0, f = lane; st < steps; ++st, f += 32) {
-            const int code = __shfl_sync(0xffffffffu, codes, r & 31);
-            if (f < n_units) {
-                V v = zero;
-                if (code >= 0) v = make_units<VEC>(a.recs[code >> 4], code, part * VEC);
-                __stcs(dst + f, v);
+        #pragma unroll 4
+        for (int f = lane; f < n_units; f += 32) dst[f] = zero;
+
+        // ---- pass 2: patch the rows that have an owner (7 scalars each) -----------------
+        // The lines were just written by this warp and are still in L2, so the patch
+        // merges there: DRAM sees every byte once.  Four rows per sweep, 8 lanes each.
+        unsigned pos = __ballot_sync(0xffffffffu, codes >= 0);
+        if (pos) {
+            __syncwarp();                                  // order the patches after the zeros
+            const int slot = lane >> 3, role = lane & 7;
+            float* ybase = a.y[l] + row0 * (long long)g.D[l];
+            while (pos) {
+                const unsigned r = nth_bit(pos, slot);
+                const int code = __shfl_sync(0xffffffffu, codes, r & 31);
+                if (r < 32u && role < 7) {
+                    const BoxRec* rec = a.recs + (code >> 4);
+                    const int nb = code & 15;
+                    int ch = role;
+                    float v = 1.0f;
+                    if (role == 0)      v = (float)__dadd_rn((double)(1 - nb / 3), rec->fx);   // -dx + fx, :3467
+                    else if (role == 1) v = (float)__dadd_rn((double)(1 - nb % 3), rec->fy);   // -dy + fy
+                    else if (role == 2) v = rec->tw;
+                    else if (role == 3) v = rec->th;
+                    else if (role == 5) ch = rec->hot_anchor;                                  // :3469
+                    else if (role == 6) ch = rec->hot_class;                                   // :3470
+                    ybase[(long long)r * g.D[l] + ch] = v;
+                }
+                #pragma unroll
+                for (int q = 0; q < 4; ++q) pos &= pos - 1;
             }
-            part += inc_p; r += inc_r;
-            if (part >= dv) { part -= dv; ++r; }
         }
     }
 }
@@ -325,9 +332,17 @@ cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
         tiles += (p.rows[l] + p.R[l] - 1) / p.R[l];
     }
     p.tile_first[g.L] = tiles;
+    // One tile per warp and no persistent loop: on B200 a write-only stream reaches
+    // ~7.5 TB/s with hundreds of thousands of short-lived CTAs but only ~6 TB/s from a
+    // single resident wave looping over the same bytes (scripts/probes/fill_probe.cu).
     long long blocks = (tiles * 32 + kFillThreads - 1) / kFillThreads;
-    const long long max_blocks = (long long)num_sms * (2048 / kFillThreads);   // one full wave
-    if (blocks > max_blocks) blocks = max_blocks;
+    static int env_waves = -1;
+    if (env_waves < 0) { const char* e = getenv("MGD_FILL_MAX_WAVES"); env_waves = e ? atoi(e) : 0; }
+    if (env_waves > 0) {
+        const long long max_blocks = (long long)num_sms * (2048 / kFillThreads) * env_waves;
+        if (blocks > max_blocks) blocks = max_blocks;
+    }
+    if (blocks > 0x7fffffffll) blocks = 0x7fffffffll;
     if (blocks < 1) blocks = 1;
     prof_mark_begin(PROF_ENCODE_FILL, stream);
     if (vec4) encode_fill_kernel<4><<<(unsigned)blocks, kFillThreads, 0, stream>>>(a, p);

@@ -61,6 +61,13 @@ __device__ __forceinline__ bool suppresses(const BoxD& a, const BoxD& b, double 
     return !(m < thr);
 }
 
+// float32 box that contains the float64 box: [x1, y1, x2, y2] rounded outward
+__device__ __forceinline__ float4 outer_box(const BoxD& b)
+{
+    return make_float4(__double2float_rd(b.x), __double2float_rd(b.y),
+                       __double2float_ru(__dadd_rn(b.x, b.w)), __double2float_ru(__dadd_rn(b.y, b.h)));
+}
+
 // order-preserving map double -> u64, inverted so an ascending sort = descending score
 __device__ __forceinline__ unsigned long long score_key(double s)
 {
@@ -80,6 +87,7 @@ nms_kernel(const __grid_constant__ NmsArgs a)
     __shared__ unsigned long long s_key[kSortSmem];
     __shared__ unsigned long long s_val[kSortSmem];
     __shared__ BoxD c_box[kChunk];
+    __shared__ float4 c_out[kChunk];          // float32 outer box [x1, y1, x2, y2] (rounded outward)
     __shared__ int c_cls[kChunk];
     __shared__ int c_pos[kChunk];
     __shared__ int c_alive[kChunk];
@@ -90,10 +98,12 @@ nms_kernel(const __grid_constant__ NmsArgs a)
     const int b = blockIdx.x;
     unsigned char* kept_mem = a.kept_scratch ? a.kept_scratch + (size_t)b * a.kept_scratch_stride : dyn;
     BoxD* k_box = reinterpret_cast<BoxD*>(kept_mem);                // [max_boxes]
-    int* k_cls = reinterpret_cast<int*>(k_box + a.max_boxes);       // [max_boxes]
+    float4* k_out = reinterpret_cast<float4*>(k_box + a.max_boxes); // [max_boxes]
+    int* k_cls = reinterpret_cast<int*>(k_out + a.max_boxes);       // [max_boxes]
 
     const int tid = threadIdx.x;
     const int M = a.counts[b];
+    if (a.skip_small && M <= a.skip_small) return;     // nms_warp_kernel handled this image
     const Cand* cand = a.cand ? a.cand + (size_t)b * a.cap : nullptr;
     const BoxD* boxes = a.cand ? a.boxes + (size_t)b * a.cap
                                : reinterpret_cast<const BoxD*>(a.in_boxes);
@@ -167,26 +177,50 @@ nms_kernel(const __grid_constant__ NmsArgs a)
             c_alive[tid] = tid < n;
             if (tid < n) {
                 const int pos = (int)(val[c0 + tid] & 0xffffffffu);
-                c_box[tid] = boxes[pos];
+                const BoxD bx = boxes[pos];
+                c_box[tid] = bx;
+                c_out[tid] = outer_box(bx);
                 c_cls[tid] = cand ? cand[pos].cls : (a.in_classes ? a.in_classes[pos] : 0);
                 c_pos[tid] = pos;
             }
         }
         __syncthreads();
+        // Pair tests: thread (member = tid % 64, group = tid / 64); the member's box stays
+        // in registers, the other box is a shared-memory broadcast.  A float32 test on
+        // outward-rounded boxes discards disjoint pairs (the vast majority) before any
+        // float64 arithmetic: disjoint outer boxes imply disjoint boxes, for which the
+        // metric is <= 0 < threshold.
+        const int mem = tid & (kChunk - 1);
+        const int grp = tid / kChunk;
+        constexpr int kGroups = kThreads / kChunk;
+        const bool pretest = a.thr > 0.0;
         // a. suppression by boxes kept in earlier chunks
-        for (int p = tid; p < n * kept; p += kThreads) {
-            const int c = p % n, k = p / n;
-            if (!c_alive[c]) continue;
-            if (a.per_class && k_cls[k] != c_cls[c]) continue;
-            if (suppresses(k_box[k], c_box[c], a.thr, diou)) c_alive[c] = 0;
+        if (mem < n) {
+            const BoxD cb = c_box[mem];
+            const float4 co = c_out[mem];
+            const int ccls = c_cls[mem];
+            bool dead = false;
+            for (int k = grp; k < kept && !dead; k += kGroups) {
+                if (a.per_class && k_cls[k] != ccls) continue;
+                const float4 ko = k_out[k];
+                if (pretest && (ko.z <= co.x || co.z <= ko.x || ko.w <= co.y || co.w <= ko.y)) continue;
+                dead = suppresses(k_box[k], cb, a.thr, diou);
+            }
+            if (dead) c_alive[mem] = 0;
         }
         __syncthreads();
         // b. intra-chunk mask: bit j of c_mask[i] <=> i (earlier) suppresses j (later)
-        for (int p = tid; p < n * n; p += kThreads) {
-            const int i = p / n, j = p % n;
-            if (j <= i || !c_alive[i] || !c_alive[j]) continue;
-            if (a.per_class && c_cls[i] != c_cls[j]) continue;
-            if (suppresses(c_box[i], c_box[j], a.thr, diou)) atomicOr(&c_mask[i], 1ull << j);
+        if (mem < n && c_alive[mem]) {
+            const BoxD cb = c_box[mem];
+            const float4 co = c_out[mem];
+            const int ccls = c_cls[mem];
+            for (int i = grp; i < mem; i += kGroups) {
+                if (!c_alive[i]) continue;
+                if (a.per_class && c_cls[i] != ccls) continue;
+                const float4 io = c_out[i];
+                if (pretest && (io.z <= co.x || co.z <= io.x || io.w <= co.y || co.w <= io.y)) continue;
+                if (suppresses(c_box[i], cb, a.thr, diou)) atomicOr(&c_mask[i], 1ull << mem);
+            }
         }
         __syncthreads();
         // c. sequential resolve on registers, one warp
@@ -213,6 +247,7 @@ nms_kernel(const __grid_constant__ NmsArgs a)
             const int i = c_new[tid];
             const int slot = kept + tid;
             k_box[slot] = c_box[i];
+            k_out[slot] = c_out[i];
             k_cls[slot] = c_cls[i];
             const BoxD cd = c_box[i];
             const int pos = c_pos[i];
@@ -255,6 +290,236 @@ nms_kernel(const __grid_constant__ NmsArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Warp-per-image variant for the common case (decode mode, <= kWarpCap candidates,
+// kept list small enough for shared memory).  Same algorithm as nms_kernel with
+// chunks of 32, but everything is warp-synchronous: no CTA barrier, the intra-chunk
+// mask is built with ballots and lives in registers, and several images share a CTA.
+// Images it does not take (too many candidates) are left to nms_kernel.
+// ---------------------------------------------------------------------------------
+constexpr int kWarpCapSmall = 512;     // candidates per image handled by one warp (first launch)
+constexpr int kWarpCapLarge = 1024;    // ... and by the second launch
+constexpr int kWarpsPerCtaW = 4;
+
+__host__ __device__ inline size_t nms_warp_bytes(int cap, int kept_cap)
+{
+    // kept boxes BoxD[kept_cap] | keys u64[cap] | kept outer boxes float4[kept_cap]
+    // | kept class int[kept_cap] | sorted position u16[cap]
+    const size_t b = (size_t)kept_cap * 32 + (size_t)cap * 8 + (size_t)kept_cap * (16 + 4) + (size_t)cap * 2;
+    return (b + 15) & ~(size_t)15;
+}
+
+struct WarpEmit {
+    const NmsArgs* a; int b; const Cand* cand; const BoxD* boxes; double W, H;
+};
+
+template <int kWarpCap>
+__global__ void __launch_bounds__(kWarpsPerCtaW * 32)
+nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
+{
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ uint64_t s_tab[MGD_EXP2F_N];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x < MGD_EXP2F_N) s_tab[threadIdx.x] = mgd_exp2f_tab[threadIdx.x];
+    __syncthreads();
+
+    // per-warp shared memory: kept list (float64 + outer float32 boxes, class), sort
+    // keys and payload
+    unsigned char* mine = dyn + (size_t)warp * nms_warp_bytes(kWarpCap, kept_cap);
+    BoxD* k_box = reinterpret_cast<BoxD*>(mine);
+    unsigned long long* key = reinterpret_cast<unsigned long long*>(k_box + kept_cap);
+    float4* k_out = reinterpret_cast<float4*>(key + kWarpCap);
+    int* k_cls = reinterpret_cast<int*>(k_out + kept_cap);
+    unsigned short* pos_of = reinterpret_cast<unsigned short*>(k_cls + kept_cap);
+
+    const HeadGeom& g = a.g;
+    const bool diou = a.use_diou != 0;
+    const bool pretest = a.thr > 0.0;
+    const int n_warps = gridDim.x * kWarpsPerCtaW;
+
+    (void)n_warps;
+    // Images are handed out dynamically (per-image cost varies by more than 10x), the
+    // expensive ones first: phase 0 takes the images with more than `min_count`
+    // candidates, phase 1 the rest, so light images fill the tail of the heavy ones.
+    int phase = 0;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(a.next_image + phase, 1);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= a.B) {
+            if (phase == 1) break;
+            phase = 1;
+            continue;
+        }
+        const int M = a.counts[b];
+        if (M > kWarpCap) continue;                      // nms_kernel takes this image
+        if ((M > min_count) != (phase == 0)) continue;   // the other phase takes it
+        const Cand* cand = a.cand + (size_t)b * a.cap;
+        BoxD* boxes = a.boxes + (size_t)b * a.cap;
+        const int ih = a.image_hw ? a.image_hw[2 * b] : a.in_h;
+        const int iw = a.image_hw ? a.image_hw[2 * b + 1] : a.in_w;
+
+        // ---- 0. boxes + keys, lane-strided ------------------------------------------
+        int mpad = 32;
+        while (mpad < M) mpad <<= 1;
+        {
+            const Letterbox lb = letterbox_consts(g.in_h, g.in_w, ih, iw);
+            for (int i = lane; i < mpad; i += 32) {
+                if (i < M) {
+                    const Cand cd = cand[i];
+                    int layer = 0;
+                    while (layer + 1 < g.L && cd.index >= g.cell_off[layer + 1]) ++layer;
+                    const int cell = cd.index - g.cell_off[layer];
+                    const int rr = cell / g.gw[layer], cc = cell - rr * g.gw[layer];
+                    BoxD bx;
+                    decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 0, s_tab, bx.x, bx.w);
+                    decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 1, s_tab, bx.y, bx.h);
+                    boxes[i] = bx;
+                    // scores are non-negative floats: their bit patterns order like the values
+                    key[i] = ((unsigned long long)(~__float_as_uint(cd.score)) << 32) | (unsigned)cd.index;
+                    pos_of[i] = (unsigned short)i;
+                } else {
+                    key[i] = ~0ull;
+                    pos_of[i] = 0xffff;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- 1. bitonic sort (score desc, cell index asc) ----------------------------
+        for (int k = 2; k <= mpad; k <<= 1) {
+            for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                for (int t = lane; t < (mpad >> 1); t += 32) {
+                    // t-th compare-exchange of this stage: i has bit jj clear
+                    const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
+                    const int p = i | jj;
+                    const unsigned long long ka = key[i], kb = key[p];
+                    const bool up = (i & k) == 0;
+                    if ((kb < ka) == up) {
+                        key[i] = kb; key[p] = ka;
+                        const unsigned short pa = pos_of[i]; pos_of[i] = pos_of[p]; pos_of[p] = pa;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- 2. chunked greedy pass, 32 candidates per chunk ---------------------------
+        int kept = 0;
+        const double W = (double)iw, H = (double)ih;
+        for (int c0 = 0; c0 < M && kept < a.max_boxes; c0 += 32) {
+            const int n = min(32, M - c0);
+            const bool have = lane < n;
+            int pos = 0, ccls = 0;
+            BoxD cb = {0.0, 0.0, 0.0, 0.0};
+            float4 co = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (have) {
+                pos = pos_of[c0 + lane];
+                cb = boxes[pos];
+                co = outer_box(cb);
+                ccls = cand[pos].cls;
+            }
+            // a. suppression by boxes kept in earlier chunks.  Two passes so the lanes never
+            //    diverge into the float64 metric one at a time: (1) a uniform sweep with the
+            //    float32 outer-box test records, per lane, which kept boxes might overlap
+            //    (128 kept boxes per sweep); (2) all lanes evaluate their next pending kept
+            //    box together, in kept order, until a lane is suppressed or runs out.
+            bool alive = have;
+            for (int k0 = 0; k0 < kept; k0 += 128) {
+                const int kn = min(128, kept - k0);
+                unsigned long long pend_lo = 0, pend_hi = 0;
+                #pragma unroll 4
+                for (int k = 0; k < kn; ++k) {
+                    const float4 ko = k_out[k0 + k];
+                    bool cand_pair = alive && !(a.per_class && k_cls[k0 + k] != ccls);
+                    if (pretest && (ko.z <= co.x || co.z <= ko.x || ko.w <= co.y || co.w <= ko.y))
+                        cand_pair = false;
+                    if (cand_pair) { if (k < 64) pend_lo |= 1ull << k; else pend_hi |= 1ull << (k - 64); }
+                }
+                while (__any_sync(0xffffffffu, alive && (pend_lo | pend_hi))) {
+                    if (alive && (pend_lo | pend_hi)) {
+                        int k;
+                        if (pend_lo) { k = __ffsll((long long)pend_lo) - 1; pend_lo &= pend_lo - 1; }
+                        else { k = 64 + __ffsll((long long)pend_hi) - 1; pend_hi &= pend_hi - 1; }
+                        if (suppresses(k_box[k0 + k], cb, a.thr, diou)) alive = false;
+                    }
+                }
+            }
+            // b. intra-chunk: lane j collects the set of EARLIER alive members that suppress
+            //    it (same two passes; the outer boxes travel by shuffle)
+            const unsigned live0 = __ballot_sync(0xffffffffu, alive);
+            unsigned pend = 0;
+            for (int i = 0; i < n - 1; ++i) {
+                if (!((live0 >> i) & 1u)) continue;               // warp-uniform
+                const float ox = __shfl_sync(0xffffffffu, co.x, i), oy = __shfl_sync(0xffffffffu, co.y, i);
+                const float oz = __shfl_sync(0xffffffffu, co.z, i), ow = __shfl_sync(0xffffffffu, co.w, i);
+                const int icls = __shfl_sync(0xffffffffu, ccls, i);
+                if (alive && lane > i && !(a.per_class && icls != ccls) &&
+                    !(pretest && (oz <= co.x || co.z <= ox || ow <= co.y || co.w <= oy)))
+                    pend |= 1u << i;
+            }
+            unsigned sup_by = 0;                                  // earlier members suppressing me
+            while (__any_sync(0xffffffffu, pend != 0)) {
+                if (pend) {
+                    const int i = __ffs((int)pend) - 1;
+                    pend &= pend - 1;
+                    const BoxD ib = boxes[pos_of[c0 + i]];
+                    if (suppresses(ib, cb, a.thr, diou)) sup_by |= 1u << i;
+                }
+            }
+            // c. sequential resolve: a kept member kills every later member it suppresses
+            unsigned live = live0, keep_bits = 0;
+            int k = kept;
+            while (live && k < a.max_boxes) {
+                const int i = __ffs((int)live) - 1;
+                const unsigned killed = __ballot_sync(0xffffffffu, (sup_by >> i) & 1u);
+                live &= ~(1u << i);
+                live &= ~killed;
+                keep_bits |= 1u << i;
+                ++k;
+            }
+            // 3. emit
+            if ((keep_bits >> lane) & 1u) {
+                const int slot = kept + __popc(keep_bits & ((1u << lane) - 1u));
+                k_box[slot] = cb; k_out[slot] = co; k_cls[slot] = ccls;
+                const size_t o = (size_t)b * a.max_boxes + slot;
+                if (a.out_xywh) {
+                    a.out_xywh[o * 4 + 0] = cb.x; a.out_xywh[o * 4 + 1] = cb.y;
+                    a.out_xywh[o * 4 + 2] = cb.w; a.out_xywh[o * 4 + 3] = cb.h;
+                }
+                if (a.out_xyxy) {
+                    a.out_xyxy[o * 4 + 0] = (int)floor(__dadd_rn(clipd(cb.x, 0.0, W), 0.5));
+                    a.out_xyxy[o * 4 + 1] = (int)floor(__dadd_rn(clipd(cb.y, 0.0, H), 0.5));
+                    a.out_xyxy[o * 4 + 2] = (int)floor(__dadd_rn(clipd(__dadd_rn(cb.x, cb.w), 0.0, W), 0.5));
+                    a.out_xyxy[o * 4 + 3] = (int)floor(__dadd_rn(clipd(__dadd_rn(cb.y, cb.h), 0.0, H), 0.5));
+                }
+                if (a.out_scores) a.out_scores[o] = (double)cand[pos].score;
+                if (a.out_classes) a.out_classes[o] = ccls;
+                if (a.out_index) a.out_index[o] = cand[pos].index;
+            }
+            kept = k;
+            __syncwarp();
+        }
+        // ---- padding + counts -------------------------------------------------------------
+        for (int q = kept + lane; q < a.max_boxes; q += 32) {
+            const size_t o = (size_t)b * a.max_boxes + q;
+            if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = 0.0;
+            if (a.out_xyxy) for (int e = 0; e < 4; ++e) a.out_xyxy[o * 4 + e] = 0;
+            if (a.out_scores) a.out_scores[o] = 0.0;
+            if (a.out_classes) a.out_classes[o] = -1;
+            if (a.out_index) a.out_index[o] = -1;
+        }
+        if (lane == 0) {
+            a.out_counts[b] = kept;
+            if (a.stats) {
+                atomicAdd(&a.stats[0], (unsigned long long)M);
+                atomicAdd(&a.stats[1], (unsigned long long)kept);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void keep_from_index_kernel(const int* index, const int* counts, int max_keep,
                                        int* keep, int* n_keep)
 {
@@ -267,15 +532,38 @@ __global__ void keep_from_index_kernel(const int* index, const int* counts, int 
 }  // namespace
 
 int nms_smem_capacity() { return kSortSmem; }
-size_t nms_kept_bytes(int max_boxes) { return (size_t)max_boxes * (sizeof(BoxD) + sizeof(int)) + 16; }
+size_t nms_kept_bytes(int max_boxes) { return (size_t)max_boxes * (sizeof(BoxD) + sizeof(float4) + sizeof(int)) + 16; }
 
-cudaError_t launch_nms(const NmsArgs& a, int, cudaStream_t stream)
+cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
 {
-    const size_t dyn = a.kept_scratch ? 16 : nms_kept_bytes(a.max_boxes);
-    cudaError_t err = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)dyn);
-    if (err != cudaSuccess) return err;
+    NmsArgs a = a_in;
+    cudaError_t err;
     prof_mark_begin(PROF_NMS, stream);
+    // decode mode with a kept list that fits shared memory: warp-per-image kernels first,
+    // a lean instance for images with <= 512 candidates and one for 513..1024
+    static int env_off = -1;
+    if (env_off < 0) { const char* e = getenv("MGD_NMS_NO_WARP_KERNEL"); env_off = e ? atoi(e) : 0; }
+    if (a.cand && nms_warp_bytes(kWarpCapLarge, a.max_boxes) <= 32 * 1024 && !env_off) {
+        auto run = [&](auto kernel, int cap, int min_count) -> cudaError_t {
+            const size_t dyn = nms_warp_bytes(cap, a.max_boxes) * kWarpsPerCtaW;
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) return e;
+            int ctas_per_sm = (int)((220 * 1024) / (dyn + 1024));
+            if (ctas_per_sm > 16) ctas_per_sm = 16;
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+            long long grid = ((long long)a.B + kWarpsPerCtaW - 1) / kWarpsPerCtaW;
+            const long long cap_grid = (long long)num_sms * ctas_per_sm;
+            if (grid > cap_grid) grid = cap_grid;
+            kernel<<<(unsigned)grid, kWarpsPerCtaW * 32, dyn, stream>>>(a, a.max_boxes, min_count);
+            return cudaGetLastError();
+        };
+        err = run(nms_warp_kernel<kWarpCapLarge>, kWarpCapLarge, kWarpCapLarge / 4);
+        if (err != cudaSuccess) return err;
+        a.skip_small = kWarpCapLarge;
+    }
+    const size_t dyn = a.kept_scratch ? 16 : nms_kept_bytes(a.max_boxes);
+    err = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (err != cudaSuccess) return err;
     nms_kernel<<<a.B, kThreads, dyn, stream>>>(a);
     prof_mark_end(PROF_NMS, stream);
     return cudaGetLastError();

@@ -1,11 +1,11 @@
-"""Aggregate `ncu --page source --print-source cuda,sass --csv` samples per CUDA source line."""
+"""Aggregate `ncu --page source --print-source cuda,sass --csv` per CUDA source line.
+usage: ncu_lines.py file.csv [top_n] [sort: inst|samples]"""
 import csv, sys, collections
 path = sys.argv[1]
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+key = sys.argv[3] if len(sys.argv) > 3 else "inst"
 rows = list(csv.reader(open(path)))
-files = {}
-cur = None
-hdr = None
+cur = None; hdr = None; line = None
 agg = collections.defaultdict(lambda: [0.0, 0.0, ""])
 def f(v):
     try: return float(v.replace(',', ''))
@@ -16,12 +16,12 @@ for r in rows:
     if r[0] == "Function Name": continue
     if r[0] == "Line No": hdr = r; si = hdr.index("# Samples"); ii = hdr.index("Instructions Executed"); continue
     if hdr is None or len(r) <= si: continue
-    if r[0].strip():            # a source line row: remember it
-        line = (cur, r[0]); src = r[1]
-        agg[line][2] = src.strip()
-    if len(r) > 2 and r[2].strip():   # sass row under current line
+    if r[0].strip():
+        line = (cur, int(r[0])); agg[line][2] = r[1].strip()
+    elif len(r) > 2 and r[2].strip() and line is not None:     # a SASS row under the current line
         agg[line][0] += f(r[si]); agg[line][1] += f(r[ii])
-tot = sum(v[0] for v in agg.values())
-print("total samples", tot)
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top_n]:
-    print(f"{v[0]:8.0f} {100*v[0]/tot:5.1f}%  inst {v[1]:12.0f}  {k[0]}:{k[1]}  {v[2][:100]}")
+tot_i = sum(v[1] for v in agg.values()) or 1; tot_s = sum(v[0] for v in agg.values()) or 1
+print(f"total warp-instructions {tot_i:.0f}  samples {tot_s:.0f}")
+k = 1 if key == "inst" else 0
+for kk, v in sorted(agg.items(), key=lambda kv: -kv[1][k])[:top_n]:
+    print(f"{100*v[1]/tot_i:5.1f}% inst {100*v[0]/tot_s:5.1f}% smp  {kk[0]}:{kk[1]}  {v[2][:100]}")
