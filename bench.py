@@ -143,6 +143,13 @@ def _cpu_inputs(n_images, seed=0):
     return anchors, boxes, preds
 
 
+_SHARDS = []          # filled before the worker pool forks: inputs are inherited, not pickled
+
+
+def _cpu_worker_indexed(i):
+    return _cpu_worker(_SHARDS[i])
+
+
 def _cpu_worker(args):
     boxes, preds = args
     import numpy as np
@@ -175,18 +182,18 @@ def run_reference(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_worker = 4
+    per_worker = 8
     n_images = cores * per_worker
     _, boxes, preds = _cpu_inputs(n_images)
-    shards = [(boxes[i * per_worker:(i + 1) * per_worker],
-               [p[i * per_worker:(i + 1) * per_worker] for p in preds]) for i in range(cores)]
+    _SHARDS[:] = [(boxes[i * per_worker:(i + 1) * per_worker],
+                   [p[i * per_worker:(i + 1) * per_worker] for p in preds]) for i in range(cores)]
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
-            pool.map(_cpu_worker, shards)
+            pool.map(_cpu_worker_indexed, range(cores), chunksize=1)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_cpu_worker, shards)
+            pool.map(_cpu_worker_indexed, range(cores), chunksize=1)
         dt = time.perf_counter() - t0
     value = n_images * args.steps / dt
     line = {

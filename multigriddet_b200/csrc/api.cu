@@ -231,11 +231,15 @@ int encode_device(const HeadGeom& g, const float* boxes, int batch, int N, float
             a.y[l] = y[l] + (size_t)b0 * g.gh[l] * g.gw[l] * g.D[l];
         a.status = d_status;
         a.stats = d_stats;
+        a.big_tables = nullptr;
+        if (encode_needs_big_tables(g, N))
+            CUDA_TRY(cudaMallocAsync(&a.big_tables, (size_t)nb * 2 * g.cells * sizeof(int), stream));
         CUDA_TRY(cudaMallocAsync(&a.table, (size_t)nb * g.cells * sizeof(int), stream));
         CUDA_TRY(cudaMallocAsync(&a.recs, (size_t)nb * (N > 0 ? N : 1) * sizeof(BoxRec), stream));
         CUDA_TRY(launch_encode(a, num_sms, stream));
         CUDA_TRY(cudaFreeAsync(a.table, stream));
         CUDA_TRY(cudaFreeAsync(a.recs, stream));
+        if (a.big_tables) CUDA_TRY(cudaFreeAsync(a.big_tables, stream));
     }
     return MGD_OK;
 }
@@ -433,10 +437,6 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
         return fail(MGD_ERR_UNSUPPORTED, "max_boxes per image must be <= 65000, got %d", max_boxes);
     if ((long long)chunk_images(g, batch > 0 ? batch : 1) * max_boxes >= (1ll << 27))
         return fail(MGD_ERR_UNSUPPORTED, "batch chunk x max_boxes too large");
-    if (encode_assign_smem_bytes(g, max_boxes) > 220 * 1024)
-        return fail(MGD_ERR_UNSUPPORTED,
-                    "%d cells + %d boxes per image do not fit the 227 KB shared memory of one SM",
-                    g.cells, max_boxes);
     int num_sms;
     if ((rc = prepare_device(device, &num_sms))) return rc;
     if (stats) memset(stats, 0, 4 * sizeof(long long));

@@ -38,6 +38,7 @@ struct EncodeArgs {
     const float* boxes;               // (B, N, 5)
     float* y[MGD_MAX_LAYERS];         // (B, gh, gw, D)
     int* table;                       // layer-major owner table: [l][b][cell]
+    int* big_tables;                  // (B, 2, cells) scratch when the tables exceed shared memory, else nullptr
     BoxRec* recs;                     // (B, N)
     int* status;                      // bit0: class >= C, bit1: negative class on a valid box
     unsigned long long* stats;        // [valid boxes, skipped writes, positive cells, -]
@@ -106,6 +107,7 @@ cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
 cudaError_t launch_decode(const DecodeArgs& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_nms(const NmsArgs& a, int num_sms, cudaStream_t stream);
 size_t encode_assign_smem_bytes(const HeadGeom& g, int N);
+bool encode_needs_big_tables(const HeadGeom& g, int N);
 int nms_smem_capacity();
 size_t nms_kept_bytes(int max_boxes);
 cudaError_t launch_decode_dense(const DecodeArgs& a, const int* image_hw, double* out,

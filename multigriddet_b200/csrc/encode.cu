@@ -80,9 +80,12 @@ encode_assign_kernel(const __grid_constant__ EncodeArgs a)
 {
     extern __shared__ int sm[];
     const HeadGeom& g = a.g;
-    int* cover = sm;                    // [cells]
-    int* owner = sm + g.cells;          // [cells]
-    int* place = owner + g.cells;       // [N]
+    // the two per-cell tables live in shared memory; heads too large for that (e.g. a
+    // stride-2 layer) fall back to a per-image slice of global scratch (L2-resident)
+    const bool big = a.big_tables != nullptr;
+    int* cover = big ? a.big_tables + (size_t)blockIdx.x * 2 * g.cells : sm;   // [cells]
+    int* owner = cover + g.cells;                                            // [cells]
+    int* place = big ? sm : owner + g.cells;                                 // [N]
     __shared__ unsigned int s_stat[3];
     __shared__ int s_status;
 
@@ -303,10 +306,15 @@ size_t encode_assign_smem_bytes(const HeadGeom& g, int N)
     return (size_t)(2 * g.cells + N) * sizeof(int);
 }
 
+bool encode_needs_big_tables(const HeadGeom& g, int N)
+{
+    return encode_assign_smem_bytes(g, N) > 200 * 1024;
+}
+
 cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
 {
     const HeadGeom& g = a.g;
-    const size_t smem = encode_assign_smem_bytes(g, a.N);
+    const size_t smem = a.big_tables ? (size_t)a.N * sizeof(int) + 16 : encode_assign_smem_bytes(g, a.N);
     cudaError_t err = cudaFuncSetAttribute(encode_assign_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;

@@ -354,3 +354,86 @@ def test_full_size_encode_decode_round_trip(c_oracle):
     ref = c_oracle.decode_nms([p[:32].cpu().numpy() for p in preds], [(S, S)], (S, S), anchors, C, **kw)
     assert np.array_equal(ref["index"], index[:32])
     assert np.array_equal(ref["scores"], scores[:32])
+
+
+# ------------------------------------------------------------------------------
+# rarely taken kernel paths
+# ------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("max_boxes", [500, 3000])
+def test_decode_large_max_boxes_paths(c_oracle, max_boxes):
+    """max_boxes = 500: kept list too large for the warp-per-image kernel -> CTA kernel;
+    3000: kept list in global scratch.  Dense-random heads so that many boxes are kept."""
+    S, C, B = 608, 80, 2
+    anchors = synth.coco_anchors(np.float32)
+    preds = [p.numpy() for p in synth.dense_random_head_outputs(B, S, 3, C, seed=5)]
+    kw = dict(max_boxes=max_boxes, confidence=0.02, nms_threshold=0.45, nms_method="diou")
+    ref = c_oracle.decode_nms(preds, [(S, S)], (S, S), anchors, C, **kw)
+    got = engine.decode_nms(preds, (S, S), (S, S), anchors, C, **kw)
+    assert int(ref["counts"].min()) > 100
+    same, bits_off = _compare_detections(got, ref, B)
+    assert same == B and bits_off == 0
+
+
+def test_decode_mixed_candidate_counts_one_launch(c_oracle):
+    """Images with 0, a few, ~500 and ~7500 candidates in one batch: every NMS tier
+    (warp kernel phases, CTA kernel with shared / global sort) runs in the same call."""
+    import torch
+    S, C = 608, 80
+    anchors = synth.coco_anchors(np.float32)
+    planted = _planted(3, 3, S, C, 100, anchors, c_oracle)
+    dense = [p.numpy() for p in synth.dense_random_head_outputs(2, S, 3, C, seed=9)]
+    quiet = [np.full((1, g, g, 88), -20.0, dtype=np.float32) for g in (19, 38, 76)]
+    preds = [np.concatenate([q, a, d], 0) for q, a, d in zip(quiet, planted, dense)]
+    B = preds[0].shape[0]
+    kw = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method="diou")
+    shapes = synth.image_shapes(5, B)
+    ref = c_oracle.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+    got = engine.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+    assert ref["n_candidates"][0] == 0 and ref["n_candidates"][-1] > 7000
+    same, bits_off = _compare_detections(got, ref, B)
+    assert same == B and bits_off == 0
+
+
+def test_encode_many_boxes_large_input(c_oracle):
+    """800 boxes per image (the reference's 8x capacity expansion) at S = 672."""
+    S, C, N, B = 672, 80, 800, 3
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(23, B, N, S, C, layout="mosaic", corners="frac", min_boxes=700)
+    ref, rstats = c_oracle.encode_targets(boxes, (S, S), anchors, C, return_stats=True)
+    got, gstats = engine.encode_targets(boxes, (S, S), anchors, C, return_stats=True)
+    _assert_encode_equal(got, ref)
+    assert gstats["n_skipped_writes"] == rstats["n_skipped_writes"] > 1000
+
+
+def test_encode_five_layers_and_custom_grids(c_oracle):
+    """All five strides the reference knows (generators.py:3423) and explicit grid_shapes."""
+    S, C = 640, 12
+    anchors = [np.array(a, dtype=np.float32) for a in
+               (((300, 280),), ((150, 120), (100, 200)), ((60, 50), (40, 80), (80, 40)),
+                ((20, 25), (30, 15)), ((8, 8), (12, 6), (6, 12), (4, 4)))]
+    boxes = synth.synth_boxes(2, 4, 60, S, C, anchors=anchors)
+    ref = c_oracle.encode_targets(boxes, (S, S), anchors, C)
+    got = engine.encode_targets(boxes, (S, S), anchors, C)
+    assert [g.shape[1] for g in got] == [20, 40, 80, 160, 320]
+    _assert_encode_equal(got, ref)
+    grids = [(10, 10), (20, 20), (40, 40), (80, 80), (160, 160)]
+    ref = c_oracle.encode_targets(boxes, (S, S), anchors, C, grid_shapes=grids)
+    got = engine.encode_targets(boxes, (S, S), anchors, C, grid_shapes=grids)
+    _assert_encode_equal(got, ref)
+
+
+def test_async_device_calls_and_deferred_status():
+    import torch
+    S, C = 608, 80
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(1, 4, 20, S, C)
+    d = torch.from_numpy(boxes).cuda()
+    y = engine.encode_targets(d, (S, S), anchors, C, sync=False)
+    engine.poll_status()                                  # nothing wrong: no exception
+    assert int(y[2][..., 4].sum().item()) > 0
+    bad = boxes.copy(); bad[0, 0, 4] = 99
+    engine.encode_targets(torch.from_numpy(bad).cuda(), (S, S), anchors, C, sync=False)
+    with pytest.raises(AssertionError):                   # generators.py:3409, reported late
+        engine.poll_status()
+    engine.poll_status()                                  # cleared
