@@ -55,7 +55,7 @@ enum {
                                       report deferred device-side errors          */
 };
 
-enum { MGD_NMS_IOU = 0, MGD_NMS_DIOU = 1 };
+enum { MGD_NMS_IOU = 0, MGD_NMS_DIOU = 1, MGD_NMS_SOFT = 2 };
 
 /*
  * Geometry of the detection head: what `anchors`, `num_classes`, `input_shape`
@@ -87,12 +87,17 @@ typedef struct {
     int rescore_confidence;   /* multigrid_decode.py:166-170                      */
     double confidence;        /* keep score >= confidence, :271                   */
     double nms_threshold;     /* suppress metric >= threshold, nms.py:180         */
-    int nms_method;           /* MGD_NMS_DIOU ('diou') or MGD_NMS_IOU
-                                 ('standard'/'cluster')                           */
+    int nms_method;           /* MGD_NMS_DIOU ('diou'), MGD_NMS_IOU ('standard' /
+                                 'cluster') or MGD_NMS_SOFT ('soft': Gaussian
+                                 SoftNMS, nms.py:234-288; nms_threshold and
+                                 per_class are ignored like in the reference)     */
     int per_class;            /* 0: class-agnostic (the reference's NMS classes);
                                  1: candidates of different argmax class never
                                  suppress each other                              */
     int max_boxes;            /* top-k after NMS, :336-345                        */
+    double soft_sigma;        /* SoftNMS sigma (nms.py:237 default 0.5); <= 0 -> 0.5  */
+    double soft_score_threshold; /* SoftNMS final / skip threshold (default 0.001);
+                                 < 0 -> 0.001                                      */
 } mgd_post_config;
 
 MGD_API int mgd_version(void);
@@ -175,6 +180,17 @@ MGD_API int mgd_decode_dense(const mgd_head_config *cfg, const mgd_post_config *
 MGD_API int mgd_nms(const double *boxes, const double *scores, const int *classes, int n,
             double nms_threshold, int nms_method, int per_class, int max_keep,
             int *keep, int *n_keep, int memory, int device, void *stream, int flags);
+
+/*
+ * Gaussian SoftNMS on caller-supplied boxes.  Replaces SoftNMS.apply_nms
+ * (multigriddet/postprocess/nms.py:249-288).
+ *   keep        (n,) int32: surviving positions in INPUT order (like boxes[keep_mask])
+ *   soft_scores (n,) float64: decayed score of keep[i]
+ *   n_keep      one int32 in the same memory space
+ */
+MGD_API int mgd_soft_nms(const double *boxes, const double *scores, int n, double sigma,
+                 double score_threshold, int *keep, double *soft_scores, int *n_keep,
+                 int memory, int device, void *stream, int flags);
 
 /*
  * Deferred device-side status of asynchronous calls issued by this thread on

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -27,6 +28,27 @@ int fail(int code, const char* fmt, ...)
     t_error = buf;
     return code;
 }
+
+// MGD_TRACE=1: print host-side timestamps of the staging path to stderr
+static bool trace_on()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MGD_TRACE"); v = e && atoi(e) ? 1 : 0; }
+    return v == 1;
+}
+struct Tracer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const char* what;
+    explicit Tracer(const char* w) : what(w) {}
+    void mark(const char* stage)
+    {
+        if (!trace_on()) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mgd %s] %-18s +%.1f us\n", what, stage,
+                std::chrono::duration<double, std::micro>(t - t0).count());
+        t0 = t;
+    }
+};
 
 #define CUDA_TRY(expr)                                                                   \
     do {                                                                                 \
@@ -303,6 +325,12 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         n.use_diou = post.nms_method == MGD_NMS_DIOU;
         n.per_class = post.per_class;
         n.max_boxes = M;
+        if (post.nms_method == MGD_NMS_SOFT) {
+            n.soft = 1;
+            n.soft_sigma = post.soft_sigma > 0.0 ? post.soft_sigma : 0.5;
+            n.soft_thr = post.soft_score_threshold >= 0.0 ? post.soft_score_threshold : 0.001;
+            CUDA_TRY(cudaMallocAsync(&n.soft_scratch, (size_t)nb * g.cells * sizeof(double), stream));
+        }
         if (big_sort) {
             n.sort_scratch_stride = pow2;
             CUDA_TRY(cudaMallocAsync(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long), stream));
@@ -321,6 +349,7 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         CUDA_TRY(launch_nms(n, num_sms, stream));
         if (n.sort_scratch) CUDA_TRY(cudaFreeAsync(n.sort_scratch, stream));
         if (n.kept_scratch) CUDA_TRY(cudaFreeAsync(n.kept_scratch, stream));
+        if (n.soft_scratch) CUDA_TRY(cudaFreeAsync(n.soft_scratch, stream));
         CUDA_TRY(cudaFreeAsync(n.boxes, stream));
         CUDA_TRY(cudaFreeAsync(d.cand, stream));
         CUDA_TRY(cudaFreeAsync(d.counts, stream));
@@ -333,8 +362,9 @@ int check_post(const mgd_post_config* post)
     if (!post) return fail(MGD_ERR_INVALID_ARGUMENT, "post config is NULL");
     if (post->max_boxes < 1 || post->max_boxes > (1 << 20))
         return fail(MGD_ERR_INVALID_ARGUMENT, "max_boxes must be in [1, 2^20], got %d", post->max_boxes);
-    if (post->nms_method != MGD_NMS_IOU && post->nms_method != MGD_NMS_DIOU)
-        return fail(MGD_ERR_UNSUPPORTED, "nms_method %d: only MGD_NMS_IOU / MGD_NMS_DIOU are built",
+    if (post->nms_method != MGD_NMS_IOU && post->nms_method != MGD_NMS_DIOU &&
+        post->nms_method != MGD_NMS_SOFT)
+        return fail(MGD_ERR_UNSUPPORTED, "nms_method %d: MGD_NMS_IOU / MGD_NMS_DIOU / MGD_NMS_SOFT are built",
                     post->nms_method);
     if (post->confidence != post->confidence || post->nms_threshold != post->nms_threshold)
         return fail(MGD_ERR_INVALID_ARGUMENT, "confidence / nms_threshold is NaN");
@@ -477,8 +507,11 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
     cudaStream_t* ss;
     if ((rc = host_streams(device, &ss))) return rc;
     unsigned long long* d_meta;      // [4 stats][status]
-    CUDA_TRY(cudaMalloc(&d_meta, 5 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(d_meta, 0, 5 * sizeof(unsigned long long)));
+    // (stream-ordered allocation: a legacy cudaMalloc / cudaFree pair costs milliseconds
+    //  here because cudaFree synchronises the device and walks the memory pool)
+    CUDA_TRY(cudaMallocAsync(&d_meta, 5 * sizeof(unsigned long long), ss[0]));
+    CUDA_TRY(cudaMemsetAsync(d_meta, 0, 5 * sizeof(unsigned long long), ss[0]));
+    CUDA_TRY(cudaStreamSynchronize(ss[0]));
     const int step = host_chunk(g, batch);
     int k = 0;
     for (int b0 = 0; b0 < batch; b0 += step, ++k) {
@@ -495,7 +528,7 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
             CUDA_TRY(cudaMallocAsync(&d_y[l], (size_t)nb * g.gh[l] * g.gw[l] * g.D[l] * 4, st));
         rc = encode_device(g, d_boxes, nb, max_boxes, d_y, num_sms, st,
                            reinterpret_cast<int*>(d_meta + 4), d_meta);
-        if (rc) { cudaFree(d_meta); return rc; }
+        if (rc) { cudaFreeAsync(d_meta, ss[0]); return rc; }
         for (int l = 0; l < g.L; ++l) {
             const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
             CUDA_TRY(cudaMemcpyAsync(y_true[l] + (size_t)b0 * per, d_y[l], (size_t)nb * per * 4,
@@ -507,8 +540,9 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
     CUDA_TRY(cudaStreamSynchronize(ss[0]));
     CUDA_TRY(cudaStreamSynchronize(ss[1]));
     unsigned long long h[5];
-    CUDA_TRY(cudaMemcpy(h, d_meta, sizeof(h), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaFree(d_meta));
+    CUDA_TRY(cudaMemcpyAsync(h, d_meta, sizeof(h), cudaMemcpyDeviceToHost, ss[0]));
+    CUDA_TRY(cudaFreeAsync(d_meta, ss[0]));
+    CUDA_TRY(cudaStreamSynchronize(ss[0]));
     if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
     return status_to_error((int)(h[4] & 0xffffffffu));
 }
@@ -557,11 +591,15 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
         return MGD_OK;
     }
 
+    Tracer tr("decode_nms/host");
     cudaStream_t* ss;
     if ((rc = host_streams(device, &ss))) return rc;
+    tr.mark("streams");
     unsigned long long* d_stats;
-    CUDA_TRY(cudaMalloc(&d_stats, 4 * sizeof(unsigned long long)));
-    CUDA_TRY(cudaMemset(d_stats, 0, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMallocAsync(&d_stats, 4 * sizeof(unsigned long long), ss[0]));
+    CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), ss[0]));
+    CUDA_TRY(cudaStreamSynchronize(ss[0]));
+    tr.mark("stats alloc");
     const int step = host_chunk(g, batch);
     int k = 0;
     for (int b0 = 0; b0 < batch; b0 += step, ++k) {
@@ -580,6 +618,7 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
             CUDA_TRY(cudaMemcpyAsync(d_hw, image_hw + 2 * (size_t)b0, (size_t)nb * 2 * sizeof(int),
                                      cudaMemcpyHostToDevice, st));
         }
+        tr.mark("h2d enqueued");
         // one output slab: xywh f64 | scores f64 | xyxy i32 | classes i32 | index i32 | counts i32
         const size_t n_det = (size_t)nb * M;
         const size_t off_scores = n_det * 4 * sizeof(double);
@@ -597,7 +636,8 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
                                reinterpret_cast<int*>(d_out + off_cls),
                                reinterpret_cast<int*>(d_out + off_idx),
                                reinterpret_cast<int*>(d_out + off_cnt), num_sms, st, d_stats);
-        if (rc) { cudaFree(d_stats); return rc; }
+        if (rc) { cudaFreeAsync(d_stats, ss[0]); return rc; }
+        tr.mark("kernels enqueued");
         if (boxes_xywh)
             CUDA_TRY(cudaMemcpyAsync(boxes_xywh + (size_t)b0 * M * 4, d_out, n_det * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (scores)
@@ -613,11 +653,13 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
         if (d_hw) CUDA_TRY(cudaFreeAsync(d_hw, st));
         for (int l = 0; l < g.L; ++l) CUDA_TRY(cudaFreeAsync(d_pred[l], st));
     }
-    CUDA_TRY(cudaStreamSynchronize(ss[0]));
+    tr.mark("d2h enqueued");
     CUDA_TRY(cudaStreamSynchronize(ss[1]));
     unsigned long long h[4];
-    CUDA_TRY(cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaFree(d_stats));
+    CUDA_TRY(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, ss[0]));
+    CUDA_TRY(cudaFreeAsync(d_stats, ss[0]));
+    CUDA_TRY(cudaStreamSynchronize(ss[0]));
+    tr.mark("synchronised");
     if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
     return MGD_OK;
 }
@@ -760,6 +802,70 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
     if (a.kept_scratch) CUDA_TRY(cudaFreeAsync(a.kept_scratch, st));
     CUDA_TRY(cudaFreeAsync(count, st));
     if (staged) CUDA_TRY(cudaFreeAsync(staged, st));
+    if (host || (flags & MGD_FLAG_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
+    return MGD_OK;
+}
+
+int mgd_soft_nms(const double* boxes, const double* scores, int n, double sigma,
+                 double score_threshold, int* keep, double* soft_scores, int* n_keep, int memory,
+                 int device, void* stream, int flags)
+{
+    int rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (n < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n must be >= 0");
+    if (!n_keep) return fail(MGD_ERR_INVALID_ARGUMENT, "n_keep is NULL");
+    if (n > 0 && (!boxes || !scores || !keep || !soft_scores))
+        return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    if (!(sigma > 0.0)) return fail(MGD_ERR_INVALID_ARGUMENT, "sigma must be positive");
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    const bool host = memory == MGD_MEM_HOST;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (host) {
+        cudaStream_t* ss;
+        if ((rc = host_streams(device, &ss))) return rc;
+        st = ss[0];
+    }
+    if (n == 0) {
+        if (host) { *n_keep = 0; return MGD_OK; }
+        CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int), st));
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    // device staging: boxes (4n f64) | scores (n f64) | soft out (n f64) | keep (n i32) | counts (2 i32)
+    const size_t nn = (size_t)n;
+    unsigned char* buf;
+    CUDA_TRY(cudaMallocAsync(&buf, nn * (32 + 8 + 8 + 8 + 4) + 64, st));
+    double* d_boxes = reinterpret_cast<double*>(buf);
+    double* d_scores = d_boxes + 4 * nn;
+    double* d_soft_out = d_scores + nn;
+    double* d_soft = d_soft_out + nn;
+    int* d_keep = reinterpret_cast<int*>(d_soft + nn);
+    int* d_cnt = d_keep + nn;
+    const cudaMemcpyKind in_kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CUDA_TRY(cudaMemcpyAsync(d_boxes, boxes, nn * 32, in_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(d_scores, scores, nn * 8, in_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cnt, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+    NmsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = 1; a.cap = n; a.counts = d_cnt;
+    a.in_boxes = d_boxes; a.in_scores = d_scores;
+    a.max_boxes = n;
+    a.soft = 1; a.soft_sigma = sigma; a.soft_thr = score_threshold; a.soft_scratch = d_soft;
+    int pow2 = 2;
+    while (pow2 < n) pow2 <<= 1;
+    if (n > nms_smem_capacity()) {
+        a.sort_scratch_stride = pow2;
+        CUDA_TRY(cudaMallocAsync(&a.sort_scratch, (size_t)2 * pow2 * sizeof(unsigned long long), st));
+    }
+    a.out_index = d_keep; a.out_scores = d_soft_out; a.out_counts = d_cnt + 1;
+    CUDA_TRY(launch_nms(a, num_sms, st));
+    const cudaMemcpyKind out_kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CUDA_TRY(cudaMemcpyAsync(keep, d_keep, nn * sizeof(int), out_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(soft_scores, d_soft_out, nn * sizeof(double), out_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(n_keep, d_cnt + 1, sizeof(int), out_kind, st));
+    if (a.sort_scratch) CUDA_TRY(cudaFreeAsync(a.sort_scratch, st));
+    CUDA_TRY(cudaFreeAsync(buf, st));
     if (host || (flags & MGD_FLAG_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
     return MGD_OK;
 }

@@ -86,6 +86,9 @@ struct NmsArgs {
     double thr;
     int use_diou, per_class, max_boxes;
     int skip_small;                   // nms_kernel: skip images with <= this many candidates
+    int soft;                         // 1: Gaussian SoftNMS (soft_nms_kernel)
+    double soft_sigma, soft_thr;
+    double* soft_scratch;             // (B, cap) decayed scores
     int* next_image;                  // nms_warp_kernel: work counter (zeroed by the caller)
     unsigned long long* sort_scratch; // (B, 2*pow2(cap)) u64, used when count > smem capacity
     int sort_scratch_stride;          // elements (pairs) per image in sort_scratch

@@ -520,6 +520,175 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Gaussian SoftNMS (reference multigriddet/postprocess/nms.py:234-288), one CTA per
+// image.  The visiting order is fixed by the ORIGINAL scores (the reference never
+// re-sorts): candidate i multiplies the score of every later candidate by
+// exp(-IoU^2 / sigma); a candidate whose decayed score is below the threshold when
+// its turn comes is zeroed and does not decay anyone.  Survivors keep their decayed
+// score and are returned in input order (ascending candidate index) -- unless there
+// are more than max_boxes, then the top max_boxes by decayed score
+// (multigrid_decode.py:336-345).  O(M^2) pair tests, M-1 CTA barriers.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double iou_xywh(const BoxD& a, const BoxD& b)
+{
+    const double iw = fmax(0.0, __dsub_rn(fmin(__dadd_rn(a.x, a.w), __dadd_rn(b.x, b.w)), fmax(a.x, b.x)));
+    const double ih = fmax(0.0, __dsub_rn(fmin(__dadd_rn(a.y, a.h), __dadd_rn(b.y, b.h)), fmax(a.y, b.y)));
+    const double inter = __dmul_rn(iw, ih);
+    const double uni = __dsub_rn(__dadd_rn(__dmul_rn(a.w, a.h), __dmul_rn(b.w, b.h)), inter);
+    return __ddiv_rn(inter, __dadd_rn(uni, 1e-8));
+}
+
+__device__ void cta_bitonic(unsigned long long* key, unsigned long long* val, int mpad, int tid)
+{
+    for (int k = 2; k <= mpad; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = tid; i < mpad; i += kThreads) {
+                const int p = i ^ jj;
+                if (p > i) {
+                    const unsigned long long ka = key[i], kb = key[p], va = val[i], vb = val[p];
+                    const bool b_lt_a = kb < ka || (kb == ka && vb < va);
+                    const bool up = (i & k) == 0;
+                    if (b_lt_a == up) { key[i] = kb; key[p] = ka; val[i] = vb; val[p] = va; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+soft_nms_kernel(const __grid_constant__ NmsArgs a)
+{
+    __shared__ unsigned long long s_key[kSortSmem];
+    __shared__ unsigned long long s_val[kSortSmem];
+    __shared__ uint64_t s_tab[MGD_EXP2F_N];
+    __shared__ int s_count;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int M = a.counts[b];
+    const Cand* cand = a.cand ? a.cand + (size_t)b * a.cap : nullptr;
+    const BoxD* boxes = a.cand ? a.boxes + (size_t)b * a.cap
+                               : reinterpret_cast<const BoxD*>(a.in_boxes);
+    double* soft = a.soft_scratch + (size_t)b * a.cap;
+
+    int mpad = 2;
+    while (mpad < M) mpad <<= 1;
+    unsigned long long* key = s_key;
+    unsigned long long* val = s_val;
+    if (mpad > kSortSmem) {
+        key = a.sort_scratch + (size_t)b * 2 * a.sort_scratch_stride;
+        val = key + a.sort_scratch_stride;
+    }
+    if (tid < MGD_EXP2F_N) s_tab[tid] = mgd_exp2f_tab[tid];
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (cand) {
+        const HeadGeom& g = a.g;
+        const int ih = a.image_hw ? a.image_hw[2 * b] : a.in_h;
+        const int iw = a.image_hw ? a.image_hw[2 * b + 1] : a.in_w;
+        const Letterbox lb = letterbox_consts(g.in_h, g.in_w, ih, iw);
+        BoxD* out = a.boxes + (size_t)b * a.cap;
+        for (int i = tid; i < M; i += kThreads) {
+            const Cand cd = cand[i];
+            int layer = 0;
+            while (layer + 1 < g.L && cd.index >= g.cell_off[layer + 1]) ++layer;
+            const int cell = cd.index - g.cell_off[layer];
+            const int rr = cell / g.gw[layer], cc = cell - rr * g.gw[layer];
+            BoxD bx;
+            decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 0, s_tab, bx.x, bx.w);
+            decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 1, s_tab, bx.y, bx.h);
+            out[i] = bx;
+        }
+    }
+    for (int i = tid; i < mpad; i += kThreads) {
+        if (i < M) {
+            const double sc = cand ? (double)cand[i].score : a.in_scores[i];
+            const unsigned idx = cand ? (unsigned)cand[i].index : (unsigned)i;
+            soft[i] = sc;
+            key[i] = score_key(sc);
+            val[i] = ((unsigned long long)idx << 32) | (unsigned)i;
+        } else {
+            key[i] = ~0ull; val[i] = ~0ull;
+        }
+    }
+    __syncthreads();
+    cta_bitonic(key, val, mpad, tid);
+
+    // ---- sequential decay in the original score order ------------------------------------
+    for (int i = 0; i < M; ++i) {
+        const int cur = (int)(val[i] & 0xffffffffu);
+        const double sc = soft[cur];                       // uniform across the CTA
+        if (sc < a.soft_thr) {                             // nms.py:265-267
+            if (tid == 0) soft[cur] = 0.0;
+            continue;
+        }
+        const BoxD cb = boxes[cur];
+        for (int j = i + 1 + tid; j < M; j += kThreads) {
+            const int p = (int)(val[j] & 0xffffffffu);
+            const double iou = iou_xywh(cb, boxes[p]);
+            if (iou > 0.0) soft[p] = __dmul_rn(soft[p], exp(__ddiv_rn(-__dmul_rn(iou, iou), a.soft_sigma)));
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+
+    // ---- survivors: input order, or the top max_boxes by decayed score -------------------
+    int mine = 0;
+    for (int i = tid; i < M; i += kThreads) mine += soft[i] >= a.soft_thr;
+    if (mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    const int K = s_count;
+    const bool by_score = K > a.max_boxes;
+    for (int i = tid; i < mpad; i += kThreads) {
+        if (i < M && soft[i] >= a.soft_thr) {
+            const unsigned idx = cand ? (unsigned)cand[i].index : (unsigned)i;
+            key[i] = by_score ? score_key(soft[i]) : 0ull;
+            val[i] = ((unsigned long long)idx << 32) | (unsigned)i;
+        } else {
+            key[i] = ~0ull; val[i] = ~0ull;
+        }
+    }
+    __syncthreads();
+    cta_bitonic(key, val, mpad, tid);
+    const int n_out = min(K, a.max_boxes);
+    const double W = (double)(a.image_hw ? a.image_hw[2 * b + 1] : a.in_w);
+    const double H = (double)(a.image_hw ? a.image_hw[2 * b] : a.in_h);
+    for (int q = tid; q < a.max_boxes; q += kThreads) {
+        const size_t o = (size_t)b * a.max_boxes + q;
+        if (q < n_out) {
+            const int pos = (int)(val[q] & 0xffffffffu);
+            const BoxD cd = boxes[pos];
+            if (a.out_xywh) {
+                a.out_xywh[o * 4 + 0] = cd.x; a.out_xywh[o * 4 + 1] = cd.y;
+                a.out_xywh[o * 4 + 2] = cd.w; a.out_xywh[o * 4 + 3] = cd.h;
+            }
+            if (a.out_xyxy) {
+                a.out_xyxy[o * 4 + 0] = (int)floor(__dadd_rn(clipd(cd.x, 0.0, W), 0.5));
+                a.out_xyxy[o * 4 + 1] = (int)floor(__dadd_rn(clipd(cd.y, 0.0, H), 0.5));
+                a.out_xyxy[o * 4 + 2] = (int)floor(__dadd_rn(clipd(__dadd_rn(cd.x, cd.w), 0.0, W), 0.5));
+                a.out_xyxy[o * 4 + 3] = (int)floor(__dadd_rn(clipd(__dadd_rn(cd.y, cd.h), 0.0, H), 0.5));
+            }
+            if (a.out_scores) a.out_scores[o] = soft[pos];
+            if (a.out_classes) a.out_classes[o] = cand ? cand[pos].cls : (a.in_classes ? a.in_classes[pos] : 0);
+            if (a.out_index) a.out_index[o] = cand ? cand[pos].index : pos;
+        } else {
+            if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = 0.0;
+            if (a.out_xyxy) for (int e = 0; e < 4; ++e) a.out_xyxy[o * 4 + e] = 0;
+            if (a.out_scores) a.out_scores[o] = 0.0;
+            if (a.out_classes) a.out_classes[o] = -1;
+            if (a.out_index) a.out_index[o] = -1;
+        }
+    }
+    if (tid == 0) {
+        a.out_counts[b] = n_out;
+        if (a.stats) {
+            atomicAdd(&a.stats[0], (unsigned long long)M);
+            atomicAdd(&a.stats[1], (unsigned long long)n_out);
+        }
+    }
+}
+
 __global__ void keep_from_index_kernel(const int* index, const int* counts, int max_keep,
                                        int* keep, int* n_keep)
 {
@@ -539,6 +708,11 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
     NmsArgs a = a_in;
     cudaError_t err;
     prof_mark_begin(PROF_NMS, stream);
+    if (a.soft) {
+        soft_nms_kernel<<<a.B, kThreads, 0, stream>>>(a);
+        prof_mark_end(PROF_NMS, stream);
+        return cudaGetLastError();
+    }
     // decode mode with a kept list that fits shared memory: warp-per-image kernels first,
     // a lean instance for images with <= 512 candidates and one for 513..1024
     static int env_off = -1;

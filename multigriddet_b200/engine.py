@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 
 _NMS_METHODS = {"diou": _lib.NMS_DIOU, "standard": _lib.NMS_IOU, "iou": _lib.NMS_IOU,
-                "cluster": _lib.NMS_IOU}
+                "cluster": _lib.NMS_IOU, "soft": _lib.NMS_SOFT}
 
 
 def _is_torch(x) -> bool:
@@ -43,11 +43,12 @@ def device_count() -> int:
 
 
 def post_config(max_boxes=100, confidence=0.1, nms_threshold=0.5, nms_method="diou",
-                per_class=False, use_softmax=True, rescore_confidence=True) -> _lib.PostConfig:
+                per_class=False, use_softmax=True, rescore_confidence=True,
+                soft_sigma=0.5, soft_score_threshold=0.001) -> _lib.PostConfig:
     if nms_method not in _NMS_METHODS:
         raise NotImplementedError(
-            f"nms_method={nms_method!r}: the CUDA path implements 'diou', 'standard' and "
-            "'cluster' (greedy hard NMS); 'soft' / WBF are not built yet")
+            f"nms_method={nms_method!r}: the CUDA path implements 'diou', 'standard', "
+            "'cluster' (greedy hard NMS) and 'soft' (Gaussian SoftNMS); WBF is not built yet")
     pc = _lib.PostConfig()
     pc.use_softmax = int(bool(use_softmax))
     pc.rescore_confidence = int(bool(rescore_confidence))
@@ -56,6 +57,8 @@ def post_config(max_boxes=100, confidence=0.1, nms_threshold=0.5, nms_method="di
     pc.nms_method = _NMS_METHODS[nms_method]
     pc.per_class = int(bool(per_class))
     pc.max_boxes = int(max_boxes)
+    pc.soft_sigma = float(soft_sigma)
+    pc.soft_score_threshold = float(soft_score_threshold)
     return pc
 
 
@@ -247,12 +250,34 @@ def decode_dense(preds, anchors, num_classes, model_image_size, image_shapes=Non
     return out
 
 
+def soft_nms(boxes, scores, sigma=0.5, score_threshold=0.001):
+    """Gaussian SoftNMS on (n,4) xywh float64 boxes: (kept positions in input order,
+    their decayed scores)."""
+    lib = _lib.load()
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
+    s = np.ascontiguousarray(np.asarray(scores, dtype=np.float64).reshape(-1))
+    n = b.shape[0]
+    if s.shape[0] != n:
+        raise ValueError("boxes and scores disagree on n")
+    keep = np.empty((max(n, 1),), dtype=np.int32)
+    soft = np.empty((max(n, 1),), dtype=np.float64)
+    n_keep = ctypes.c_int(0)
+    rc = lib.mgd_soft_nms(ctypes.c_void_p(b.ctypes.data), ctypes.c_void_p(s.ctypes.data), n,
+                          float(sigma), float(score_threshold), ctypes.c_void_p(keep.ctypes.data),
+                          ctypes.c_void_p(soft.ctypes.data),
+                          ctypes.cast(ctypes.byref(n_keep), ctypes.c_void_p), _lib.MEM_HOST,
+                          _current_device(), None, _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    k = n_keep.value
+    return keep[:k].astype(np.int64), soft[:k].copy()
+
+
 def nms(boxes, scores, classes=None, nms_threshold=0.5, nms_method="diou", per_class=False,
         max_keep=0):
     """Greedy NMS on (n,4) xywh float64 boxes; returns kept positions (descending score)."""
     lib = _lib.load()
-    if nms_method not in _NMS_METHODS:
-        raise NotImplementedError(f"nms_method={nms_method!r} is not built")
+    if nms_method not in _NMS_METHODS or nms_method == "soft":
+        raise NotImplementedError(f"nms_method={nms_method!r} is not a greedy hard NMS")
     b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
     s = np.ascontiguousarray(np.asarray(scores, dtype=np.float64).reshape(-1))
     n = b.shape[0]

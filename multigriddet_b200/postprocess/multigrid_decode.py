@@ -82,7 +82,10 @@ class MultiGridDecoder:
         boxes = np.concatenate(n_boxes)
         classes = np.concatenate(n_classes).astype("int32")
         scores = np.concatenate(n_scores)
-        return boxes[:max_boxes], classes[:max_boxes], scores[:max_boxes]   # already sorted
+        if len(boxes) <= max_boxes:                                          # :336-337
+            return boxes, classes, scores
+        top = np.argsort(-scores, kind="stable")[:max_boxes]                 # :340-345
+        return boxes[top], classes[top], scores[top]
 
     # ---- the hot path ------------------------------------------------------------
     def postprocess(self, multigriddet_outputs, image_shape, model_image_size,
@@ -93,12 +96,12 @@ class MultiGridDecoder:
 
         Returns ``(boxes, classes, scores)``: int32 (K, 4) xyxy (or float64 xywh when
         ``return_xyxy=False``), int32 (K,), float64 (K,); three empty arrays when
-        nothing passes.  ``nms_method``: 'diou', 'cluster' or 'standard' ('standard'
-        raises ``NotImplementedError`` in the reference; here it is IoU greedy NMS).
+        nothing passes.  ``nms_method``: 'diou', 'cluster', 'soft' or 'standard'
+        ('standard' raises ``NotImplementedError`` in the reference; here it is IoU greedy NMS).
         """
         if use_wbf:
             raise NotImplementedError("Weighted Boxes Fusion is not part of the CUDA path yet")
-        if nms_method not in ("diou", "cluster", "standard"):
+        if nms_method not in ("diou", "cluster", "standard", "soft"):
             raise NotImplementedError(f"nms_method={nms_method!r} is not part of the CUDA path")
         if not self._usable(multigriddet_outputs):
             return _EMPTY()

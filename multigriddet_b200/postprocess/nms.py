@@ -53,7 +53,8 @@ class ClusterNMS(_GreedyNMS):
 
 
 class SoftNMS(NMS):
-    """Gaussian SoftNMS (reference nms.py:234-317) -- not built yet."""
+    """Gaussian SoftNMS (reference nms.py:234-317): survivors in input order with their
+    decayed scores."""
 
     def __init__(self, sigma: float = 0.5, score_threshold: float = 0.001):
         super().__init__()
@@ -61,9 +62,14 @@ class SoftNMS(NMS):
         self.score_threshold = score_threshold
 
     def apply_nms(self, boxes, classes, scores, nms_threshold, confidence):
-        raise NotImplementedError(
-            "SoftNMS is not part of the CUDA path yet (next row in SURVEY.md 8f); "
-            "there is deliberately no CPU fallback")
+        if len(boxes) == 0:
+            return [], [], []
+        boxes = np.asarray(boxes)
+        classes = np.asarray(classes)
+        keep, soft = engine.soft_nms(boxes, np.asarray(scores), self.sigma, self.score_threshold)
+        if len(keep) == 0:
+            return [], [], []
+        return [boxes[keep]], [classes[keep]], [soft]
 
 
 def nms_boxes(boxes, classes, scores, nms_threshold, use_iol=True, use_diou=False,

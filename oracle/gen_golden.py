@@ -95,6 +95,8 @@ def decode_cases():
         dict(image_shape=(480, 640), confidence=0.1, nms_threshold=0.45, nms_method="diou", max_boxes=100),
         dict(image_shape=(1080, 1920), confidence=0.001, nms_threshold=0.5, nms_method="cluster", max_boxes=5),
         dict(image_shape=(375, 500), confidence=0.3, nms_threshold=0.3, nms_method="diou", max_boxes=100),
+        dict(image_shape=(480, 640), confidence=0.001, nms_threshold=0.45, nms_method="soft", max_boxes=100),
+        dict(image_shape=None, confidence=0.001, nms_threshold=0.45, nms_method="soft", max_boxes=4),
     ]
     for i, (name, S, C, B, N, dt) in enumerate(cases):
         anchors = synth.coco_anchors(dt)
@@ -153,6 +155,10 @@ def nms_cases():
                 kb, kc, ks = cls().apply_nms(boxes, classes, scores, thr, 0.0)
                 store[f"n{i}_{name}_{thr}_scores"] = ks[0]
                 store[f"n{i}_{name}_{thr}_boxes"] = kb[0]
+        for sigma in (0.5, 0.1):
+            kb, kc, ks = post.SoftNMS(sigma=sigma).apply_nms(boxes, classes, scores, 0.5, 0.0)
+            store[f"n{i}_soft_{sigma}_scores"] = ks[0]
+            store[f"n{i}_soft_{sigma}_boxes"] = kb[0]
     np.savez_compressed(os.path.join(OUT, "nms_cases.npz"), **store)
     print("nms cases written")
 

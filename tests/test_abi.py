@@ -40,13 +40,13 @@ def test_struct_layout_matches_c(tmp_path):
                    'int main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(mgd_head_config),'
                    'offsetof(mgd_head_config, anchors), offsetof(mgd_head_config, anchors_f64),'
                    'sizeof(mgd_post_config), offsetof(mgd_post_config, nms_method),'
-                   'offsetof(mgd_post_config, max_boxes));return 0;}\n')
+                   'offsetof(mgd_post_config, soft_score_threshold));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
     H, P = _lib.HeadConfig, _lib.PostConfig
     assert got == [ctypes.sizeof(H), H.anchors.offset, H.anchors_f64.offset,
-                   ctypes.sizeof(P), P.nms_method.offset, P.max_boxes.offset]
+                   ctypes.sizeof(P), P.nms_method.offset, P.soft_score_threshold.offset]
 
 
 def test_version_and_device_count(lib):
@@ -71,7 +71,7 @@ def test_argument_validation_without_a_device(lib):
     with pytest.raises(ValueError):
         engine.decode_nms(preds, None, (608, 608), anchors, 80, max_boxes=0)
     with pytest.raises(NotImplementedError):
-        engine.decode_nms(preds, None, (608, 608), anchors, 80, nms_method="soft")
+        engine.decode_nms(preds, None, (608, 608), anchors, 80, nms_method="wbf")
     with pytest.raises(ValueError):                    # wrong channel count
         engine.decode_nms(preds, None, (608, 608), anchors, 20)
 
@@ -88,6 +88,8 @@ def test_no_cpu_fallback(lib):
         engine.decode_nms(preds, None, (608, 608), anchors, 80)
     with pytest.raises(_lib.MgdError, match="no CPU fallback"):
         engine.nms(np.zeros((3, 4)), np.zeros(3))
+    with pytest.raises(_lib.MgdError, match="no CPU fallback"):
+        engine.soft_nms(np.zeros((3, 4)), np.ones(3))
     with pytest.raises(_lib.MgdError, match="no CPU fallback"):
         engine.decode_dense(preds, anchors, 80, (608, 608))
 

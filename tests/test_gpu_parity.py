@@ -252,7 +252,7 @@ def test_decode_empty_and_threshold_edges(c_oracle):
     with pytest.raises(ValueError):
         engine.decode_nms(preds[:2], (S, S), (S, S), anchors, C)
     with pytest.raises(NotImplementedError):
-        engine.decode_nms(preds, (S, S), (S, S), anchors, C, nms_method="soft")
+        engine.decode_nms(preds, (S, S), (S, S), anchors, C, nms_method="wbf")
 
 
 def test_decode_device_tensors_match_host_path(c_oracle):
@@ -437,3 +437,43 @@ def test_async_device_calls_and_deferred_status():
     with pytest.raises(AssertionError):                   # generators.py:3409, reported late
         engine.poll_status()
     engine.poll_status()                                  # cleared
+
+
+# ------------------------------------------------------------------------------
+# SoftNMS
+# ------------------------------------------------------------------------------
+
+def test_soft_nms_matches_oracle():
+    from oracle import mgd_oracle as O
+    rng = np.random.default_rng(3)
+    for n in (1, 6, 150, 2500):
+        xy = rng.uniform(0, 300, size=(n, 2))
+        wh = rng.uniform(5, 120, size=(n, 2))
+        boxes = np.concatenate([xy, wh], 1)
+        scores = rng.uniform(0.0005, 1, size=n)
+        for sigma in (0.5, 0.1):
+            keep_r, soft_r = O.soft_nms(boxes, scores, sigma=sigma)
+            keep_g, soft_g = engine.soft_nms(boxes, scores, sigma=sigma)
+            assert np.array_equal(keep_g, keep_r), (n, sigma)
+            # the decay uses float64 exp: device and libm agree to ~1 ulp per factor
+            np.testing.assert_allclose(soft_g, soft_r, rtol=1e-12)
+
+
+def test_postprocess_soft_matches_oracle(c_oracle):
+    from oracle import mgd_oracle as O
+    S, C, B = 608, 80, 4
+    anchors = synth.coco_anchors(np.float32)
+    preds = _planted(31, B, S, C, 60, anchors, c_oracle)
+    shapes = synth.image_shapes(3, B)
+    for max_boxes in (100, 7):
+        kw = dict(max_boxes=max_boxes, confidence=0.001, nms_threshold=0.45, nms_method="soft")
+        ref = O.postprocess_batch(preds, shapes, (S, S), anchors, C, **kw)
+        got = engine.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+        for b in range(B):
+            k = len(ref[b]["index"])
+            assert int(got["counts"][b]) == k
+            assert np.array_equal(got["index"][b, :k], ref[b]["index"])
+            assert np.array_equal(got["classes"][b, :k], ref[b]["classes"])
+            # decayed scores inherit the 1e-5 box tolerance (np.tanh is not bit-reproducible)
+            np.testing.assert_allclose(got["scores"][b, :k], ref[b]["scores"], rtol=RTOL)
+            np.testing.assert_allclose(got["boxes_xywh"][b, :k], ref[b]["boxes_xywh"], rtol=RTOL, atol=1e-4)

@@ -26,7 +26,7 @@ def test_decoder_shim_conventions():
                         (608, 608), (608, 608), use_wbf=True)
     with pytest.raises(NotImplementedError):
         dec.postprocess([np.zeros((1, g, g, 88), np.float32) for g in (19, 38, 76)],
-                        (608, 608), (608, 608), nms_method="soft")
+                        (608, 608), (608, 608), nms_method="wbf-something")
     # an empty scale: the reference returns three empty arrays
     b, c, s = dec.postprocess([np.zeros((0, g, g, 88), np.float32) for g in (19, 38, 76)],
                               (608, 608), (608, 608))
@@ -52,9 +52,8 @@ def test_nms_shim_conventions():
     assert nms_boxes([], [], [], 0.5) == ([], [], [])
     with pytest.raises(NotImplementedError):
         NMS().apply_nms(np.zeros((1, 4)), np.zeros(1), np.ones(1), 0.5, 0.1)
-    with pytest.raises(NotImplementedError):
-        SoftNMS().apply_nms(np.zeros((1, 4)), np.zeros(1), np.ones(1), 0.5, 0.1)
-    assert SoftNMS().sigma == 0.5 and DIoUNMS(use_iol=True).use_iol is True
+    assert SoftNMS().apply_nms(np.zeros((0, 4)), np.zeros(0), np.zeros(0), 0.5, 0.1) == ([], [], [])
+    assert SoftNMS().sigma == 0.5 and SoftNMS().score_threshold == 0.001 and DIoUNMS(use_iol=True).use_iol is True
 
 
 def test_target_encoder_shim_fields():

@@ -62,11 +62,12 @@ def test_decode_oracles_match_reference_golden(path, c_oracle):
     for k, kn in G.knobs_of(z):
         ishape = kn.pop("image_shape")
         py = O.postprocess_batch(preds, np.tile(np.array(ishape), (B, 1)), (S, S), anchors, C, **kn)
-        cc = c_oracle.decode_nms(preds, [ishape], (S, S), anchors, C, **kn)
+        soft = kn["nms_method"] == "soft"
+        cc = None if soft else c_oracle.decode_nms(preds, [ishape], (S, S), anchors, C, **kn)
         for b in range(B):
             ref_s = z[f"k{k}_b{b}_scores"]
             n = len(ref_s)
-            assert len(py[b]["scores"]) == n and int(cc["counts"][b]) == n
+            assert len(py[b]["scores"]) == n and (soft or int(cc["counts"][b]) == n)
             if G.numpy_pinned():
                 assert np.array_equal(py[b]["scores"], ref_s)
                 assert np.array_equal(py[b]["boxes_xywh"], z[f"k{k}_b{b}_xywh"].reshape(-1, 4))
@@ -76,6 +77,8 @@ def test_decode_oracles_match_reference_golden(path, c_oracle):
                                            rtol=1e-6, atol=1e-4)
             assert np.array_equal(py[b]["boxes_xyxy"], z[f"k{k}_b{b}_xyxy"].reshape(-1, 4))
             assert np.array_equal(py[b]["classes"], z[f"k{k}_b{b}_classes"])
+            if soft:           # SoftNMS is restated in NumPy only
+                continue
             # the C restatement: bit-exact too (NumPy pinned to libm in conftest.py)
             assert np.array_equal(cc["scores"][b, :n], ref_s)
             assert np.array_equal(cc["boxes_xywh"][b, :n], z[f"k{k}_b{b}_xywh"].reshape(-1, 4))
@@ -94,5 +97,9 @@ def test_nms_oracle_matches_reference_golden():
                 keep = O.greedy_nms(boxes, scores, thr, diou)
                 assert np.array_equal(scores[keep], z[f"n{i}_{name}_{thr}_scores"])
                 assert np.array_equal(boxes[keep], z[f"n{i}_{name}_{thr}_boxes"])
+        for sigma in (0.5, 0.1):
+            keep, soft = O.soft_nms(boxes, scores, sigma=sigma)
+            assert np.array_equal(soft, z[f"n{i}_soft_{sigma}_scores"])
+            assert np.array_equal(boxes[keep], z[f"n{i}_soft_{sigma}_boxes"])
         i += 1
     assert i == 4
