@@ -55,7 +55,8 @@ enum {
                                       report deferred device-side errors          */
 };
 
-enum { MGD_NMS_IOU = 0, MGD_NMS_DIOU = 1, MGD_NMS_SOFT = 2 };
+enum { MGD_NMS_IOU = 0, MGD_NMS_DIOU = 1, MGD_NMS_SOFT = 2, MGD_NMS_WBF = 3 };
+enum { MGD_WBF_CONF_AVG = 0, MGD_WBF_CONF_MAX = 1, MGD_WBF_CONF_BOX_AND_MODEL_AVG = 2 };
 
 /*
  * Geometry of the detection head: what `anchors`, `num_classes`, `input_shape`
@@ -90,7 +91,9 @@ typedef struct {
     int nms_method;           /* MGD_NMS_DIOU ('diou'), MGD_NMS_IOU ('standard' /
                                  'cluster') or MGD_NMS_SOFT ('soft': Gaussian
                                  SoftNMS, nms.py:234-288; nms_threshold and
-                                 per_class are ignored like in the reference)     */
+                                 per_class are ignored like in the reference) or
+                                 MGD_NMS_WBF (use_wbf=True: weighted boxes fusion
+                                 with iou_thr = nms_threshold, wbf.py:98-218)     */
     int per_class;            /* 0: class-agnostic (the reference's NMS classes);
                                  1: candidates of different argmax class never
                                  suppress each other                              */
@@ -188,6 +191,20 @@ MGD_API int mgd_nms(const double *boxes, const double *scores, const int *classe
  *   soft_scores (n,) float64: decayed score of keep[i]
  *   n_keep      one int32 in the same memory space
  */
+/*
+ * Weighted Boxes Fusion on caller-supplied boxes.  Replaces WeightedBoxesFusion.
+ * fuse_boxes / weighted_boxes_fusion (multigriddet/postprocess/wbf.py:38-290) for the
+ * concatenated boxes of all models.
+ *   boxes (n,4) f64 xywh, scores (n,) f64, classes (n,) int32,
+ *   box_weights (n,) f64 = weights[model of box] or NULL (all 1)
+ *   out_boxes (n,4) f64, out_scores (n,) f64, out_classes (n,) int32: the fused clusters in
+ *   (class ascending, leader score descending) order; *n_out = how many.
+ */
+MGD_API int mgd_wbf(const double *boxes, const double *scores, const int *classes,
+            const double *box_weights, int n, double iou_thr, double skip_box_thr,
+            int conf_type, double *out_boxes, double *out_scores, int *out_classes,
+            int *n_out, int memory, int device, void *stream, int flags);
+
 MGD_API int mgd_soft_nms(const double *boxes, const double *scores, int n, double sigma,
                  double score_threshold, int *keep, double *soft_scores, int *n_keep,
                  int memory, int device, void *stream, int flags);

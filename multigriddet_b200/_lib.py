@@ -18,7 +18,7 @@ MGD_MAX_LAYERS = 5
 MGD_MAX_ANCHORS_PER_LAYER = 8
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_SYNC = 1
-NMS_IOU, NMS_DIOU, NMS_SOFT = 0, 1, 2
+NMS_IOU, NMS_DIOU, NMS_SOFT, NMS_WBF = 0, 1, 2, 3
 
 OK, ERR_INVALID_ARGUMENT, ERR_CLASS_RANGE, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(6)
 
@@ -65,7 +65,7 @@ _IP = ctypes.POINTER(ctypes.c_int)
 _LLP = ctypes.POINTER(ctypes.c_longlong)
 
 EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targets",
-           "mgd_decode_nms", "mgd_decode_dense", "mgd_nms", "mgd_soft_nms", "mgd_poll_status",
+           "mgd_decode_nms", "mgd_decode_dense", "mgd_nms", "mgd_soft_nms", "mgd_wbf", "mgd_poll_status",
            "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack", "mgd_profile_begin",
            "mgd_profile_end")
 
@@ -104,6 +104,11 @@ def load():
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.mgd_wbf.restype = ctypes.c_int
+    lib.mgd_wbf.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+        ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     lib.mgd_soft_nms.restype = ctypes.c_int
     lib.mgd_soft_nms.argtypes = [
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double,

@@ -331,6 +331,18 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
             n.soft_thr = post.soft_score_threshold >= 0.0 ? post.soft_score_threshold : 0.001;
             CUDA_TRY(cudaMallocAsync(&n.soft_scratch, (size_t)nb * g.cells * sizeof(double), stream));
         }
+        if (post.nms_method == MGD_NMS_WBF) {
+            if (g.C > 65535) return fail(MGD_ERR_UNSUPPORTED, "WBF supports up to 65535 classes");
+            n.wbf = 1;
+            n.wbf_conf_type = MGD_WBF_CONF_AVG;            // handle_predictions: WeightedBoxesFusion(iou_thr=...)
+            n.soft_thr = 0.0;                              // skip_box_thr default
+            CUDA_TRY(cudaMallocAsync(&n.soft_scratch, (size_t)nb * g.cells * 5 * sizeof(double), stream));
+            CUDA_TRY(cudaMallocAsync(&n.wbf_ints, (size_t)nb * g.cells * 4 * sizeof(int), stream));
+            if (!n.sort_scratch) {
+                n.sort_scratch_stride = pow2;
+                CUDA_TRY(cudaMallocAsync(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long), stream));
+            }
+        }
         if (big_sort) {
             n.sort_scratch_stride = pow2;
             CUDA_TRY(cudaMallocAsync(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long), stream));
@@ -350,6 +362,7 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         if (n.sort_scratch) CUDA_TRY(cudaFreeAsync(n.sort_scratch, stream));
         if (n.kept_scratch) CUDA_TRY(cudaFreeAsync(n.kept_scratch, stream));
         if (n.soft_scratch) CUDA_TRY(cudaFreeAsync(n.soft_scratch, stream));
+        if (n.wbf_ints) CUDA_TRY(cudaFreeAsync(n.wbf_ints, stream));
         CUDA_TRY(cudaFreeAsync(n.boxes, stream));
         CUDA_TRY(cudaFreeAsync(d.cand, stream));
         CUDA_TRY(cudaFreeAsync(d.counts, stream));
@@ -362,10 +375,8 @@ int check_post(const mgd_post_config* post)
     if (!post) return fail(MGD_ERR_INVALID_ARGUMENT, "post config is NULL");
     if (post->max_boxes < 1 || post->max_boxes > (1 << 20))
         return fail(MGD_ERR_INVALID_ARGUMENT, "max_boxes must be in [1, 2^20], got %d", post->max_boxes);
-    if (post->nms_method != MGD_NMS_IOU && post->nms_method != MGD_NMS_DIOU &&
-        post->nms_method != MGD_NMS_SOFT)
-        return fail(MGD_ERR_UNSUPPORTED, "nms_method %d: MGD_NMS_IOU / MGD_NMS_DIOU / MGD_NMS_SOFT are built",
-                    post->nms_method);
+    if (post->nms_method < MGD_NMS_IOU || post->nms_method > MGD_NMS_WBF)
+        return fail(MGD_ERR_UNSUPPORTED, "nms_method %d is not built", post->nms_method);
     if (post->confidence != post->confidence || post->nms_threshold != post->nms_threshold)
         return fail(MGD_ERR_INVALID_ARGUMENT, "confidence / nms_threshold is NaN");
     return MGD_OK;
@@ -802,6 +813,79 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
     if (a.kept_scratch) CUDA_TRY(cudaFreeAsync(a.kept_scratch, st));
     CUDA_TRY(cudaFreeAsync(count, st));
     if (staged) CUDA_TRY(cudaFreeAsync(staged, st));
+    if (host || (flags & MGD_FLAG_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
+    return MGD_OK;
+}
+
+int mgd_wbf(const double* boxes, const double* scores, const int* classes,
+            const double* box_weights, int n, double iou_thr, double skip_box_thr, int conf_type,
+            double* out_boxes, double* out_scores, int* out_classes, int* n_out, int memory,
+            int device, void* stream, int flags)
+{
+    int rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (n < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n must be >= 0");
+    if (!n_out) return fail(MGD_ERR_INVALID_ARGUMENT, "n_out is NULL");
+    if (n > 0 && (!boxes || !scores || !classes || !out_boxes || !out_scores || !out_classes))
+        return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    if (conf_type < 0 || conf_type > 2) return fail(MGD_ERR_INVALID_ARGUMENT, "bad conf_type");
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    const bool host = memory == MGD_MEM_HOST;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (host) {
+        cudaStream_t* ss;
+        if ((rc = host_streams(device, &ss))) return rc;
+        st = ss[0];
+    }
+    if (n == 0) {
+        if (host) { *n_out = 0; return MGD_OK; }
+        CUDA_TRY(cudaMemsetAsync(n_out, 0, sizeof(int), st));
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    const size_t nn = (size_t)n;
+    int pow2 = 2;
+    while (pow2 < n) pow2 <<= 1;
+    // staging: boxes 4n | scores n | weights n | fused 5n | out_boxes 4n | out_scores n  (f64)
+    //          sort 2*pow2 (u64) | classes n | out_classes n | ints 4n | counts 2        (i32)
+    unsigned char* buf;
+    const size_t f64s = nn * (4 + 1 + 1 + 5 + 4 + 1);
+    CUDA_TRY(cudaMallocAsync(&buf, f64s * 8 + (size_t)2 * pow2 * 8 + nn * 6 * 4 + 64, st));
+    double* d_boxes = reinterpret_cast<double*>(buf);
+    double* d_scores = d_boxes + 4 * nn;
+    double* d_w = d_scores + nn;
+    double* d_fused = d_w + nn;
+    double* d_ob = d_fused + 5 * nn;
+    double* d_os = d_ob + 4 * nn;
+    unsigned long long* d_sort = reinterpret_cast<unsigned long long*>(d_os + nn);
+    int* d_cls = reinterpret_cast<int*>(d_sort + 2 * (size_t)pow2);
+    int* d_oc = d_cls + nn;
+    int* d_ints = d_oc + nn;
+    int* d_cnt = d_ints + 4 * nn;
+    const cudaMemcpyKind in_kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CUDA_TRY(cudaMemcpyAsync(d_boxes, boxes, nn * 32, in_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(d_scores, scores, nn * 8, in_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cls, classes, nn * 4, in_kind, st));
+    if (box_weights) CUDA_TRY(cudaMemcpyAsync(d_w, box_weights, nn * 8, in_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(d_cnt, &n, sizeof(int), cudaMemcpyHostToDevice, st));
+    NmsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = 1; a.cap = n; a.counts = d_cnt;
+    a.in_boxes = d_boxes; a.in_scores = d_scores; a.in_classes = d_cls;
+    a.in_weights = box_weights ? d_w : nullptr;
+    a.max_boxes = n;
+    a.wbf = 1; a.wbf_conf_type = conf_type; a.thr = iou_thr; a.soft_thr = skip_box_thr;
+    a.soft_scratch = d_fused; a.wbf_ints = d_ints;
+    a.sort_scratch = d_sort; a.sort_scratch_stride = pow2;
+    a.out_xywh = d_ob; a.out_scores = d_os; a.out_classes = d_oc; a.out_counts = d_cnt + 1;
+    CUDA_TRY(launch_nms(a, num_sms, st));
+    const cudaMemcpyKind out_kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CUDA_TRY(cudaMemcpyAsync(out_boxes, d_ob, nn * 32, out_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(out_scores, d_os, nn * 8, out_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(out_classes, d_oc, nn * 4, out_kind, st));
+    CUDA_TRY(cudaMemcpyAsync(n_out, d_cnt + 1, sizeof(int), out_kind, st));
+    CUDA_TRY(cudaFreeAsync(buf, st));
     if (host || (flags & MGD_FLAG_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
     return MGD_OK;
 }

@@ -88,7 +88,12 @@ struct NmsArgs {
     int skip_small;                   // nms_kernel: skip images with <= this many candidates
     int soft;                         // 1: Gaussian SoftNMS (soft_nms_kernel)
     double soft_sigma, soft_thr;
-    double* soft_scratch;             // (B, cap) decayed scores
+    double* soft_scratch;             // soft: (B, cap) decayed scores; wbf: (B, cap, 5) fused clusters
+    int wbf;                          // 1: weighted boxes fusion (wbf_kernel); thr = iou_thr,
+                                      //    soft_thr = skip_box_thr
+    int wbf_conf_type;                // 0 avg, 1 max, 2 mean(score * weight)
+    const double* in_weights;         // explicit mode: per-box model weight or nullptr
+    int* wbf_ints;                    // (B, 4, cap) int scratch
     int* next_image;                  // nms_warp_kernel: work counter (zeroed by the caller)
     unsigned long long* sort_scratch; // (B, 2*pow2(cap)) u64, used when count > smem capacity
     int sort_scratch_stride;          // elements (pairs) per image in sort_scratch

@@ -689,6 +689,249 @@ soft_nms_kernel(const __grid_constant__ NmsArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Weighted Boxes Fusion as the reference implements it (multigriddet/postprocess/
+// wbf.py:98-218): per class, boxes sorted by score; every still unused box becomes a
+// cluster leader and absorbs the later unused boxes of its class whose IoU WITH THE
+// LEADER is >= iou_thr; a cluster is fused into the (score x weight)-weighted mean box
+// and a fused confidence (mean / max / mean of score x weight).  One CTA per image:
+// clustering is a leader loop with one barrier per leader, fusion is one thread per
+// leader walking its members in the reference's order (deterministic, NumPy's float64
+// summation order), output in (class asc, leader score desc) order, or the top
+// max_boxes by fused score when there are more (multigrid_decode.py:336-345).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double wbf_iou(const BoxD& a, const BoxD& b)      // wbf.py:220-250
+{
+    const double x0 = fmax(a.x, b.x), y0 = fmax(a.y, b.y);
+    const double x1 = fmin(__dadd_rn(a.x, a.w), __dadd_rn(b.x, b.w));
+    const double y1 = fmin(__dadd_rn(a.y, a.h), __dadd_rn(b.y, b.h));
+    if (x1 <= x0 || y1 <= y0) return 0.0;
+    const double inter = __dmul_rn(__dsub_rn(x1, x0), __dsub_rn(y1, y0));
+    const double uni = __dsub_rn(__dadd_rn(__dmul_rn(a.w, a.h), __dmul_rn(b.w, b.h)), inter);
+    return uni > 0.0 ? __ddiv_rn(inter, uni) : 0.0;
+}
+
+// NumPy float64 add.reduce order (pairwise, 8 accumulators); get(k) returns the k-th term
+template <typename F>
+__device__ double np_sum_f64(F get, int first, int n)
+{
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, get(first + i));
+        return res;
+    }
+    if (n <= 128) {
+        double r[8];
+        for (int j = 0; j < 8; ++j) r[j] = get(first + j);
+        int i = 8;
+        for (; i < n - (n & 7); i += 8)
+            for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], get(first + i + j));
+        double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                               __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __dadd_rn(res, get(first + i));
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 & 7;
+    return __dadd_rn(np_sum_f64(get, first, n2), np_sum_f64(get, first + n2, n - n2));
+}
+
+__global__ void __launch_bounds__(kThreads)
+wbf_kernel(const __grid_constant__ NmsArgs a)
+{
+    __shared__ uint64_t s_tab[MGD_EXP2F_N];
+    __shared__ int s_count, s_clusters;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int M = a.counts[b];
+    const Cand* cand = a.cand ? a.cand + (size_t)b * a.cap : nullptr;
+    const BoxD* boxes = a.cand ? a.boxes + (size_t)b * a.cap
+                               : reinterpret_cast<const BoxD*>(a.in_boxes);
+    // per-image scratch, all indexed by sorted position
+    int mpad = 2;
+    while (mpad < M) mpad <<= 1;
+    unsigned long long* key = a.sort_scratch + (size_t)b * 2 * a.sort_scratch_stride;   // fused-score keys
+    unsigned long long* val = key + a.sort_scratch_stride;
+    int* order = a.wbf_ints + (size_t)b * 4 * a.cap;     // sorted position -> candidate position
+    int* leader_of = order + a.cap;                      // sorted position -> leader's sorted position
+    int* member = leader_of + a.cap;                     // cluster member lists (sorted positions)
+    int* tmp = member + a.cap;
+    double* fused = a.soft_scratch + (size_t)b * a.cap * 5;   // per cluster rank: x y w h score
+
+    if (tid < MGD_EXP2F_N) s_tab[tid] = mgd_exp2f_tab[tid];
+    if (tid == 0) { s_count = 0; s_clusters = 0; }
+    __syncthreads();
+    if (cand) {
+        const HeadGeom& g = a.g;
+        const int ih = a.image_hw ? a.image_hw[2 * b] : a.in_h;
+        const int iw = a.image_hw ? a.image_hw[2 * b + 1] : a.in_w;
+        const Letterbox lb = letterbox_consts(g.in_h, g.in_w, ih, iw);
+        BoxD* out = a.boxes + (size_t)b * a.cap;
+        for (int i = tid; i < M; i += kThreads) {
+            const Cand cd = cand[i];
+            int layer = 0;
+            while (layer + 1 < g.L && cd.index >= g.cell_off[layer + 1]) ++layer;
+            const int cell = cd.index - g.cell_off[layer];
+            const int rr = cell / g.gw[layer], cc = cell - rr * g.gw[layer];
+            BoxD bx;
+            decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 0, s_tab, bx.x, bx.w);
+            decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 1, s_tab, bx.y, bx.h);
+            out[i] = bx;
+        }
+    }
+    auto score_of = [&](int pos) { return cand ? (double)cand[pos].score : a.in_scores[pos]; };
+    auto class_of = [&](int pos) { return cand ? cand[pos].cls : (a.in_classes ? a.in_classes[pos] : 0); };
+    auto weight_of = [&](int pos) { return a.in_weights ? a.in_weights[pos] : 1.0; };
+    auto index_of = [&](int pos) { return cand ? cand[pos].index : pos; };
+
+    // ---- sort positions by (class asc, score desc, index asc); skipped boxes last -----------
+    // bitonic network on `order` with a comparator that looks the three keys up
+    for (int i = tid; i < mpad; i += kThreads) {
+        const bool ok = i < M && score_of(i) >= a.soft_thr;          // wbf.py:74 skip_box_thr
+        val[i] = ok ? (unsigned long long)i : ~0ull;
+    }
+    __syncthreads();
+    auto before = [&](unsigned long long x, unsigned long long y) {   // strict order
+        if (x == ~0ull || y == ~0ull) return y == ~0ull && x != ~0ull;
+        const int px = (int)x, py = (int)y;
+        const int cx = class_of(px), cy = class_of(py);
+        if (cx != cy) return cx < cy;
+        const double sx = score_of(px), sy = score_of(py);
+        if (sx != sy) return sx > sy;
+        return index_of(px) < index_of(py);
+    };
+    for (int k = 2; k <= mpad; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = tid; i < mpad; i += kThreads) {
+                const int p = i ^ jj;
+                if (p > i) {
+                    const unsigned long long va = val[i], vb = val[p];
+                    const bool up = (i & k) == 0;
+                    if (before(vb, va) == up && va != vb) { val[i] = vb; val[p] = va; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    int n_valid = 0;
+    for (int i = tid; i < M; i += kThreads) {
+        const bool ok = val[i] != ~0ull;
+        n_valid += ok;
+        order[i] = ok ? (int)val[i] : -1;
+        leader_of[i] = -1;
+    }
+    if (n_valid) atomicAdd(&s_count, n_valid);
+    __syncthreads();
+    const int V = s_count;                                     // boxes that take part
+    __syncthreads();
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+
+    // ---- clustering: leader loop (wbf.py:159-183) -------------------------------------------
+    for (int i = 0; i < V; ++i) {
+        if (leader_of[i] >= 0) continue;                       // already absorbed (uniform)
+        const int pi = order[i];
+        const BoxD lbx = boxes[pi];
+        const int lcls = class_of(pi);
+        if (tid == 0) leader_of[i] = i;
+        for (int j = i + 1 + tid; j < V; j += kThreads) {
+            if (leader_of[j] >= 0) continue;
+            const int pj = order[j];
+            if (class_of(pj) != lcls) continue;
+            if (wbf_iou(lbx, boxes[pj]) >= a.thr) leader_of[j] = i;
+        }
+        __syncthreads();
+    }
+
+    // ---- fusion: one thread per leader, members in sorted order (wbf.py:189-213) ---------------
+    for (int i = tid; i < V; i += kThreads) {
+        if (leader_of[i] != i) continue;
+        int n = 0, rank = 0;
+        for (int j = 0; j < i; ++j) rank += leader_of[j] == j;     // clusters before this one
+        for (int j = i; j < V; ++j) n += leader_of[j] == i;
+        const int base = atomicAdd(&s_count, n);
+        int w = 0;
+        for (int j = i; j < V && w < n; ++j)
+            if (leader_of[j] == i) member[base + w++] = j;
+        auto sw = [&](int k) { const int p = order[member[k]]; return __dmul_rn(score_of(p), weight_of(p)); };
+        const double total = np_sum_f64(sw, base, n);
+        auto tw = [&](int k) { return __ddiv_rn(sw(k), total); };
+        const double scl = np_sum_f64(tw, base, n);                 // np.average: weights.sum()
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < n; ++k) {                               // axis-0 reduction: row by row
+            const BoxD bx = boxes[order[member[base + k]]];
+            const double t = tw(base + k);
+            acc[0] = __dadd_rn(acc[0], __dmul_rn(bx.x, t)); acc[1] = __dadd_rn(acc[1], __dmul_rn(bx.y, t));
+            acc[2] = __dadd_rn(acc[2], __dmul_rn(bx.w, t)); acc[3] = __dadd_rn(acc[3], __dmul_rn(bx.h, t));
+        }
+        double conf;
+        if (a.wbf_conf_type == 1) {                                 // 'max'
+            conf = score_of(order[member[base]]);
+            for (int k = 1; k < n; ++k) conf = fmax(conf, score_of(order[member[base + k]]));
+        } else if (a.wbf_conf_type == 2) {                          // mean(score * weight)
+            conf = __ddiv_rn(np_sum_f64(sw, base, n), (double)n);
+        } else {                                                    // 'avg'
+            auto sc = [&](int k) { return score_of(order[member[k]]); };
+            conf = __ddiv_rn(np_sum_f64(sc, base, n), (double)n);
+        }
+        double* f = fused + (size_t)rank * 5;
+        f[0] = __ddiv_rn(acc[0], scl); f[1] = __ddiv_rn(acc[1], scl);
+        f[2] = __ddiv_rn(acc[2], scl); f[3] = __ddiv_rn(acc[3], scl);
+        f[4] = conf;
+        tmp[rank] = i;                                              // cluster rank -> leader position
+        atomicAdd(&s_clusters, 1);
+    }
+    __syncthreads();
+    const int K = s_clusters;
+
+    // ---- output order ---------------------------------------------------------------------------
+    const bool by_score = K > a.max_boxes;
+    int kpad = 2;
+    while (kpad < K) kpad <<= 1;
+    if (by_score) {
+        for (int i = tid; i < kpad; i += kThreads) {
+            key[i] = i < K ? score_key(fused[(size_t)i * 5 + 4]) : ~0ull;
+            val[i] = i < K ? (unsigned long long)i : ~0ull;
+        }
+        __syncthreads();
+        cta_bitonic(key, val, kpad, tid);
+    }
+    const int n_out = min(K, a.max_boxes);
+    const double W = (double)(a.image_hw ? a.image_hw[2 * b + 1] : a.in_w);
+    const double H = (double)(a.image_hw ? a.image_hw[2 * b] : a.in_h);
+    for (int q = tid; q < a.max_boxes; q += kThreads) {
+        const size_t o = (size_t)b * a.max_boxes + q;
+        if (q < n_out) {
+            const int rank = by_score ? (int)val[q] : q;
+            const double* f = fused + (size_t)rank * 5;
+            const int lead_pos = order[tmp[rank]];
+            if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = f[e];
+            if (a.out_xyxy) {
+                a.out_xyxy[o * 4 + 0] = (int)floor(__dadd_rn(clipd(f[0], 0.0, W), 0.5));
+                a.out_xyxy[o * 4 + 1] = (int)floor(__dadd_rn(clipd(f[1], 0.0, H), 0.5));
+                a.out_xyxy[o * 4 + 2] = (int)floor(__dadd_rn(clipd(__dadd_rn(f[0], f[2]), 0.0, W), 0.5));
+                a.out_xyxy[o * 4 + 3] = (int)floor(__dadd_rn(clipd(__dadd_rn(f[1], f[3]), 0.0, H), 0.5));
+            }
+            if (a.out_scores) a.out_scores[o] = f[4];
+            if (a.out_classes) a.out_classes[o] = class_of(lead_pos);
+            if (a.out_index) a.out_index[o] = index_of(lead_pos);
+        } else {
+            if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = 0.0;
+            if (a.out_xyxy) for (int e = 0; e < 4; ++e) a.out_xyxy[o * 4 + e] = 0;
+            if (a.out_scores) a.out_scores[o] = 0.0;
+            if (a.out_classes) a.out_classes[o] = -1;
+            if (a.out_index) a.out_index[o] = -1;
+        }
+    }
+    if (tid == 0) {
+        a.out_counts[b] = n_out;
+        if (a.stats) {
+            atomicAdd(&a.stats[0], (unsigned long long)M);
+            atomicAdd(&a.stats[1], (unsigned long long)n_out);
+        }
+    }
+}
+
 __global__ void keep_from_index_kernel(const int* index, const int* counts, int max_keep,
                                        int* keep, int* n_keep)
 {
@@ -710,6 +953,11 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
     prof_mark_begin(PROF_NMS, stream);
     if (a.soft) {
         soft_nms_kernel<<<a.B, kThreads, 0, stream>>>(a);
+        prof_mark_end(PROF_NMS, stream);
+        return cudaGetLastError();
+    }
+    if (a.wbf) {
+        wbf_kernel<<<a.B, kThreads, 0, stream>>>(a);
         prof_mark_end(PROF_NMS, stream);
         return cudaGetLastError();
     }

@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 
 _NMS_METHODS = {"diou": _lib.NMS_DIOU, "standard": _lib.NMS_IOU, "iou": _lib.NMS_IOU,
-                "cluster": _lib.NMS_IOU, "soft": _lib.NMS_SOFT}
+                "cluster": _lib.NMS_IOU, "soft": _lib.NMS_SOFT, "wbf": _lib.NMS_WBF}
 
 
 def _is_torch(x) -> bool:
@@ -48,7 +48,7 @@ def post_config(max_boxes=100, confidence=0.1, nms_threshold=0.5, nms_method="di
     if nms_method not in _NMS_METHODS:
         raise NotImplementedError(
             f"nms_method={nms_method!r}: the CUDA path implements 'diou', 'standard', "
-            "'cluster' (greedy hard NMS) and 'soft' (Gaussian SoftNMS); WBF is not built yet")
+            "'cluster' (greedy hard NMS), 'soft' (Gaussian SoftNMS) and 'wbf' (use_wbf=True)")
     pc = _lib.PostConfig()
     pc.use_softmax = int(bool(use_softmax))
     pc.rescore_confidence = int(bool(rescore_confidence))
@@ -250,6 +250,38 @@ def decode_dense(preds, anchors, num_classes, model_image_size, image_shapes=Non
     return out
 
 
+_WBF_CONF = {"avg": 0, "max": 1, "box_and_model_avg": 2, "absent_model_aware_avg": 2}
+
+
+def wbf(boxes, scores, classes, box_weights=None, iou_thr=0.55, skip_box_thr=0.0, conf_type="avg"):
+    """Weighted boxes fusion of (n,4) xywh float64 boxes (reference wbf.py semantics):
+    (fused boxes, fused scores, classes) in (class asc, leader score desc) order."""
+    lib = _lib.load()
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
+    s = np.ascontiguousarray(np.asarray(scores, dtype=np.float64).reshape(-1))
+    c = np.ascontiguousarray(np.asarray(classes).astype(np.int32).reshape(-1))
+    n = b.shape[0]
+    if s.shape[0] != n or c.shape[0] != n:
+        raise ValueError("boxes, scores and classes disagree on n")
+    w = None
+    if box_weights is not None:
+        w = np.ascontiguousarray(np.asarray(box_weights, dtype=np.float64).reshape(-1))
+    ob = np.empty((max(n, 1), 4), dtype=np.float64)
+    osc = np.empty((max(n, 1),), dtype=np.float64)
+    oc = np.empty((max(n, 1),), dtype=np.int32)
+    n_out = ctypes.c_int(0)
+    rc = lib.mgd_wbf(ctypes.c_void_p(b.ctypes.data), ctypes.c_void_p(s.ctypes.data),
+                     ctypes.c_void_p(c.ctypes.data),
+                     ctypes.c_void_p(w.ctypes.data) if w is not None else None, n, float(iou_thr),
+                     float(skip_box_thr), _WBF_CONF.get(conf_type, 0), ctypes.c_void_p(ob.ctypes.data),
+                     ctypes.c_void_p(osc.ctypes.data), ctypes.c_void_p(oc.ctypes.data),
+                     ctypes.cast(ctypes.byref(n_out), ctypes.c_void_p), _lib.MEM_HOST,
+                     _current_device(), None, _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    k = n_out.value
+    return ob[:k].copy(), osc[:k].copy(), oc[:k].copy()
+
+
 def soft_nms(boxes, scores, sigma=0.5, score_threshold=0.001):
     """Gaussian SoftNMS on (n,4) xywh float64 boxes: (kept positions in input order,
     their decayed scores)."""
@@ -276,7 +308,7 @@ def nms(boxes, scores, classes=None, nms_threshold=0.5, nms_method="diou", per_c
         max_keep=0):
     """Greedy NMS on (n,4) xywh float64 boxes; returns kept positions (descending score)."""
     lib = _lib.load()
-    if nms_method not in _NMS_METHODS or nms_method == "soft":
+    if nms_method not in _NMS_METHODS or nms_method in ("soft", "wbf"):
         raise NotImplementedError(f"nms_method={nms_method!r} is not a greedy hard NMS")
     b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 4))
     s = np.ascontiguousarray(np.asarray(scores, dtype=np.float64).reshape(-1))

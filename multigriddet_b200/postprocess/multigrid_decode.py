@@ -14,6 +14,7 @@ import numpy as np
 
 from .. import engine
 from .nms import NMS, ClusterNMS, DIoUNMS, SoftNMS, StandardNMS
+from .wbf import WeightedBoxesFusion
 
 _EMPTY = lambda: (np.array([]), np.array([]), np.array([]))     # multigrid_decode.py:273-274
 
@@ -65,14 +66,22 @@ class MultiGridDecoder:
                            use_iol: bool = True, nms_method: str = "diou", use_wbf: bool = False):
         """Threshold + NMS + top-k on a decoded, corrected tensor (reference :237-345).
         Candidate selection is indexing glue; the NMS itself runs on the GPU."""
-        if use_wbf:
-            raise NotImplementedError("Weighted Boxes Fusion is not part of the CUDA path yet")
         scores_all = predictions[..., 4]
         classes_all = np.argmax(predictions[..., 5:], axis=-1)
         pos = np.where(scores_all >= confidence)
         if len(pos[0]) == 0:
             return _EMPTY()
         boxes, classes, scores = predictions[..., 0:4][pos], classes_all[pos], scores_all[pos]
+        if use_wbf:                                                          # :281-287
+            n_boxes, n_classes, n_scores = WeightedBoxesFusion(iou_thr=nms_threshold).fuse_boxes(
+                [boxes], [classes], [scores], image_shape)
+            if not n_boxes:
+                return _EMPTY()
+            boxes, classes, scores = n_boxes[0], n_classes[0].astype("int32"), n_scores[0]
+            if len(boxes) <= max_boxes:
+                return boxes, classes, scores
+            top = np.argsort(-scores, kind="stable")[:max_boxes]
+            return boxes[top], classes[top], scores[top]
         nms = {"diou": DIoUNMS, "cluster": ClusterNMS, "standard": StandardNMS,
                "soft": SoftNMS}.get(nms_method, NMS)
         nms = nms() if nms is SoftNMS else nms(use_iol=use_iol)
@@ -100,8 +109,8 @@ class MultiGridDecoder:
         ('standard' raises ``NotImplementedError`` in the reference; here it is IoU greedy NMS).
         """
         if use_wbf:
-            raise NotImplementedError("Weighted Boxes Fusion is not part of the CUDA path yet")
-        if nms_method not in ("diou", "cluster", "standard", "soft"):
+            nms_method = "wbf"                      # fusion with iou_thr = nms_threshold, :283
+        elif nms_method not in ("diou", "cluster", "standard", "soft"):
             raise NotImplementedError(f"nms_method={nms_method!r} is not part of the CUDA path")
         if not self._usable(multigriddet_outputs):
             return _EMPTY()

@@ -97,6 +97,8 @@ def decode_cases():
         dict(image_shape=(375, 500), confidence=0.3, nms_threshold=0.3, nms_method="diou", max_boxes=100),
         dict(image_shape=(480, 640), confidence=0.001, nms_threshold=0.45, nms_method="soft", max_boxes=100),
         dict(image_shape=None, confidence=0.001, nms_threshold=0.45, nms_method="soft", max_boxes=4),
+        dict(image_shape=(427, 640), confidence=0.001, nms_threshold=0.55, nms_method="wbf", max_boxes=100),
+        dict(image_shape=None, confidence=0.05, nms_threshold=0.4, nms_method="wbf", max_boxes=3),
     ]
     for i, (name, S, C, B, N, dt) in enumerate(cases):
         anchors = synth.coco_anchors(dt)
@@ -128,7 +130,8 @@ def decode_cases():
                     bx, cl, sc = dec.postprocess(one, ishape, (S, S), max_boxes=kn["max_boxes"],
                                                  confidence=kn["confidence"],
                                                  nms_threshold=kn["nms_threshold"],
-                                                 nms_method=kn["nms_method"], return_xyxy=xyxy)
+                                                 nms_method="diou" if kn["nms_method"] == "wbf" else kn["nms_method"],
+                                                 use_wbf=kn["nms_method"] == "wbf", return_xyxy=xyxy)
                     tag = "xyxy" if xyxy else "xywh"
                     store[f"k{k}_b{b}_{tag}"] = np.asarray(bx)
                 store[f"k{k}_b{b}_classes"] = np.asarray(cl)
@@ -155,6 +158,14 @@ def nms_cases():
                 kb, kc, ks = cls().apply_nms(boxes, classes, scores, thr, 0.0)
                 store[f"n{i}_{name}_{thr}_scores"] = ks[0]
                 store[f"n{i}_{name}_{thr}_boxes"] = kb[0]
+        half = n // 2
+        for ct in ("avg", "max", "box_and_model_avg"):
+            fb, fc, fs = post.WeightedBoxesFusion(iou_thr=0.4, skip_box_thr=0.05, conf_type=ct).fuse_boxes(
+                [boxes[:half], boxes[half:]], [classes[:half], classes[half:]],
+                [scores[:half], scores[half:]], (600, 600), weights=[1.0, 0.6])
+            store[f"n{i}_wbf_{ct}_boxes"] = fb[0] if fb else np.zeros((0, 4))
+            store[f"n{i}_wbf_{ct}_scores"] = fs[0] if fs else np.zeros((0,))
+            store[f"n{i}_wbf_{ct}_classes"] = fc[0] if fc else np.zeros((0,), np.int64)
         for sigma in (0.5, 0.1):
             kb, kc, ks = post.SoftNMS(sigma=sigma).apply_nms(boxes, classes, scores, 0.5, 0.0)
             store[f"n{i}_soft_{sigma}_scores"] = ks[0]

@@ -360,6 +360,63 @@ def soft_nms(boxes, scores, sigma=0.5, score_threshold=0.001, tiebreak=None):
     return keep, s[keep]
 
 
+def wbf_iou(a, b):
+    """Scalar IoU of two xywh boxes as wbf.py:220-250 computes it (no epsilon)."""
+    x0, y0 = max(a[0], b[0]), max(a[1], b[1])
+    x1, y1 = min(a[0] + a[2], b[0] + b[2]), min(a[1] + a[3], b[1] + b[3])
+    if x1 <= x0 or y1 <= y0:
+        return 0.0
+    inter = (x1 - x0) * (y1 - y0)
+    union = a[2] * a[3] + b[2] * b[3] - inter
+    return inter / union if union > 0 else 0.0
+
+
+def weighted_boxes_fusion(boxes, scores, classes, box_weights=None, iou_thr=0.55,
+                          skip_box_thr=0.0, conf_type="avg", tiebreak=None):
+    """The reference's box fusion (wbf.py:38-218) on the concatenated boxes of all models.
+
+    Per class (ascending id): boxes in descending score order; each unused box leads a
+    cluster and absorbs the later unused boxes whose IoU with the LEADER is >= iou_thr;
+    a cluster becomes its (score x weight)-weighted mean box and a fused confidence.
+    Returns (fused boxes, fused scores, classes, leader positions)."""
+    boxes = np.asarray(boxes, dtype=np.float64).reshape(-1, 4)
+    scores = np.asarray(scores, dtype=np.float64).reshape(-1)
+    classes = np.asarray(classes).reshape(-1)
+    n = len(boxes)
+    weights = np.ones(n) if box_weights is None else np.asarray(box_weights, dtype=np.float64)
+    if tiebreak is None:
+        tiebreak = np.arange(n)
+    live = np.nonzero(scores >= skip_box_thr)[0]                      # wbf.py:74
+    out_b, out_s, out_c, out_lead = [], [], [], []
+    for cls in np.unique(classes[live]):                              # wbf.py:98
+        members = live[classes[live] == cls]
+        order = members[np.lexsort((tiebreak[members], -scores[members]))]   # wbf.py:150
+        used = np.zeros(len(order), dtype=bool)
+        for i in range(len(order)):
+            if used[i]:
+                continue
+            group = [order[i]]
+            for j in range(i + 1, len(order)):
+                if not used[j] and wbf_iou(boxes[order[i]], boxes[order[j]]) >= iou_thr:
+                    group.append(order[j])
+                    used[j] = True
+            g = np.array(group)
+            w = scores[g] * weights[g]                                # wbf.py:198-199
+            w = w / np.sum(w)
+            out_b.append(np.average(boxes[g], axis=0, weights=w))     # wbf.py:202
+            if conf_type == "max":
+                out_s.append(np.max(scores[g]))
+            elif conf_type in ("box_and_model_avg", "absent_model_aware_avg"):
+                out_s.append(np.mean(scores[g] * weights[g]))
+            else:
+                out_s.append(np.mean(scores[g]))
+            out_c.append(cls)
+            out_lead.append(order[i])
+    if not out_b:
+        return np.zeros((0, 4)), np.zeros((0,)), np.zeros((0,), np.int64), np.zeros((0,), np.int64)
+    return np.array(out_b), np.array(out_s), np.array(out_c), np.array(out_lead)
+
+
 _GREEDY = {"diou": True, "cluster": False, "standard": False, "iou": False}
 
 
@@ -389,6 +446,15 @@ def postprocess_image(preds, image_shape, model_image_size, anchors, num_classes
     boxes = cor[cand, 0:4]
     scores = score[cand]
     classes = cls_all[cand]
+    if nms_method == "wbf":                                           # use_wbf=True, :281-287
+        fb, fs, fc, lead = weighted_boxes_fusion(boxes, scores, classes, iou_thr=nms_threshold,
+                                                 tiebreak=cand)
+        if len(fb) > max_boxes:                                       # :336-345
+            top = np.lexsort((np.arange(len(fs)), -fs))[:max_boxes]
+            fb, fs, fc, lead = fb[top], fs[top], fc[top], lead[top]
+        return {"boxes_xywh": fb, "boxes_xyxy": to_xyxy(fb, image_shape),
+                "classes": fc.astype(np.int32), "scores": fs,
+                "index": cand[lead].astype(np.int64), "n_candidates": int(len(cand))}
     if nms_method == "soft":
         keep, soft = soft_nms(boxes, scores, tiebreak=cand)
         # multigrid_decode.py:336-345: stays in input order unless > max_boxes

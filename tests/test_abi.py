@@ -71,7 +71,7 @@ def test_argument_validation_without_a_device(lib):
     with pytest.raises(ValueError):
         engine.decode_nms(preds, None, (608, 608), anchors, 80, max_boxes=0)
     with pytest.raises(NotImplementedError):
-        engine.decode_nms(preds, None, (608, 608), anchors, 80, nms_method="wbf")
+        engine.decode_nms(preds, None, (608, 608), anchors, 80, nms_method="fuse")
     with pytest.raises(ValueError):                    # wrong channel count
         engine.decode_nms(preds, None, (608, 608), anchors, 20)
 

@@ -10,6 +10,7 @@ import golden_util as G
 from multigriddet_b200 import engine, _lib
 from multigriddet_b200.data import MultiGridTargetEncoder, MultiGridConfig, preprocess_true_boxes
 from multigriddet_b200.postprocess import (ClusterNMS, DIoUNMS, MultiGridDecoder, SoftNMS, StandardNMS,
+                                           WeightedBoxesFusion,
                                            multigriddet_postprocess_gpu, nms_boxes)
 
 pytestmark = pytest.mark.gpu
@@ -52,6 +53,9 @@ def test_postprocess_against_reference_golden(path):
     np.testing.assert_allclose(dense[:, ::37, :4], z["dense_sample"][..., :4], rtol=1e-5, atol=1e-7)
     for k, kn in G.knobs_of(z):
         ishape = kn.pop("image_shape")
+        wbf = kn["nms_method"] == "wbf"
+        if wbf:
+            kn = dict(kn, nms_method="diou", use_wbf=True)
         for b in range(B):
             one = [p[b:b + 1] for p in preds]
             boxes, classes, scores = dec.postprocess(one, ishape, (S, S), **kn)
@@ -62,8 +66,8 @@ def test_postprocess_against_reference_golden(path):
                 continue
             # the reference's container types
             assert boxes.dtype == np.int32 and classes.dtype == np.int32 and scores.dtype == np.float64
-            if kn["nms_method"] == "soft":
-                np.testing.assert_allclose(scores, ref_s, rtol=1e-5)   # decay depends on the boxes (1e-5 bar)
+            if kn["nms_method"] == "soft" or wbf:
+                np.testing.assert_allclose(scores, ref_s, rtol=1e-5)   # depend on the boxes (1e-5 bar)
             else:
                 assert np.array_equal(scores, ref_s)        # float32 scores reproduced bit-for-bit
             assert np.array_equal(classes, z[f"k{k}_b{b}_classes"])
@@ -79,7 +83,7 @@ def test_postprocess_against_reference_golden(path):
         kn2 = dict(kn)
         batch = dec.postprocess_batch(preds, [ishape] * B, (S, S), kn2.pop("max_boxes"),
                                       kn2.pop("confidence"), kn2.pop("nms_threshold"),
-                                      kn2.pop("nms_method"))
+                                      "wbf" if wbf else kn2.pop("nms_method"))
         for b in range(B):
             np.testing.assert_allclose(batch[b][2], z[f"k{k}_b{b}_scores"], rtol=1e-5)
 
@@ -97,6 +101,18 @@ def test_nms_classes_against_reference_golden():
                 assert np.array_equal(kb[0], z[f"n{i}_{name}_{thr}_boxes"])
         kb, kc, ks = nms_boxes(boxes, classes, scores, 0.5, use_diou=True)
         assert np.array_equal(ks[0], z[f"n{i}_diou_0.5_scores"])
+        half = len(boxes) // 2
+        for ct in ("avg", "max", "box_and_model_avg"):
+            fb, fc, fs = WeightedBoxesFusion(iou_thr=0.4, skip_box_thr=0.05, conf_type=ct).fuse_boxes(
+                [boxes[:half], boxes[half:]], [classes[:half], classes[half:]],
+                [scores[:half], scores[half:]], (600, 600), weights=[1.0, 0.6])
+            ref_b = z[f"n{i}_wbf_{ct}_boxes"]
+            if len(ref_b) == 0:
+                assert fb == []
+                continue
+            np.testing.assert_allclose(fb[0], ref_b, rtol=1e-12)
+            np.testing.assert_allclose(fs[0], z[f"n{i}_wbf_{ct}_scores"], rtol=1e-12)
+            assert np.array_equal(fc[0], z[f"n{i}_wbf_{ct}_classes"])
         for sigma in (0.5, 0.1):
             kb, kc, ks = SoftNMS(sigma=sigma).apply_nms(boxes, classes, scores, 0.5, 0.0)
             np.testing.assert_allclose(ks[0], z[f"n{i}_soft_{sigma}_scores"], rtol=1e-12)

@@ -252,7 +252,7 @@ def test_decode_empty_and_threshold_edges(c_oracle):
     with pytest.raises(ValueError):
         engine.decode_nms(preds[:2], (S, S), (S, S), anchors, C)
     with pytest.raises(NotImplementedError):
-        engine.decode_nms(preds, (S, S), (S, S), anchors, C, nms_method="wbf")
+        engine.decode_nms(preds, (S, S), (S, S), anchors, C, nms_method="fuse")
 
 
 def test_decode_device_tensors_match_host_path(c_oracle):
@@ -475,5 +475,40 @@ def test_postprocess_soft_matches_oracle(c_oracle):
             assert np.array_equal(got["index"][b, :k], ref[b]["index"])
             assert np.array_equal(got["classes"][b, :k], ref[b]["classes"])
             # decayed scores inherit the 1e-5 box tolerance (np.tanh is not bit-reproducible)
+            np.testing.assert_allclose(got["scores"][b, :k], ref[b]["scores"], rtol=RTOL)
+            np.testing.assert_allclose(got["boxes_xywh"][b, :k], ref[b]["boxes_xywh"], rtol=RTOL, atol=1e-4)
+
+
+def test_wbf_matches_oracle(c_oracle):
+    from oracle import mgd_oracle as O
+    rng = np.random.default_rng(11)
+    for n in (1, 9, 300, 2600):
+        xy = rng.uniform(0, 250, size=(n, 2))
+        wh = rng.uniform(8, 100, size=(n, 2))
+        boxes = np.concatenate([xy, wh], 1)
+        scores = rng.uniform(0.01, 1, size=n)
+        classes = rng.integers(0, 4, size=n)
+        w = rng.choice([1.0, 0.5], size=n)
+        for ct in ("avg", "max", "box_and_model_avg"):
+            rb, rs, rc, _ = O.weighted_boxes_fusion(boxes, scores, classes, w, iou_thr=0.5,
+                                                    skip_box_thr=0.1, conf_type=ct)
+            gb, gs, gc = engine.wbf(boxes, scores, classes, w, 0.5, 0.1, ct)
+            assert np.array_equal(gc, rc), (n, ct)
+            np.testing.assert_allclose(gb, rb, rtol=1e-12)
+            np.testing.assert_allclose(gs, rs, rtol=1e-12)
+    # through the decode path (use_wbf=True)
+    S, C, B = 608, 80, 3
+    anchors = synth.coco_anchors(np.float32)
+    preds = _planted(41, B, S, C, 60, anchors, c_oracle)
+    shapes = synth.image_shapes(7, B)
+    for max_boxes in (100, 5):
+        kw = dict(max_boxes=max_boxes, confidence=0.001, nms_threshold=0.55, nms_method="wbf")
+        ref = O.postprocess_batch(preds, shapes, (S, S), anchors, C, **kw)
+        got = engine.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+        for b in range(B):
+            k = len(ref[b]["index"])
+            assert int(got["counts"][b]) == k
+            assert np.array_equal(got["index"][b, :k], ref[b]["index"])
+            assert np.array_equal(got["classes"][b, :k], ref[b]["classes"])
             np.testing.assert_allclose(got["scores"][b, :k], ref[b]["scores"], rtol=RTOL)
             np.testing.assert_allclose(got["boxes_xywh"][b, :k], ref[b]["boxes_xywh"], rtol=RTOL, atol=1e-4)

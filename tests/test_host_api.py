@@ -23,9 +23,6 @@ def test_decoder_shim_conventions():
         dec.decode_predictions([np.zeros((1, 19, 19, 88), np.float32)] * 2)
     with pytest.raises(NotImplementedError):
         dec.postprocess([np.zeros((1, g, g, 88), np.float32) for g in (19, 38, 76)],
-                        (608, 608), (608, 608), use_wbf=True)
-    with pytest.raises(NotImplementedError):
-        dec.postprocess([np.zeros((1, g, g, 88), np.float32) for g in (19, 38, 76)],
                         (608, 608), (608, 608), nms_method="wbf-something")
     # an empty scale: the reference returns three empty arrays
     b, c, s = dec.postprocess([np.zeros((0, g, g, 88), np.float32) for g in (19, 38, 76)],

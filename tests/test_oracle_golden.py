@@ -62,7 +62,7 @@ def test_decode_oracles_match_reference_golden(path, c_oracle):
     for k, kn in G.knobs_of(z):
         ishape = kn.pop("image_shape")
         py = O.postprocess_batch(preds, np.tile(np.array(ishape), (B, 1)), (S, S), anchors, C, **kn)
-        soft = kn["nms_method"] == "soft"
+        soft = kn["nms_method"] in ("soft", "wbf")      # restated in NumPy only
         cc = None if soft else c_oracle.decode_nms(preds, [ishape], (S, S), anchors, C, **kn)
         for b in range(B):
             ref_s = z[f"k{k}_b{b}_scores"]
@@ -77,7 +77,7 @@ def test_decode_oracles_match_reference_golden(path, c_oracle):
                                            rtol=1e-6, atol=1e-4)
             assert np.array_equal(py[b]["boxes_xyxy"], z[f"k{k}_b{b}_xyxy"].reshape(-1, 4))
             assert np.array_equal(py[b]["classes"], z[f"k{k}_b{b}_classes"])
-            if soft:           # SoftNMS is restated in NumPy only
+            if soft:
                 continue
             # the C restatement: bit-exact too (NumPy pinned to libm in conftest.py)
             assert np.array_equal(cc["scores"][b, :n], ref_s)
@@ -97,6 +97,14 @@ def test_nms_oracle_matches_reference_golden():
                 keep = O.greedy_nms(boxes, scores, thr, diou)
                 assert np.array_equal(scores[keep], z[f"n{i}_{name}_{thr}_scores"])
                 assert np.array_equal(boxes[keep], z[f"n{i}_{name}_{thr}_boxes"])
+        half = len(boxes) // 2
+        w = np.concatenate([np.full(half, 1.0), np.full(len(boxes) - half, 0.6)])
+        for ct in ("avg", "max", "box_and_model_avg"):
+            fb, fs, fc, _ = O.weighted_boxes_fusion(boxes, scores, z[f"n{i}_classes"], w, iou_thr=0.4,
+                                                    skip_box_thr=0.05, conf_type=ct)
+            assert np.array_equal(fb, z[f"n{i}_wbf_{ct}_boxes"])
+            assert np.array_equal(fs, z[f"n{i}_wbf_{ct}_scores"])
+            assert np.array_equal(fc, z[f"n{i}_wbf_{ct}_classes"])
         for sigma in (0.5, 0.1):
             keep, soft = O.soft_nms(boxes, scores, sigma=sigma)
             assert np.array_equal(soft, z[f"n{i}_soft_{sigma}_scores"])
