@@ -981,6 +981,8 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
         };
         err = run(nms_warp_kernel<kWarpCapLarge>, kWarpCapLarge, kWarpCapLarge / 4);
         if (err != cudaSuccess) return err;
+        prof_mark_end(PROF_NMS, stream);          // one span (= one counted launch) per kernel
+        prof_mark_begin(PROF_NMS, stream);
         a.skip_small = kWarpCapLarge;
     }
     const size_t dyn = a.kept_scratch ? 16 : nms_kept_bytes(a.max_boxes);
