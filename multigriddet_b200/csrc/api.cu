@@ -32,9 +32,8 @@ int fail(int code, const char* fmt, ...)
 // MGD_TRACE=1: print host-side timestamps of the staging path to stderr
 static bool trace_on()
 {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("MGD_TRACE"); v = e && atoi(e) ? 1 : 0; }
-    return v == 1;
+    const char* e = getenv("MGD_TRACE");
+    return e && atoi(e);
 }
 struct Tracer {
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -44,8 +43,9 @@ struct Tracer {
     {
         if (!trace_on()) return;
         const auto t = std::chrono::steady_clock::now();
-        fprintf(stderr, "[mgd %s] %-18s +%.1f us\n", what, stage,
-                std::chrono::duration<double, std::micro>(t - t0).count());
+        fprintf(stderr, "[mgd %s] %-18s +%.1f us (abs %.3f ms)\n", what, stage,
+                std::chrono::duration<double, std::micro>(t - t0).count(),
+                std::chrono::duration<double, std::milli>(t.time_since_epoch()).count());
         t0 = t;
     }
 };
@@ -87,12 +87,97 @@ void prof_mark_end(int kind, cudaStream_t stream)
 namespace {
 
 // ---- per-device state -----------------------------------------------------------
+// All scratch and staging memory comes from a library-owned stream-ordered pool per
+// device (the application's default pool is left alone).  The pool never inserts
+// cross-stream dependencies to reuse a block: a block freed behind a long D2H copy on
+// one stream must not make another stream's H2D wait for that copy (with the default
+// policy concurrent host-memory calls serialised their PCIe directions this way).
 struct DeviceInfo {
     bool ready = false;
     int num_sms = 0;
+    cudaMemPool_t pool = nullptr;
 };
 std::mutex g_mutex;
 DeviceInfo g_dev[64];
+thread_local cudaMemPool_t t_pool = nullptr;     // pool of the device the current call runs on
+
+template <typename T> cudaError_t pool_malloc(T** p, size_t bytes, cudaStream_t stream)
+{
+    return cudaMallocFromPoolAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, t_pool, stream);
+}
+
+// Grow-only bump arena for the host-memory entry points: their staging buffers and
+// per-chunk scratch are carved from memory cached per (host thread, device, stream slot),
+// so a steady-state call performs no allocation at all.  (Per-chunk cudaMallocAsync /
+// cudaFreeAsync made a second host thread's enqueue loop block until the first thread's
+// call had drained, which serialised the two PCIe directions of concurrent calls.)
+// reset() at the start of a chunk is safe because the arena is only ever used by work
+// enqueued on one stream: stream order separates the chunks that share the memory.
+struct Arena {
+    struct Block { char* p; size_t cap; };
+    std::vector<Block> blocks;
+    size_t cur = 0, used = 0;
+    void reset() { cur = 0; used = 0; }
+    struct Mark { size_t cur, used; };
+    Mark mark() const { return Mark{cur, used}; }
+    void rewind(const Mark& m) { cur = m.cur; used = m.used; }
+    cudaError_t take(void** out, size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (bytes == 0) bytes = 256;
+        for (; cur < blocks.size(); ++cur, used = 0)
+            if (used + bytes <= blocks[cur].cap) {
+                *out = blocks[cur].p + used;
+                used += bytes;
+                return cudaSuccess;
+            }
+        Block b;
+        b.cap = bytes > (32u << 20) ? bytes : (32u << 20);
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b.p), b.cap);
+        if (e != cudaSuccess) return e;
+        blocks.push_back(b);
+        cur = blocks.size() - 1;
+        used = bytes;
+        *out = b.p;
+        return cudaSuccess;
+    }
+    // after the call has synchronised: merge a fragmented arena into one block so the
+    // next call of the same shape fits without growing
+    void consolidate()
+    {
+        if (blocks.size() < 2) return;
+        size_t total = 0;
+        for (Block& b : blocks) { total += b.cap; cudaFree(b.p); }
+        blocks.clear();
+        Block b;
+        b.cap = total;
+        if (cudaMalloc(reinterpret_cast<void**>(&b.p), total) == cudaSuccess) blocks.push_back(b);
+        else cudaGetLastError();
+        reset();
+    }
+    void release()
+    {
+        for (Block& b : blocks) cudaFree(b.p);
+        blocks.clear();
+        reset();
+    }
+};
+
+// where a kernel driver takes its scratch from: the stream-ordered pool (device-memory
+// calls: freed back in stream order) or a bump arena (host-memory calls: nothing to free)
+struct Alloc {
+    Arena* arena;
+    cudaStream_t stream;
+    template <typename T> cudaError_t get(T** p, size_t bytes) const
+    {
+        if (arena) return arena->take(reinterpret_cast<void**>(p), bytes);
+        return pool_malloc(p, bytes, stream);
+    }
+    cudaError_t put(void* p) const { return arena || !p ? cudaSuccess : cudaFreeAsync(p, stream); }
+    // arena mode: scratch of one internal chunk is recycled by the next (same stream)
+    Arena::Mark mark() const { return arena ? arena->mark() : Arena::Mark{0, 0}; }
+    void rewind(const Arena::Mark& m) const { if (arena) arena->rewind(m); }
+};
 
 int device_count_quiet()
 {
@@ -120,13 +205,21 @@ int prepare_device(int device, int* num_sms)
                         "device %d is sm_%d%d; libmgd is built for sm_100a (B200) only",
                         device, prop.major, prop.minor);
         d.num_sms = prop.multiProcessorCount;
-        // keep freed scratch in the stream-ordered pool instead of returning it to the OS
-        cudaMemPool_t pool;
-        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        cudaMemPoolProps pp;
+        memset(&pp, 0, sizeof(pp));
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        CUDA_TRY(cudaMemPoolCreate(&d.pool, &pp));
+        // keep freed scratch in the pool instead of returning it to the OS
         unsigned long long keep = ~0ull;
-        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        CUDA_TRY(cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        int off = 0;
+        CUDA_TRY(cudaMemPoolSetAttribute(d.pool, cudaMemPoolReuseAllowInternalDependencies, &off));
         d.ready = true;
     }
+    t_pool = d.pool;
     *num_sms = d.num_sms;
     return MGD_OK;
 }
@@ -239,11 +332,13 @@ int status_to_error(int st)
 struct EncodeScratch { int* table; BoxRec* recs; };
 
 int encode_device(const HeadGeom& g, const float* boxes, int batch, int N, float* const* y,
-                  int num_sms, cudaStream_t stream, int* d_status, unsigned long long* d_stats)
+                  int num_sms, cudaStream_t stream, int* d_status, unsigned long long* d_stats,
+                  const Alloc& al)
 {
     const int step = chunk_images(g, batch);
     for (int b0 = 0; b0 < batch; b0 += step) {
         const int nb = batch - b0 < step ? batch - b0 : step;
+        const Arena::Mark mk = al.mark();
         EncodeArgs a;
         a.g = g;
         a.B = nb;
@@ -255,13 +350,14 @@ int encode_device(const HeadGeom& g, const float* boxes, int batch, int N, float
         a.stats = d_stats;
         a.big_tables = nullptr;
         if (encode_needs_big_tables(g, N))
-            CUDA_TRY(cudaMallocAsync(&a.big_tables, (size_t)nb * 2 * g.cells * sizeof(int), stream));
-        CUDA_TRY(cudaMallocAsync(&a.table, (size_t)nb * g.cells * sizeof(int), stream));
-        CUDA_TRY(cudaMallocAsync(&a.recs, (size_t)nb * (N > 0 ? N : 1) * sizeof(BoxRec), stream));
+            CUDA_TRY(al.get(&a.big_tables, (size_t)nb * 2 * g.cells * sizeof(int)));
+        CUDA_TRY(al.get(&a.table, (size_t)nb * g.cells * sizeof(int)));
+        CUDA_TRY(al.get(&a.recs, (size_t)nb * (N > 0 ? N : 1) * sizeof(BoxRec)));
         CUDA_TRY(launch_encode(a, num_sms, stream));
-        CUDA_TRY(cudaFreeAsync(a.table, stream));
-        CUDA_TRY(cudaFreeAsync(a.recs, stream));
-        if (a.big_tables) CUDA_TRY(cudaFreeAsync(a.big_tables, stream));
+        CUDA_TRY(al.put(a.table));
+        CUDA_TRY(al.put(a.recs));
+        CUDA_TRY(al.put(a.big_tables));
+        al.rewind(mk);
     }
     return MGD_OK;
 }
@@ -282,7 +378,7 @@ float objectness_prefilter(const mgd_post_config& post)
 int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const float* const* preds,
                       int batch, const int* image_hw, double* xywh, int* xyxy, double* scores,
                       int* classes, int* index, int* counts, int num_sms, cudaStream_t stream,
-                      unsigned long long* d_stats)
+                      unsigned long long* d_stats, const Alloc& al)
 {
     const int step = decode_chunk_images(g, batch);
     const int M = post.max_boxes;
@@ -292,6 +388,7 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
     const bool big_keep = nms_kept_bytes(M) > 64 * 1024;
     for (int b0 = 0; b0 < batch; b0 += step) {
         const int nb = batch - b0 < step ? batch - b0 : step;
+        const Arena::Mark mk = al.mark();
         DecodeArgs d;
         memset(&d, 0, sizeof(d));
         d.g = g;
@@ -304,9 +401,9 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         d.confidence = post.confidence;
         d.obj_logit_min = objectness_prefilter(post);
         d.score_lo = post.confidence > 0.0 ? (float)(post.confidence * (1.0 - 1e-3)) : -1.0f;
-        CUDA_TRY(cudaMallocAsync(&d.cand, (size_t)nb * g.cells * sizeof(Cand), stream));
+        CUDA_TRY(al.get(&d.cand, (size_t)nb * g.cells * sizeof(Cand)));
         // counts[nb], counts[nb+1]: the work counters of the two warp-per-image NMS launches
-        CUDA_TRY(cudaMallocAsync(&d.counts, (size_t)(nb + 2) * sizeof(int), stream));
+        CUDA_TRY(al.get(&d.counts, (size_t)(nb + 2) * sizeof(int)));
         CUDA_TRY(cudaMemsetAsync(d.counts, 0, (size_t)(nb + 2) * sizeof(int), stream));
         CUDA_TRY(launch_decode(d, num_sms, stream));
 
@@ -316,7 +413,7 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         n.B = nb;
         n.cap = g.cells;
         n.cand = d.cand;
-        CUDA_TRY(cudaMallocAsync(&n.boxes, (size_t)nb * g.cells * sizeof(BoxD), stream));
+        CUDA_TRY(al.get(&n.boxes, (size_t)nb * g.cells * sizeof(BoxD)));
         n.counts = d.counts;
         n.next_image = d.counts + nb;
         n.image_hw = d.image_hw;
@@ -329,27 +426,27 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
             n.soft = 1;
             n.soft_sigma = post.soft_sigma > 0.0 ? post.soft_sigma : 0.5;
             n.soft_thr = post.soft_score_threshold >= 0.0 ? post.soft_score_threshold : 0.001;
-            CUDA_TRY(cudaMallocAsync(&n.soft_scratch, (size_t)nb * g.cells * sizeof(double), stream));
+            CUDA_TRY(al.get(&n.soft_scratch, (size_t)nb * g.cells * sizeof(double)));
         }
         if (post.nms_method == MGD_NMS_WBF) {
             if (g.C > 65535) return fail(MGD_ERR_UNSUPPORTED, "WBF supports up to 65535 classes");
             n.wbf = 1;
             n.wbf_conf_type = MGD_WBF_CONF_AVG;            // handle_predictions: WeightedBoxesFusion(iou_thr=...)
             n.soft_thr = 0.0;                              // skip_box_thr default
-            CUDA_TRY(cudaMallocAsync(&n.soft_scratch, (size_t)nb * g.cells * 5 * sizeof(double), stream));
-            CUDA_TRY(cudaMallocAsync(&n.wbf_ints, (size_t)nb * g.cells * 4 * sizeof(int), stream));
+            CUDA_TRY(al.get(&n.soft_scratch, (size_t)nb * g.cells * 5 * sizeof(double)));
+            CUDA_TRY(al.get(&n.wbf_ints, (size_t)nb * g.cells * 4 * sizeof(int)));
             if (!n.sort_scratch) {
                 n.sort_scratch_stride = pow2;
-                CUDA_TRY(cudaMallocAsync(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long), stream));
+                CUDA_TRY(al.get(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long)));
             }
         }
         if (big_sort) {
             n.sort_scratch_stride = pow2;
-            CUDA_TRY(cudaMallocAsync(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long), stream));
+            CUDA_TRY(al.get(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long)));
         }
         if (big_keep) {
             n.kept_scratch_stride = (nms_kept_bytes(M) + 15) & ~(size_t)15;
-            CUDA_TRY(cudaMallocAsync(&n.kept_scratch, (size_t)nb * n.kept_scratch_stride, stream));
+            CUDA_TRY(al.get(&n.kept_scratch, (size_t)nb * n.kept_scratch_stride));
         }
         n.out_xywh = xywh ? xywh + (size_t)b0 * M * 4 : nullptr;
         n.out_xyxy = xyxy ? xyxy + (size_t)b0 * M * 4 : nullptr;
@@ -359,13 +456,14 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         n.out_counts = counts + b0;
         n.stats = d_stats;
         CUDA_TRY(launch_nms(n, num_sms, stream));
-        if (n.sort_scratch) CUDA_TRY(cudaFreeAsync(n.sort_scratch, stream));
-        if (n.kept_scratch) CUDA_TRY(cudaFreeAsync(n.kept_scratch, stream));
-        if (n.soft_scratch) CUDA_TRY(cudaFreeAsync(n.soft_scratch, stream));
-        if (n.wbf_ints) CUDA_TRY(cudaFreeAsync(n.wbf_ints, stream));
-        CUDA_TRY(cudaFreeAsync(n.boxes, stream));
-        CUDA_TRY(cudaFreeAsync(d.cand, stream));
-        CUDA_TRY(cudaFreeAsync(d.counts, stream));
+        CUDA_TRY(al.put(n.sort_scratch));
+        CUDA_TRY(al.put(n.kept_scratch));
+        CUDA_TRY(al.put(n.soft_scratch));
+        CUDA_TRY(al.put(n.wbf_ints));
+        CUDA_TRY(al.put(n.boxes));
+        CUDA_TRY(al.put(d.cand));
+        CUDA_TRY(al.put(d.counts));
+        al.rewind(mk);
     }
     return MGD_OK;
 }
@@ -383,25 +481,65 @@ int check_post(const mgd_post_config* post)
 }
 
 // streams used for host-memory calls, one pair per host thread and device
-struct HostStreams { cudaStream_t s[2] = {nullptr, nullptr}; };
+struct HostStreams {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    Arena chunk[2];          // staging + scratch of the chunk in flight on s[i]
+    Arena call;              // per-call tensors (boxes, output slab, status words)
+};
 thread_local HostStreams t_streams[64];
 
-int host_streams(int device, cudaStream_t** out)
+int host_streams(int device, cudaStream_t** out, cudaEvent_t** ev, HostStreams** self = nullptr)
 {
     HostStreams& hs = t_streams[device];
-    for (int i = 0; i < 2; ++i)
+    if (self) *self = &hs;
+    for (int i = 0; i < 2; ++i) {
         if (!hs.s[i]) CUDA_TRY(cudaStreamCreateWithFlags(&hs.s[i], cudaStreamNonBlocking));
+        if (!hs.ev[i]) CUDA_TRY(cudaEventCreateWithFlags(&hs.ev[i], cudaEventDisableTiming));
+    }
     *out = hs.s;
+    if (ev) *ev = hs.ev;
     return MGD_OK;
+}
+
+// A host pointer the GPU can address in place (cudaHostAlloc / cudaHostRegister /
+// torch pin_memory under UVA): returns its device alias, nullptr for pageable memory.
+template <typename T> T* mapped_alias(T* p, size_t bytes)
+{
+    if (!p || bytes == 0) return nullptr;
+    const unsigned char* ends[2] = {reinterpret_cast<const unsigned char*>(p),
+                                    reinterpret_cast<const unsigned char*>(p) + bytes - 1};
+    void* dev = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ends[i]) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+        if (i == 0) dev = at.devicePointer;
+    }
+    return reinterpret_cast<T*>(dev);
+}
+
+// MGD_HOST_ZEROCOPY: bit 0 = decode reads pinned predictions in place over PCIe (only the
+// sectors the three-level filter asks for cross the link), bit 1 = encode writes pinned
+// y_true in place.  Pageable memory always takes the staged path.
+int zerocopy_mode()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MGD_HOST_ZEROCOPY"); v = e ? atoi(e) : 0; }
+    return v;
 }
 
 int host_chunk(const HeadGeom& g, int batch)
 {
-    // ~0.7 GB of y_true / predictions per chunk: long enough copies to run the PCIe
-    // link at speed, short enough for the two streams to overlap H2D, kernels and D2H
+    // ~128 MB of y_true / predictions per chunk (2.3 ms on a Gen5 x16 link): long enough
+    // to run the link at speed, short enough that (a) the two streams overlap H2D, kernels
+    // and D2H within a call and (b) concurrent calls from other host threads interleave on
+    // the copy engines instead of queueing behind a near-gigabyte transfer
+    static long long mb = -1;
+    if (mb < 0) { const char* e = getenv("MGD_HOST_CHUNK_MB"); mb = e && atoll(e) > 0 ? atoll(e) : 128; }
     long long per_image = 0;
     for (int l = 0; l < g.L; ++l) per_image += (long long)g.gh[l] * g.gw[l] * g.D[l] * 4;
-    long long n = (700ll << 20) / (per_image > 0 ? per_image : 1);
+    long long n = (mb << 20) / (per_image > 0 ? per_image : 1);
     if (n < 1) n = 1;
     if (n > batch) n = batch;
     return (int)n;
@@ -487,12 +625,13 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
         cudaStream_t st = (cudaStream_t)stream;
         int* d_status;
         unsigned long long* d_stats = nullptr;
-        CUDA_TRY(cudaMallocAsync(&d_status, sizeof(int) + 4 * sizeof(unsigned long long), st));
+        CUDA_TRY(pool_malloc(&d_status, sizeof(int) + 4 * sizeof(unsigned long long), st));
         CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int) + 4 * sizeof(unsigned long long), st));
         // keep the 8-byte counters aligned: status word sits after them
         d_stats = reinterpret_cast<unsigned long long*>(d_status);
         int* d_flag = reinterpret_cast<int*>(d_stats + 4);
-        rc = encode_device(g, boxes, batch, max_boxes, y_true, num_sms, st, d_flag, d_stats);
+        rc = encode_device(g, boxes, batch, max_boxes, y_true, num_sms, st, d_flag, d_stats,
+                           Alloc{nullptr, st});
         if (rc) return rc;
         if (flags & MGD_FLAG_SYNC) {
             unsigned long long h[5] = {0, 0, 0, 0, 0};
@@ -514,46 +653,62 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
     }
 
     // host memory: stage through the GPU in chunks, two streams so that the D2H of one
-    // chunk overlaps the H2D + kernels of the next
+    // chunk overlaps the kernels of the next.  The (small) box tensor goes up once, ahead
+    // of the chunks, so no chunk waits on the H2D engine behind another call's bulk copy.
+    Tracer tr("encode/host");
     cudaStream_t* ss;
-    if ((rc = host_streams(device, &ss))) return rc;
+    cudaEvent_t* ev;
+    HostStreams* hs;
+    if ((rc = host_streams(device, &ss, &ev, &hs))) return rc;
+    hs->call.reset();
     unsigned long long* d_meta;      // [4 stats][status]
-    // (stream-ordered allocation: a legacy cudaMalloc / cudaFree pair costs milliseconds
-    //  here because cudaFree synchronises the device and walks the memory pool)
-    CUDA_TRY(cudaMallocAsync(&d_meta, 5 * sizeof(unsigned long long), ss[0]));
+    CUDA_TRY(hs->call.take(reinterpret_cast<void**>(&d_meta), 5 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemsetAsync(d_meta, 0, 5 * sizeof(unsigned long long), ss[0]));
-    CUDA_TRY(cudaStreamSynchronize(ss[0]));
-    const int step = host_chunk(g, batch);
+    float* d_boxes;
+    const size_t box_bytes = (size_t)batch * max_boxes * 5 * sizeof(float);
+    CUDA_TRY(hs->call.take(reinterpret_cast<void**>(&d_boxes), box_bytes));
+    if (box_bytes) CUDA_TRY(cudaMemcpyAsync(d_boxes, boxes, box_bytes, cudaMemcpyHostToDevice, ss[0]));
+    CUDA_TRY(cudaEventRecord(ev[0], ss[0]));
+    CUDA_TRY(cudaStreamWaitEvent(ss[1], ev[0], 0));
+    int step = host_chunk(g, batch);
+    float* z_y[MGD_MAX_LAYERS];
+    bool zero_copy = (zerocopy_mode() & 2) != 0;
+    for (int l = 0; l < g.L && zero_copy; ++l) {
+        z_y[l] = mapped_alias(y_true[l], (size_t)batch * g.gh[l] * g.gw[l] * g.D[l] * 4);
+        zero_copy = z_y[l] != nullptr;
+    }
+    if (zero_copy) step = batch;
     int k = 0;
     for (int b0 = 0; b0 < batch; b0 += step, ++k) {
         const int nb = batch - b0 < step ? batch - b0 : step;
         cudaStream_t st = ss[k & 1];
-        float* d_boxes;
+        Arena& ar = hs->chunk[k & 1];
+        ar.reset();
         float* d_y[MGD_MAX_LAYERS];
-        const size_t box_bytes = (size_t)nb * max_boxes * 5 * sizeof(float);
-        CUDA_TRY(cudaMallocAsync(&d_boxes, box_bytes ? box_bytes : 4, st));
-        if (box_bytes)
-            CUDA_TRY(cudaMemcpyAsync(d_boxes, boxes + (size_t)b0 * max_boxes * 5, box_bytes,
-                                     cudaMemcpyHostToDevice, st));
-        for (int l = 0; l < g.L; ++l)
-            CUDA_TRY(cudaMallocAsync(&d_y[l], (size_t)nb * g.gh[l] * g.gw[l] * g.D[l] * 4, st));
-        rc = encode_device(g, d_boxes, nb, max_boxes, d_y, num_sms, st,
-                           reinterpret_cast<int*>(d_meta + 4), d_meta);
-        if (rc) { cudaFreeAsync(d_meta, ss[0]); return rc; }
         for (int l = 0; l < g.L; ++l) {
+            if (zero_copy) d_y[l] = z_y[l];
+            else CUDA_TRY(ar.take(reinterpret_cast<void**>(&d_y[l]), (size_t)nb * g.gh[l] * g.gw[l] * g.D[l] * 4));
+        }
+        rc = encode_device(g, d_boxes + (size_t)b0 * max_boxes * 5, nb, max_boxes, d_y, num_sms, st,
+                           reinterpret_cast<int*>(d_meta + 4), d_meta, Alloc{&ar, st});
+        if (rc) return rc;
+        for (int l = 0; l < g.L && !zero_copy; ++l) {
             const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
             CUDA_TRY(cudaMemcpyAsync(y_true[l] + (size_t)b0 * per, d_y[l], (size_t)nb * per * 4,
                                      cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaFreeAsync(d_y[l], st));
         }
-        CUDA_TRY(cudaFreeAsync(d_boxes, st));
     }
+    tr.mark("chunks enqueued");
+    CUDA_TRY(cudaEventRecord(ev[1], ss[1]));
+    CUDA_TRY(cudaStreamWaitEvent(ss[0], ev[1], 0));
+    // drain first, read back after: a copy into pageable memory (this stack word, or the
+    // caller's unpinned arrays) waits for the stream INSIDE the driver, and other host
+    // threads' launches stall behind it for the whole transfer
     CUDA_TRY(cudaStreamSynchronize(ss[0]));
-    CUDA_TRY(cudaStreamSynchronize(ss[1]));
     unsigned long long h[5];
-    CUDA_TRY(cudaMemcpyAsync(h, d_meta, sizeof(h), cudaMemcpyDeviceToHost, ss[0]));
-    CUDA_TRY(cudaFreeAsync(d_meta, ss[0]));
-    CUDA_TRY(cudaStreamSynchronize(ss[0]));
+    CUDA_TRY(cudaMemcpy(h, d_meta, sizeof(h), cudaMemcpyDeviceToHost));
+    tr.mark("synchronised");
+    hs->chunk[0].consolidate(); hs->chunk[1].consolidate(); hs->call.consolidate();
     if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
     return status_to_error((int)(h[4] & 0xffffffffu));
 }
@@ -584,11 +739,11 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
         unsigned long long* d_stats = nullptr;
         const bool want_stats = stats && (flags & MGD_FLAG_SYNC);
         if (want_stats) {
-            CUDA_TRY(cudaMallocAsync(&d_stats, 4 * sizeof(unsigned long long), st));
+            CUDA_TRY(pool_malloc(&d_stats, 4 * sizeof(unsigned long long), st));
             CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), st));
         }
         rc = decode_nms_device(g, *post, preds, batch, image_hw, boxes_xywh, boxes_xyxy, scores,
-                               classes, index, counts, num_sms, st, d_stats);
+                               classes, index, counts, num_sms, st, d_stats, Alloc{nullptr, st});
         if (rc) return rc;
         if (flags & MGD_FLAG_SYNC) {
             unsigned long long h[4] = {0, 0, 0, 0};
@@ -602,75 +757,96 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
         return MGD_OK;
     }
 
+    // host memory: predictions go up in chunks on two streams (H2D of one chunk overlaps the
+    // kernels of the previous one); image shapes go up once ahead of the chunks and all
+    // detections come back in one slab at the end, so the small copies never queue behind
+    // another call's bulk transfer more than once.
     Tracer tr("decode_nms/host");
     cudaStream_t* ss;
-    if ((rc = host_streams(device, &ss))) return rc;
+    cudaEvent_t* ev;
+    HostStreams* hs;
+    if ((rc = host_streams(device, &ss, &ev, &hs))) return rc;
     tr.mark("streams");
-    unsigned long long* d_stats;
-    CUDA_TRY(cudaMallocAsync(&d_stats, 4 * sizeof(unsigned long long), ss[0]));
+    // one output slab: stats u64[4] | xywh f64 | scores f64 | xyxy i32 | classes i32 | index i32 | counts i32 | hw i32
+    const size_t n_det = (size_t)batch * M;
+    const size_t off_xywh = 4 * sizeof(unsigned long long);
+    const size_t off_scores = off_xywh + n_det * 4 * sizeof(double);
+    const size_t off_xyxy = off_scores + n_det * sizeof(double);
+    const size_t off_cls = off_xyxy + n_det * 4 * sizeof(int);
+    const size_t off_idx = off_cls + n_det * sizeof(int);
+    const size_t off_cnt = off_idx + n_det * sizeof(int);
+    const size_t off_hw = off_cnt + (size_t)batch * sizeof(int);
+    const size_t slab = off_hw + (size_t)batch * 2 * sizeof(int);
+    unsigned char* d_out;
+    hs->call.reset();
+    CUDA_TRY(hs->call.take(reinterpret_cast<void**>(&d_out), slab));
+    unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(d_out);
     CUDA_TRY(cudaMemsetAsync(d_stats, 0, 4 * sizeof(unsigned long long), ss[0]));
-    CUDA_TRY(cudaStreamSynchronize(ss[0]));
-    tr.mark("stats alloc");
-    const int step = host_chunk(g, batch);
+    int* d_hw = nullptr;
+    if (image_hw) {
+        d_hw = reinterpret_cast<int*>(d_out + off_hw);
+        CUDA_TRY(cudaMemcpyAsync(d_hw, image_hw, (size_t)batch * 2 * sizeof(int), cudaMemcpyHostToDevice, ss[0]));
+    }
+    CUDA_TRY(cudaEventRecord(ev[0], ss[0]));
+    CUDA_TRY(cudaStreamWaitEvent(ss[1], ev[0], 0));
+    tr.mark("slab");
+    int step = host_chunk(g, batch);
+    // pinned predictions: the decode kernel can read them in place
+    const float* z_pred[MGD_MAX_LAYERS];
+    bool zero_copy = (zerocopy_mode() & 1) != 0;
+    for (int l = 0; l < g.L && zero_copy; ++l) {
+        z_pred[l] = mapped_alias(preds[l], (size_t)batch * g.gh[l] * g.gw[l] * g.D[l] * 4);
+        zero_copy = z_pred[l] != nullptr;
+    }
+    // (still chunked: kernels of other calls get onto the SMs between the chunks)
     int k = 0;
     for (int b0 = 0; b0 < batch; b0 += step, ++k) {
         const int nb = batch - b0 < step ? batch - b0 : step;
         cudaStream_t st = ss[k & 1];
+        Arena& ar = hs->chunk[k & 1];
+        ar.reset();
         float* d_pred[MGD_MAX_LAYERS];
         for (int l = 0; l < g.L; ++l) {
             const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
-            CUDA_TRY(cudaMallocAsync(&d_pred[l], (size_t)nb * per * 4, st));
+            if (zero_copy) { d_pred[l] = const_cast<float*>(z_pred[l]) + (size_t)b0 * per; continue; }
+            CUDA_TRY(ar.take(reinterpret_cast<void**>(&d_pred[l]), (size_t)nb * per * 4));
             CUDA_TRY(cudaMemcpyAsync(d_pred[l], preds[l] + (size_t)b0 * per, (size_t)nb * per * 4,
                                      cudaMemcpyHostToDevice, st));
         }
-        int* d_hw = nullptr;
-        if (image_hw) {
-            CUDA_TRY(cudaMallocAsync(&d_hw, (size_t)nb * 2 * sizeof(int), st));
-            CUDA_TRY(cudaMemcpyAsync(d_hw, image_hw + 2 * (size_t)b0, (size_t)nb * 2 * sizeof(int),
-                                     cudaMemcpyHostToDevice, st));
-        }
-        tr.mark("h2d enqueued");
-        // one output slab: xywh f64 | scores f64 | xyxy i32 | classes i32 | index i32 | counts i32
-        const size_t n_det = (size_t)nb * M;
-        const size_t off_scores = n_det * 4 * sizeof(double);
-        const size_t off_xyxy = off_scores + n_det * sizeof(double);
-        const size_t off_cls = off_xyxy + n_det * 4 * sizeof(int);
-        const size_t off_idx = off_cls + n_det * sizeof(int);
-        const size_t off_cnt = off_idx + n_det * sizeof(int);
-        const size_t slab = off_cnt + (size_t)nb * sizeof(int);
-        unsigned char* d_out;
-        CUDA_TRY(cudaMallocAsync(&d_out, slab, st));
-        rc = decode_nms_device(g, *post, d_pred, nb, d_hw,
-                               reinterpret_cast<double*>(d_out),
-                               reinterpret_cast<int*>(d_out + off_xyxy),
-                               reinterpret_cast<double*>(d_out + off_scores),
-                               reinterpret_cast<int*>(d_out + off_cls),
-                               reinterpret_cast<int*>(d_out + off_idx),
-                               reinterpret_cast<int*>(d_out + off_cnt), num_sms, st, d_stats);
-        if (rc) { cudaFreeAsync(d_stats, ss[0]); return rc; }
-        tr.mark("kernels enqueued");
-        if (boxes_xywh)
-            CUDA_TRY(cudaMemcpyAsync(boxes_xywh + (size_t)b0 * M * 4, d_out, n_det * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (scores)
-            CUDA_TRY(cudaMemcpyAsync(scores + (size_t)b0 * M, d_out + off_scores, n_det * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (boxes_xyxy)
-            CUDA_TRY(cudaMemcpyAsync(boxes_xyxy + (size_t)b0 * M * 4, d_out + off_xyxy, n_det * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (classes)
-            CUDA_TRY(cudaMemcpyAsync(classes + (size_t)b0 * M, d_out + off_cls, n_det * sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (index)
-            CUDA_TRY(cudaMemcpyAsync(index + (size_t)b0 * M, d_out + off_idx, n_det * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(counts + b0, d_out + off_cnt, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaFreeAsync(d_out, st));
-        if (d_hw) CUDA_TRY(cudaFreeAsync(d_hw, st));
-        for (int l = 0; l < g.L; ++l) CUDA_TRY(cudaFreeAsync(d_pred[l], st));
+        rc = decode_nms_device(g, *post, d_pred, nb, d_hw ? d_hw + 2 * (size_t)b0 : nullptr,
+                               reinterpret_cast<double*>(d_out + off_xywh) + (size_t)b0 * M * 4,
+                               reinterpret_cast<int*>(d_out + off_xyxy) + (size_t)b0 * M * 4,
+                               reinterpret_cast<double*>(d_out + off_scores) + (size_t)b0 * M,
+                               reinterpret_cast<int*>(d_out + off_cls) + (size_t)b0 * M,
+                               reinterpret_cast<int*>(d_out + off_idx) + (size_t)b0 * M,
+                               reinterpret_cast<int*>(d_out + off_cnt) + b0, num_sms, st, d_stats,
+                               Alloc{&ar, st});
+        if (rc) return rc;
     }
-    tr.mark("d2h enqueued");
-    CUDA_TRY(cudaStreamSynchronize(ss[1]));
+    tr.mark("chunks enqueued");
+    CUDA_TRY(cudaEventRecord(ev[1], ss[1]));
+    CUDA_TRY(cudaStreamWaitEvent(ss[0], ev[1], 0));
+    cudaStream_t st = ss[0];
+    // drain first, read back after (see mgd_encode_targets): the detection arrays are
+    // usually pageable, and a pageable copy that has to wait for the stream blocks the
+    // launches of every other host thread meanwhile
+    CUDA_TRY(cudaStreamSynchronize(st));
     unsigned long long h[4];
-    CUDA_TRY(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, ss[0]));
-    CUDA_TRY(cudaFreeAsync(d_stats, ss[0]));
-    CUDA_TRY(cudaStreamSynchronize(ss[0]));
+    CUDA_TRY(cudaMemcpyAsync(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    if (boxes_xywh)
+        CUDA_TRY(cudaMemcpyAsync(boxes_xywh, d_out + off_xywh, n_det * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (scores)
+        CUDA_TRY(cudaMemcpyAsync(scores, d_out + off_scores, n_det * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (boxes_xyxy)
+        CUDA_TRY(cudaMemcpyAsync(boxes_xyxy, d_out + off_xyxy, n_det * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (classes)
+        CUDA_TRY(cudaMemcpyAsync(classes, d_out + off_cls, n_det * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (index)
+        CUDA_TRY(cudaMemcpyAsync(index, d_out + off_idx, n_det * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(counts, d_out + off_cnt, (size_t)batch * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     tr.mark("synchronised");
+    hs->chunk[0].consolidate(); hs->chunk[1].consolidate(); hs->call.consolidate();
     if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
     return MGD_OK;
 }
@@ -704,7 +880,7 @@ int mgd_decode_dense(const mgd_head_config* cfg, const mgd_post_config* post,
         return MGD_OK;
     }
     cudaStream_t* ss;
-    if ((rc = host_streams(device, &ss))) return rc;
+    if ((rc = host_streams(device, &ss, nullptr))) return rc;
     cudaStream_t st = ss[0];
     long long per_image = (long long)out_per * 8;
     int step = (int)((512ll << 20) / per_image);
@@ -715,19 +891,19 @@ int mgd_decode_dense(const mgd_head_config* cfg, const mgd_post_config* post,
         d.B = nb;
         for (int l = 0; l < g.L; ++l) {
             const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
-            CUDA_TRY(cudaMallocAsync(&d_pred[l], (size_t)nb * per * 4, st));
+            CUDA_TRY(pool_malloc(&d_pred[l], (size_t)nb * per * 4, st));
             CUDA_TRY(cudaMemcpyAsync(d_pred[l], preds[l] + (size_t)b0 * per, (size_t)nb * per * 4,
                                      cudaMemcpyHostToDevice, st));
             d.pred[l] = d_pred[l];
         }
         int* d_hw = nullptr;
         if (image_hw) {
-            CUDA_TRY(cudaMallocAsync(&d_hw, (size_t)nb * 2 * sizeof(int), st));
+            CUDA_TRY(pool_malloc(&d_hw, (size_t)nb * 2 * sizeof(int), st));
             CUDA_TRY(cudaMemcpyAsync(d_hw, image_hw + 2 * (size_t)b0, (size_t)nb * 2 * sizeof(int),
                                      cudaMemcpyHostToDevice, st));
         }
         double* d_out;
-        CUDA_TRY(cudaMallocAsync(&d_out, (size_t)nb * out_per * 8, st));
+        CUDA_TRY(pool_malloc(&d_out, (size_t)nb * out_per * 8, st));
         CUDA_TRY(launch_decode_dense(d, d_hw, d_out, st));
         CUDA_TRY(cudaMemcpyAsync(out + (size_t)b0 * out_per, d_out, (size_t)nb * out_per * 8,
                                  cudaMemcpyDeviceToHost, st));
@@ -757,7 +933,7 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
     cudaStream_t st = (cudaStream_t)stream;
     if (host) {
         cudaStream_t* ss;
-        if ((rc = host_streams(device, &ss))) return rc;
+        if ((rc = host_streams(device, &ss, nullptr))) return rc;
         st = ss[0];
     }
     if (n == 0) {
@@ -771,7 +947,7 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
     void* staged = nullptr;
     if (host) {
         const size_t bytes = (size_t)n * (4 * 8 + 8 + 4 + 4) + 16;
-        CUDA_TRY(cudaMallocAsync(&staged, bytes, st));
+        CUDA_TRY(pool_malloc(&staged, bytes, st));
         double* p = reinterpret_cast<double*>(staged);
         CUDA_TRY(cudaMemcpyAsync(p, boxes, (size_t)n * 32, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(p + 4 * (size_t)n, scores, (size_t)n * 8, cudaMemcpyHostToDevice, st));
@@ -781,7 +957,7 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
         d_keep = q + n; d_nkeep = q + 2 * (size_t)n;
     }
     int* count; int* d_index; int* d_counts;
-    CUDA_TRY(cudaMallocAsync(&count, 2 * sizeof(int) + (size_t)max_keep * sizeof(int), st));
+    CUDA_TRY(pool_malloc(&count, 2 * sizeof(int) + (size_t)max_keep * sizeof(int), st));
     d_counts = count + 1;
     d_index = count + 2;
     CUDA_TRY(cudaMemcpyAsync(count, &n, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -795,11 +971,11 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
     while (pow2 < n) pow2 <<= 1;
     if (n > nms_smem_capacity()) {
         a.sort_scratch_stride = pow2;
-        CUDA_TRY(cudaMallocAsync(&a.sort_scratch, (size_t)2 * pow2 * sizeof(unsigned long long), st));
+        CUDA_TRY(pool_malloc(&a.sort_scratch, (size_t)2 * pow2 * sizeof(unsigned long long), st));
     }
     if (nms_kept_bytes(max_keep) > 64 * 1024) {
         a.kept_scratch_stride = (nms_kept_bytes(max_keep) + 15) & ~(size_t)15;
-        CUDA_TRY(cudaMallocAsync(&a.kept_scratch, a.kept_scratch_stride, st));
+        CUDA_TRY(pool_malloc(&a.kept_scratch, a.kept_scratch_stride, st));
     }
     a.out_index = d_index;
     a.out_counts = d_counts;
@@ -835,7 +1011,7 @@ int mgd_wbf(const double* boxes, const double* scores, const int* classes,
     cudaStream_t st = (cudaStream_t)stream;
     if (host) {
         cudaStream_t* ss;
-        if ((rc = host_streams(device, &ss))) return rc;
+        if ((rc = host_streams(device, &ss, nullptr))) return rc;
         st = ss[0];
     }
     if (n == 0) {
@@ -851,7 +1027,7 @@ int mgd_wbf(const double* boxes, const double* scores, const int* classes,
     //          sort 2*pow2 (u64) | classes n | out_classes n | ints 4n | counts 2        (i32)
     unsigned char* buf;
     const size_t f64s = nn * (4 + 1 + 1 + 5 + 4 + 1);
-    CUDA_TRY(cudaMallocAsync(&buf, f64s * 8 + (size_t)2 * pow2 * 8 + nn * 6 * 4 + 64, st));
+    CUDA_TRY(pool_malloc(&buf, f64s * 8 + (size_t)2 * pow2 * 8 + nn * 6 * 4 + 64, st));
     double* d_boxes = reinterpret_cast<double*>(buf);
     double* d_scores = d_boxes + 4 * nn;
     double* d_w = d_scores + nn;
@@ -907,7 +1083,7 @@ int mgd_soft_nms(const double* boxes, const double* scores, int n, double sigma,
     cudaStream_t st = (cudaStream_t)stream;
     if (host) {
         cudaStream_t* ss;
-        if ((rc = host_streams(device, &ss))) return rc;
+        if ((rc = host_streams(device, &ss, nullptr))) return rc;
         st = ss[0];
     }
     if (n == 0) {
@@ -919,7 +1095,7 @@ int mgd_soft_nms(const double* boxes, const double* scores, int n, double sigma,
     // device staging: boxes (4n f64) | scores (n f64) | soft out (n f64) | keep (n i32) | counts (2 i32)
     const size_t nn = (size_t)n;
     unsigned char* buf;
-    CUDA_TRY(cudaMallocAsync(&buf, nn * (32 + 8 + 8 + 8 + 4) + 64, st));
+    CUDA_TRY(pool_malloc(&buf, nn * (32 + 8 + 8 + 8 + 4) + 64, st));
     double* d_boxes = reinterpret_cast<double*>(buf);
     double* d_scores = d_boxes + 4 * nn;
     double* d_soft_out = d_scores + nn;
@@ -940,7 +1116,7 @@ int mgd_soft_nms(const double* boxes, const double* scores, int n, double sigma,
     while (pow2 < n) pow2 <<= 1;
     if (n > nms_smem_capacity()) {
         a.sort_scratch_stride = pow2;
-        CUDA_TRY(cudaMallocAsync(&a.sort_scratch, (size_t)2 * pow2 * sizeof(unsigned long long), st));
+        CUDA_TRY(pool_malloc(&a.sort_scratch, (size_t)2 * pow2 * sizeof(unsigned long long), st));
     }
     a.out_index = d_keep; a.out_scores = d_soft_out; a.out_counts = d_cnt + 1;
     CUDA_TRY(launch_nms(a, num_sms, st));
