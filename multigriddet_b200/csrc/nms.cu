@@ -296,25 +296,79 @@ nms_kernel(const __grid_constant__ NmsArgs a)
 // chunks of 32, but everything is warp-synchronous: no CTA barrier, the intra-chunk
 // mask is built with ballots and lives in registers, and several images share a CTA.
 // Images it does not take (too many candidates) are left to nms_kernel.
+//
+// The kernel is bound by fixed-latency dependency stalls, so what matters is how many
+// warps (= images) an SM holds and how few instructions a pair test costs:
+//   * 8.2 KB of shared memory per warp (32-bit score keys, 16-bit positions, float32
+//     outer boxes of the kept list; the float64 kept boxes stay in global memory / L1)
+//     -> 6 CTAs x 4 warps per SM;
+//   * a pair is tested in three levels: outer-box overlap in float32 (32 kept boxes per
+//     unrolled sweep, bit positions are compile-time constants); an approximate float32
+//     metric that decides whenever it is further than 1e-2 from the threshold (its error
+//     is < 3e-3 once both intersection sides exceed 1e-3 of the coordinate scale, see
+//     approx_verdict); and the exact float64 formula only for the few undecided pairs.
 // ---------------------------------------------------------------------------------
-constexpr int kWarpCapSmall = 512;     // candidates per image handled by one warp (first launch)
-constexpr int kWarpCapLarge = 1024;    // ... and by the second launch
+constexpr int kWarpCapLarge = 1024;    // candidates per image handled by one warp
 constexpr int kWarpsPerCtaW = 4;
+
+__host__ __device__ inline int nms_kept_pad(int kept_cap) { return (kept_cap + 31) & ~31; }
 
 __host__ __device__ inline size_t nms_warp_bytes(int cap, int kept_cap)
 {
-    // kept boxes BoxD[kept_cap] | keys u64[cap] | kept outer boxes float4[kept_cap]
-    // | kept class int[kept_cap] | sorted position u16[cap]
-    const size_t b = (size_t)kept_cap * 32 + (size_t)cap * 8 + (size_t)kept_cap * (16 + 4) + (size_t)cap * 2;
+    // kept outer boxes float4[kpad] | keys u32[cap] | kept class int[kpad]
+    // | sorted position u16[cap] | kept position u16[kpad]
+    const size_t kpad = (size_t)nms_kept_pad(kept_cap);
+    const size_t b = kpad * 16 + (size_t)cap * 4 + kpad * 4 + (size_t)cap * 2 + kpad * 2;
     return (b + 15) & ~(size_t)15;
 }
 
-struct WarpEmit {
-    const NmsArgs* a; int b; const Cand* cand; const BoxD* boxes; double W, H;
-};
+// Approximate pair metric on float32 outer boxes [x1, y1, x2, y2].
+// Returns 1 (suppress), 0 (keep) or -1 (undecided: evaluate the exact formula).
+// Error bound: every coordinate is within eps = 1.2e-7 * L of the float64 one (L = largest
+// coordinate magnitude of the image's boxes).  With iw, ih >= tmin = 1e-3 * L:
+//   |dIoU|        <= 6 eps (1/iw + 1/ih)              <= 1.5e-3
+//   |d dist/diag| <= 8 eps / sqrt(diag), sqrt(diag) >= tmin  =>  <= 1e-3
+// plus a few float32 roundings (1e-6): total < 3e-3, decided only beyond 1e-2.
+__device__ __forceinline__ int approx_verdict(const float4& a, const float4& b, float thr, bool diou,
+                                              float tmin)
+{
+    const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    const float ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    if (!(iw >= tmin && ih >= tmin)) return -1;
+    const float inter = iw * ih;
+    const float uni = ((a.z - a.x) * (a.w - a.y) + (b.z - b.x) * (b.w - b.y)) - inter;
+    float m = __fdividef(inter, uni + 1e-8f);
+    if (diou) {
+        const float dxc = 0.5f * ((a.x + a.z) - (b.x + b.z));
+        const float dyc = 0.5f * ((a.y + a.w) - (b.y + b.w));
+        const float ex = fmaxf(a.z, b.z) - fminf(a.x, b.x);
+        const float ey = fmaxf(a.w, b.w) - fminf(a.y, b.y);
+        m -= __fdividef(dxc * dxc + dyc * dyc, (ex * ex + ey * ey) + 1e-8f);
+    }
+    if (m > thr + 1e-2f) return 1;
+    if (m < thr - 1e-2f) return 0;
+    return -1;                                   // also every NaN
+}
+
+// bit k set <=> kept box k0 + k may overlap the lane's box (and shares its class in
+// per-class mode).  Slots beyond the kept count hold an empty box that never overlaps.
+template <bool kPerClass>
+__device__ __forceinline__ unsigned overlap_sweep(const float4* k_out, const int* k_cls,
+                                                  const float4& co, int ccls, bool pretest)
+{
+    unsigned m = 0;
+    #pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const float4 ko = k_out[k];
+        bool hit = !(pretest && (ko.z <= co.x || co.z <= ko.x || ko.w <= co.y || co.w <= ko.y));
+        if (kPerClass) hit = hit && k_cls[k] == ccls;
+        m |= hit ? (1u << k) : 0u;
+    }
+    return m;
+}
 
 template <int kWarpCap>
-__global__ void __launch_bounds__(kWarpsPerCtaW * 32)
+__global__ void __launch_bounds__(kWarpsPerCtaW * 32, 6)
 nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -324,21 +378,20 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
     if (threadIdx.x < MGD_EXP2F_N) s_tab[threadIdx.x] = mgd_exp2f_tab[threadIdx.x];
     __syncthreads();
 
-    // per-warp shared memory: kept list (float64 + outer float32 boxes, class), sort
-    // keys and payload
+    const int kpad = nms_kept_pad(kept_cap);
     unsigned char* mine = dyn + (size_t)warp * nms_warp_bytes(kWarpCap, kept_cap);
-    BoxD* k_box = reinterpret_cast<BoxD*>(mine);
-    unsigned long long* key = reinterpret_cast<unsigned long long*>(k_box + kept_cap);
-    float4* k_out = reinterpret_cast<float4*>(key + kWarpCap);
-    int* k_cls = reinterpret_cast<int*>(k_out + kept_cap);
-    unsigned short* pos_of = reinterpret_cast<unsigned short*>(k_cls + kept_cap);
+    float4* k_out = reinterpret_cast<float4*>(mine);
+    unsigned* key = reinterpret_cast<unsigned*>(k_out + kpad);
+    int* k_cls = reinterpret_cast<int*>(key + kWarpCap);
+    unsigned short* pos_of = reinterpret_cast<unsigned short*>(k_cls + kpad);
+    unsigned short* k_pos = pos_of + kWarpCap;
 
     const HeadGeom& g = a.g;
     const bool diou = a.use_diou != 0;
     const bool pretest = a.thr > 0.0;
-    const int n_warps = gridDim.x * kWarpsPerCtaW;
+    const float thr_f = (float)a.thr;
+    const float inf = __int_as_float(0x7f800000);
 
-    (void)n_warps;
     // Images are handed out dynamically (per-image cost varies by more than 10x), the
     // expensive ones first: phase 0 takes the images with more than `min_count`
     // candidates, phase 1 the rest, so light images fill the tail of the heavy ones.
@@ -363,6 +416,7 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
         // ---- 0. boxes + keys, lane-strided ------------------------------------------
         int mpad = 32;
         while (mpad < M) mpad <<= 1;
+        float scale = 0.f;                               // largest coordinate magnitude
         {
             const Letterbox lb = letterbox_consts(g.in_h, g.in_w, ih, iw);
             for (int i = lane; i < mpad; i += 32) {
@@ -376,26 +430,42 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
                     decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 0, s_tab, bx.x, bx.w);
                     decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 1, s_tab, bx.y, bx.h);
                     boxes[i] = bx;
+                    const float4 o = outer_box(bx);
+                    scale = fmaxf(scale, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
                     // scores are non-negative floats: their bit patterns order like the values
-                    key[i] = ((unsigned long long)(~__float_as_uint(cd.score)) << 32) | (unsigned)cd.index;
+                    key[i] = ~__float_as_uint(cd.score);
                     pos_of[i] = (unsigned short)i;
                 } else {
-                    key[i] = ~0ull;
+                    key[i] = 0xffffffffu;
                     pos_of[i] = 0xffff;
                 }
             }
+            for (int k = lane; k < kpad; k += 32) k_out[k] = make_float4(inf, inf, -inf, -inf);
         }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) scale = fmaxf(scale, __shfl_xor_sync(0xffffffffu, scale, o));
+        // NaN / infinite coordinates: no pair may be decided approximately
+        const float tmin = scale < 3.0e38f ? 1e-3f * scale : inf;
         __syncwarp();
         // ---- 1. bitonic sort (score desc, cell index asc) ----------------------------
+        // 32-bit score keys; the cell index (the deterministic tie rule) is only looked up
+        // when two keys are equal.  Padding sorts last: index +inf.
         for (int k = 2; k <= mpad; k <<= 1) {
             for (int jj = k >> 1; jj > 0; jj >>= 1) {
                 for (int t = lane; t < (mpad >> 1); t += 32) {
                     // t-th compare-exchange of this stage: i has bit jj clear
                     const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
                     const int p = i | jj;
-                    const unsigned long long ka = key[i], kb = key[p];
+                    const unsigned ka = key[i], kb = key[p];
                     const bool up = (i & k) == 0;
-                    if ((kb < ka) == up) {
+                    bool b_lt_a = kb < ka;
+                    if (kb == ka) {
+                        const unsigned short pa = pos_of[i], pb = pos_of[p];
+                        const int ia = pa == 0xffff ? 0x7fffffff : cand[pa].index;
+                        const int ib = pb == 0xffff ? 0x7fffffff : cand[pb].index;
+                        b_lt_a = ib < ia;
+                    }
+                    if (b_lt_a == up) {
                         key[i] = kb; key[p] = ka;
                         const unsigned short pa = pos_of[i]; pos_of[i] = pos_of[p]; pos_of[p] = pa;
                     }
@@ -419,34 +489,30 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
                 co = outer_box(cb);
                 ccls = cand[pos].cls;
             }
-            // a. suppression by boxes kept in earlier chunks.  Two passes so the lanes never
-            //    diverge into the float64 metric one at a time: (1) a uniform sweep with the
-            //    float32 outer-box test records, per lane, which kept boxes might overlap
-            //    (128 kept boxes per sweep); (2) all lanes evaluate their next pending kept
-            //    box together, in kept order, until a lane is suppressed or runs out.
+            // a. suppression by boxes kept in earlier chunks, 32 kept boxes per sweep: a
+            //    uniform float32 sweep records which kept boxes might overlap, then all lanes
+            //    evaluate their next pending kept box together until suppressed or done.
             bool alive = have;
-            for (int k0 = 0; k0 < kept; k0 += 128) {
-                const int kn = min(128, kept - k0);
-                unsigned long long pend_lo = 0, pend_hi = 0;
-                #pragma unroll 4
-                for (int k = 0; k < kn; ++k) {
-                    const float4 ko = k_out[k0 + k];
-                    bool cand_pair = alive && !(a.per_class && k_cls[k0 + k] != ccls);
-                    if (pretest && (ko.z <= co.x || co.z <= ko.x || ko.w <= co.y || co.w <= ko.y))
-                        cand_pair = false;
-                    if (cand_pair) { if (k < 64) pend_lo |= 1ull << k; else pend_hi |= 1ull << (k - 64); }
-                }
-                while (__any_sync(0xffffffffu, alive && (pend_lo | pend_hi))) {
-                    if (alive && (pend_lo | pend_hi)) {
-                        int k;
-                        if (pend_lo) { k = __ffsll((long long)pend_lo) - 1; pend_lo &= pend_lo - 1; }
-                        else { k = 64 + __ffsll((long long)pend_hi) - 1; pend_hi &= pend_hi - 1; }
-                        if (suppresses(k_box[k0 + k], cb, a.thr, diou)) alive = false;
+            for (int k0 = 0; k0 < kept; k0 += 32) {
+                if (!__any_sync(0xffffffffu, alive)) break;
+                unsigned pend = a.per_class ? overlap_sweep<true>(k_out + k0, k_cls + k0, co, ccls, pretest)
+                                            : overlap_sweep<false>(k_out + k0, k_cls + k0, co, ccls, pretest);
+                const int kn = kept - k0;
+                if (kn < 32) pend &= (1u << kn) - 1u;
+                if (!alive) pend = 0;
+                while (__any_sync(0xffffffffu, pend != 0)) {
+                    if (pend) {
+                        const int k = k0 + __ffs((int)pend) - 1;
+                        pend &= pend - 1;
+                        int v = approx_verdict(k_out[k], co, thr_f, diou, tmin);
+                        if (v < 0) v = suppresses(boxes[k_pos[k]], cb, a.thr, diou) ? 1 : 0;
+                        if (v) pend = 0;
+                        alive = alive && !v;
                     }
                 }
             }
             // b. intra-chunk: lane j collects the set of EARLIER alive members that suppress
-            //    it (same two passes; the outer boxes travel by shuffle)
+            //    it (same levels; the outer boxes travel by shuffle)
             const unsigned live0 = __ballot_sync(0xffffffffu, alive);
             unsigned pend = 0;
             for (int i = 0; i < n - 1; ++i) {
@@ -460,11 +526,15 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
             }
             unsigned sup_by = 0;                                  // earlier members suppressing me
             while (__any_sync(0xffffffffu, pend != 0)) {
+                // the partner's outer box comes by shuffle from the lane that holds it
+                const int i = pend ? __ffs((int)pend) - 1 : 0;
+                const float ox = __shfl_sync(0xffffffffu, co.x, i), oy = __shfl_sync(0xffffffffu, co.y, i);
+                const float oz = __shfl_sync(0xffffffffu, co.z, i), ow = __shfl_sync(0xffffffffu, co.w, i);
                 if (pend) {
-                    const int i = __ffs((int)pend) - 1;
                     pend &= pend - 1;
-                    const BoxD ib = boxes[pos_of[c0 + i]];
-                    if (suppresses(ib, cb, a.thr, diou)) sup_by |= 1u << i;
+                    int v = approx_verdict(make_float4(ox, oy, oz, ow), co, thr_f, diou, tmin);
+                    if (v < 0) v = suppresses(boxes[pos_of[c0 + i]], cb, a.thr, diou) ? 1 : 0;
+                    if (v) sup_by |= 1u << i;
                 }
             }
             // c. sequential resolve: a kept member kills every later member it suppresses
@@ -481,7 +551,7 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
             // 3. emit
             if ((keep_bits >> lane) & 1u) {
                 const int slot = kept + __popc(keep_bits & ((1u << lane) - 1u));
-                k_box[slot] = cb; k_out[slot] = co; k_cls[slot] = ccls;
+                k_out[slot] = co; k_cls[slot] = ccls; k_pos[slot] = (unsigned short)pos;
                 const size_t o = (size_t)b * a.max_boxes + slot;
                 if (a.out_xywh) {
                     a.out_xywh[o * 4 + 0] = cb.x; a.out_xywh[o * 4 + 1] = cb.y;
@@ -961,8 +1031,8 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
         prof_mark_end(PROF_NMS, stream);
         return cudaGetLastError();
     }
-    // decode mode with a kept list that fits shared memory: warp-per-image kernels first,
-    // a lean instance for images with <= 512 candidates and one for 513..1024
+    // decode mode with a kept list that fits shared memory: the warp-per-image kernel takes
+    // every image with <= 1024 candidates, nms_kernel the rest
     static int env_off = -1;
     if (env_off < 0) { const char* e = getenv("MGD_NMS_NO_WARP_KERNEL"); env_off = e ? atoi(e) : 0; }
     if (a.cand && nms_warp_bytes(kWarpCapLarge, a.max_boxes) <= 32 * 1024 && !env_off) {
