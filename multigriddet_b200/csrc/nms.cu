@@ -313,12 +313,21 @@ constexpr int kWarpsPerCtaW = 4;
 
 __host__ __device__ inline int nms_kept_pad(int kept_cap) { return (kept_cap + 31) & ~31; }
 
+__host__ __device__ inline size_t nms_warp_key_bytes(int cap, int kept_cap)
+{
+    // sort keys u32[cap]; dead once the sort is done, so the greedy pass keeps its state in
+    // the same bytes: kept outer boxes float4[kpad] | chunk outer boxes float4[32]
+    // | kept class int[kpad] | chunk class int[32] | kept position u16[kpad]
+    const size_t kpad = (size_t)nms_kept_pad(kept_cap);
+    const size_t overlay = kpad * 16 + 32 * 16 + kpad * 4 + 32 * 4 + kpad * 2;
+    const size_t keys = (size_t)cap * 4 > overlay ? (size_t)cap * 4 : overlay;
+    return (keys + 15) & ~(size_t)15;
+}
+
 __host__ __device__ inline size_t nms_warp_bytes(int cap, int kept_cap)
 {
-    // kept outer boxes float4[kpad] | keys u32[cap] | kept class int[kpad]
-    // | sorted position u16[cap] | kept position u16[kpad]
-    const size_t kpad = (size_t)nms_kept_pad(kept_cap);
-    const size_t b = kpad * 16 + (size_t)cap * 4 + kpad * 4 + (size_t)cap * 2 + kpad * 2;
+    // keys / greedy state | sorted position u16[cap]
+    const size_t b = nms_warp_key_bytes(cap, kept_cap) + (size_t)cap * 2;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -368,7 +377,7 @@ __device__ __forceinline__ unsigned overlap_sweep(const float4* k_out, const int
 }
 
 template <int kWarpCap>
-__global__ void __launch_bounds__(kWarpsPerCtaW * 32, 6)
+__global__ void __launch_bounds__(kWarpsPerCtaW * 32, 7)
 nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -380,11 +389,13 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
 
     const int kpad = nms_kept_pad(kept_cap);
     unsigned char* mine = dyn + (size_t)warp * nms_warp_bytes(kWarpCap, kept_cap);
-    float4* k_out = reinterpret_cast<float4*>(mine);
-    unsigned* key = reinterpret_cast<unsigned*>(k_out + kpad);
-    int* k_cls = reinterpret_cast<int*>(key + kWarpCap);
-    unsigned short* pos_of = reinterpret_cast<unsigned short*>(k_cls + kpad);
-    unsigned short* k_pos = pos_of + kWarpCap;
+    unsigned* key = reinterpret_cast<unsigned*>(mine);
+    float4* k_out = reinterpret_cast<float4*>(mine);         // (overlays the keys after the sort)
+    float4* c_out = k_out + kpad;
+    int* k_cls = reinterpret_cast<int*>(c_out + 32);
+    int* c_cls = k_cls + kpad;
+    unsigned short* k_pos = reinterpret_cast<unsigned short*>(c_cls + 32);
+    unsigned short* pos_of = reinterpret_cast<unsigned short*>(mine + nms_warp_key_bytes(kWarpCap, kept_cap));
 
     const HeadGeom& g = a.g;
     const bool diou = a.use_diou != 0;
@@ -414,7 +425,7 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
         const int iw = a.image_hw ? a.image_hw[2 * b + 1] : a.in_w;
 
         // ---- 0. boxes + keys, lane-strided ------------------------------------------
-        int mpad = 32;
+        int mpad = 64;                                   // (every lane takes part in every stage)
         while (mpad < M) mpad <<= 1;
         float scale = 0.f;                               // largest coordinate magnitude
         {
@@ -432,15 +443,16 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
                     boxes[i] = bx;
                     const float4 o = outer_box(bx);
                     scale = fmaxf(scale, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-                    // scores are non-negative floats: their bit patterns order like the values
-                    key[i] = ~__float_as_uint(cd.score);
+                    // scores are non-negative floats: their bit patterns order like the values.
+                    // Real keys stay below 2^31, every padding key is unique and above them, so
+                    // the tie branch of the sort only ever sees genuinely equal scores.
+                    key[i] = 0x7fffffffu - (__float_as_uint(cd.score) & 0x7fffffffu);
                     pos_of[i] = (unsigned short)i;
                 } else {
-                    key[i] = 0xffffffffu;
+                    key[i] = 0x80000000u + (unsigned)i;
                     pos_of[i] = 0xffff;
                 }
             }
-            for (int k = lane; k < kpad; k += 32) k_out[k] = make_float4(inf, inf, -inf, -inf);
         }
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) scale = fmaxf(scale, __shfl_xor_sync(0xffffffffu, scale, o));
@@ -448,33 +460,69 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
         const float tmin = scale < 3.0e38f ? 1e-3f * scale : inf;
         __syncwarp();
         // ---- 1. bitonic sort (score desc, cell index asc) ----------------------------
-        // 32-bit score keys; the cell index (the deterministic tie rule) is only looked up
-        // when two keys are equal.  Padding sorts last: index +inf.
+        // 32-bit score keys only; the deterministic tie rule (lower cell index first) is
+        // applied afterwards to the runs of equal keys, which are rare.
+        // Two compare-exchanges per lane and step, all loads issued before any store: the
+        // pairs of one stage are disjoint, and a lone warp needs the ILP (mpad >= 64, so
+        // both are always in range).
         for (int k = 2; k <= mpad; k <<= 1) {
             for (int jj = k >> 1; jj > 0; jj >>= 1) {
-                for (int t = lane; t < (mpad >> 1); t += 32) {
+                for (int t = lane; t < (mpad >> 1); t += 64) {
                     // t-th compare-exchange of this stage: i has bit jj clear
-                    const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));
-                    const int p = i | jj;
-                    const unsigned ka = key[i], kb = key[p];
-                    const bool up = (i & k) == 0;
-                    bool b_lt_a = kb < ka;
-                    if (kb == ka) {
-                        const unsigned short pa = pos_of[i], pb = pos_of[p];
-                        const int ia = pa == 0xffff ? 0x7fffffff : cand[pa].index;
-                        const int ib = pb == 0xffff ? 0x7fffffff : cand[pb].index;
-                        b_lt_a = ib < ia;
+                    int i[2], p[2];
+                    unsigned ka[2], kb[2];
+                    unsigned short pa[2], pb[2];
+                    #pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int tt = t + 32 * u;
+                        i[u] = ((tt & ~(jj - 1)) << 1) | (tt & (jj - 1));
+                        p[u] = i[u] | jj;
+                        ka[u] = key[i[u]]; kb[u] = key[p[u]];
+                        pa[u] = pos_of[i[u]]; pb[u] = pos_of[p[u]];
                     }
-                    if (b_lt_a == up) {
-                        key[i] = kb; key[p] = ka;
-                        const unsigned short pa = pos_of[i]; pos_of[i] = pos_of[p]; pos_of[p] = pa;
+                    #pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const bool up = (i[u] & k) == 0;
+                        if ((kb[u] < ka[u]) == up) {
+                            key[i[u]] = kb[u]; key[p[u]] = ka[u];
+                            pos_of[i[u]] = pb[u]; pos_of[p[u]] = pa[u];
+                        }
                     }
                 }
                 __syncwarp();
             }
         }
 
+        // equal scores (rare): order each run of equal keys by cell index, rank-sort per run
+        {
+            bool tie = false;
+            for (int i = lane; i < M - 1; i += 32) tie = tie || key[i] == key[i + 1];
+            if (__any_sync(0xffffffffu, tie)) {
+                int s0 = 0;
+                while (s0 < M) {                                  // warp-uniform walk over the runs
+                    int e0 = s0 + 1;
+                    while (e0 < M && key[e0] == key[s0]) ++e0;
+                    if (e0 - s0 > 1) {
+                        for (int j = s0 + lane; j < e0; j += 32) {
+                            const unsigned short pj = pos_of[j];
+                            const int ij = cand[pj].index;
+                            int rank = 0;
+                            for (int i = s0; i < e0; ++i) rank += cand[pos_of[i]].index < ij;
+                            key[s0 + rank] = pj;                  // the run's keys are no longer needed
+                        }
+                        __syncwarp();
+                        for (int j = s0 + lane; j < e0; j += 32) pos_of[j] = (unsigned short)key[j];
+                        __syncwarp();
+                    }
+                    s0 = e0;
+                }
+            }
+        }
+
         // ---- 2. chunked greedy pass, 32 candidates per chunk ---------------------------
+        // (the keys are dead: their bytes now hold the kept list, initialised to empty boxes)
+        for (int k = lane; k < kpad; k += 32) k_out[k] = make_float4(inf, inf, -inf, -inf);
+        __syncwarp();
         int kept = 0;
         const double W = (double)iw, H = (double)ih;
         for (int c0 = 0; c0 < M && kept < a.max_boxes; c0 += 32) {
@@ -512,27 +560,31 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
                 }
             }
             // b. intra-chunk: lane j collects the set of EARLIER alive members that suppress
-            //    it (same levels; the outer boxes travel by shuffle)
+            //    it (same levels; only members still alive are visited, their outer boxes
+            //    travel by shuffle)
             const unsigned live0 = __ballot_sync(0xffffffffu, alive);
             unsigned pend = 0;
-            for (int i = 0; i < n - 1; ++i) {
-                if (!((live0 >> i) & 1u)) continue;               // warp-uniform
-                const float ox = __shfl_sync(0xffffffffu, co.x, i), oy = __shfl_sync(0xffffffffu, co.y, i);
-                const float oz = __shfl_sync(0xffffffffu, co.z, i), ow = __shfl_sync(0xffffffffu, co.w, i);
-                const int icls = __shfl_sync(0xffffffffu, ccls, i);
-                if (alive && lane > i && !(a.per_class && icls != ccls) &&
-                    !(pretest && (oz <= co.x || co.z <= ox || ow <= co.y || co.w <= oy)))
-                    pend |= 1u << i;
+            {
+                unsigned rest = live0;
+                while (rest) {                                    // warp-uniform
+                    const int i = __ffs((int)rest) - 1;
+                    rest &= rest - 1;
+                    const float ox = __shfl_sync(0xffffffffu, co.x, i), oy = __shfl_sync(0xffffffffu, co.y, i);
+                    const float oz = __shfl_sync(0xffffffffu, co.z, i), ow = __shfl_sync(0xffffffffu, co.w, i);
+                    const int icls = __shfl_sync(0xffffffffu, ccls, i);
+                    if (alive && lane > i && !(a.per_class && icls != ccls) &&
+                        !(pretest && (oz <= co.x || co.z <= ox || ow <= co.y || co.w <= oy)))
+                        pend |= 1u << i;
+                }
             }
+            c_out[lane] = co;
+            __syncwarp();
             unsigned sup_by = 0;                                  // earlier members suppressing me
             while (__any_sync(0xffffffffu, pend != 0)) {
-                // the partner's outer box comes by shuffle from the lane that holds it
-                const int i = pend ? __ffs((int)pend) - 1 : 0;
-                const float ox = __shfl_sync(0xffffffffu, co.x, i), oy = __shfl_sync(0xffffffffu, co.y, i);
-                const float oz = __shfl_sync(0xffffffffu, co.z, i), ow = __shfl_sync(0xffffffffu, co.w, i);
                 if (pend) {
+                    const int i = __ffs((int)pend) - 1;
                     pend &= pend - 1;
-                    int v = approx_verdict(make_float4(ox, oy, oz, ow), co, thr_f, diou, tmin);
+                    int v = approx_verdict(c_out[i], co, thr_f, diou, tmin);
                     if (v < 0) v = suppresses(boxes[pos_of[c0 + i]], cb, a.thr, diou) ? 1 : 0;
                     if (v) sup_by |= 1u << i;
                 }
@@ -1037,7 +1089,9 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
     if (env_off < 0) { const char* e = getenv("MGD_NMS_NO_WARP_KERNEL"); env_off = e ? atoi(e) : 0; }
     if (a.cand && nms_warp_bytes(kWarpCapLarge, a.max_boxes) <= 32 * 1024 && !env_off) {
         auto run = [&](auto kernel, int cap, int min_count) -> cudaError_t {
-            const size_t dyn = nms_warp_bytes(cap, a.max_boxes) * kWarpsPerCtaW;
+            static int env_pad = -1;
+            if (env_pad < 0) { const char* e = getenv("MGD_NMS_SMEM_PAD"); env_pad = e ? atoi(e) : 0; }
+            const size_t dyn = nms_warp_bytes(cap, a.max_boxes) * kWarpsPerCtaW + (size_t)env_pad;
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
             if (e != cudaSuccess) return e;
             int ctas_per_sm = (int)((220 * 1024) / (dyn + 1024));

@@ -512,3 +512,39 @@ def test_wbf_matches_oracle(c_oracle):
             assert np.array_equal(got["classes"][b, :k], ref[b]["classes"])
             np.testing.assert_allclose(got["scores"][b, :k], ref[b]["scores"], rtol=RTOL)
             np.testing.assert_allclose(got["boxes_xywh"][b, :k], ref[b]["boxes_xywh"], rtol=RTOL, atol=1e-4)
+
+
+def test_decode_equal_scores_follow_the_cell_index_rule(c_oracle):
+    """Exactly equal scores: lower cell index first, on the warp-per-image NMS path
+    (<= 1024 candidates).  Rows are duplicated across cells so whole runs of candidates tie."""
+    S, C, B = 608, 80, 6
+    anchors = synth.coco_anchors(np.float32)
+    preds = _planted(33, B, S, C, 40, anchors, c_oracle)
+    rng = np.random.default_rng(5)
+    for b in range(B):
+        for l, p in enumerate(preds):
+            G = p.shape[1]
+            flat = p[b].reshape(G * G, -1)
+            hot = np.flatnonzero(flat[:, 4] > 0)               # positive cells (objectness logit > 0)
+            if hot.size == 0:
+                continue
+            for src in rng.choice(hot, size=min(4, hot.size), replace=False):
+                dst = rng.choice(G * G, size=6 + 3 * b, replace=False)
+                flat[dst] = flat[src]                          # identical logits -> identical score
+    shapes = synth.image_shapes(2, B, mixed=True)
+    for method, per_class in (("diou", False), ("standard", True)):
+        kw = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method=method,
+                  per_class=per_class)
+        ref = c_oracle.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+        got = engine.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+        assert int(ref["counts"].max()) > 0
+        same, bits_off = _compare_detections(got, ref, B)
+        assert same == B and bits_off == 0
+    # every cell identical (constant head): one giant run of equal scores
+    S2, C2 = 160, 3
+    const = [np.full((2, g, g, 5 + 3 + C2), 0.25, dtype=np.float32) for g in (5, 10, 20)]
+    kw = dict(max_boxes=50, confidence=0.0, nms_threshold=0.45, nms_method="diou")
+    ref = c_oracle.decode_nms(const, [(S2, S2)], (S2, S2), anchors, C2, **kw)
+    got = engine.decode_nms(const, (S2, S2), (S2, S2), anchors, C2, **kw)
+    same, bits_off = _compare_detections(got, ref, 2)
+    assert same == 2 and bits_off == 0
