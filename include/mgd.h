@@ -51,8 +51,18 @@ typedef enum {
 enum { MGD_MEM_HOST = 0, MGD_MEM_DEVICE = 1 };
 
 enum {
-    MGD_FLAG_SYNC = 1              /* synchronise `stream` before returning and
+    MGD_FLAG_SYNC = 1,             /* synchronise `stream` before returning and
                                       report deferred device-side errors          */
+    MGD_FLAG_TF_COMPAT = 2         /* mgd_encode_targets: the semantics of the
+                                      reference's TensorFlow encoder
+                                      tf_preprocess_true_boxes (generators.py:
+                                      2696-3390) instead of the NumPy encoder's:
+                                      exact centre, unrounded IoL (+1e-7), every
+                                      in-bounds cell of the 3x3 block written,
+                                      highest box index wins a shared cell, xy =
+                                      [-dcol + frac(cy), -drow + frac(cx)], class ids
+                                      outside [0, C) light no class channel and
+                                      raise no error                              */
 };
 
 enum { MGD_NMS_IOU = 0, MGD_NMS_DIOU = 1, MGD_NMS_SOFT = 2, MGD_NMS_WBF = 3 };

@@ -18,6 +18,7 @@ MGD_MAX_LAYERS = 5
 MGD_MAX_ANCHORS_PER_LAYER = 8
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_SYNC = 1
+FLAG_TF_COMPAT = 2
 NMS_IOU, NMS_DIOU, NMS_SOFT, NMS_WBF = 0, 1, 2, 3
 
 OK, ERR_INVALID_ARGUMENT, ERR_CLASS_RANGE, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(6)

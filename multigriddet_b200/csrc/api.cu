@@ -333,7 +333,7 @@ struct EncodeScratch { int* table; BoxRec* recs; };
 
 int encode_device(const HeadGeom& g, const float* boxes, int batch, int N, float* const* y,
                   int num_sms, cudaStream_t stream, int* d_status, unsigned long long* d_stats,
-                  const Alloc& al)
+                  const Alloc& al, int tf_compat)
 {
     const int step = chunk_images(g, batch);
     for (int b0 = 0; b0 < batch; b0 += step) {
@@ -346,6 +346,7 @@ int encode_device(const HeadGeom& g, const float* boxes, int batch, int N, float
         a.boxes = boxes + (size_t)b0 * N * 5;
         for (int l = 0; l < g.L; ++l)
             a.y[l] = y[l] + (size_t)b0 * g.gh[l] * g.gw[l] * g.D[l];
+        a.tf_compat = tf_compat;
         a.status = d_status;
         a.stats = d_stats;
         a.big_tables = nullptr;
@@ -631,7 +632,7 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
         d_stats = reinterpret_cast<unsigned long long*>(d_status);
         int* d_flag = reinterpret_cast<int*>(d_stats + 4);
         rc = encode_device(g, boxes, batch, max_boxes, y_true, num_sms, st, d_flag, d_stats,
-                           Alloc{nullptr, st});
+                           Alloc{nullptr, st}, (flags & MGD_FLAG_TF_COMPAT) != 0);
         if (rc) return rc;
         if (flags & MGD_FLAG_SYNC) {
             unsigned long long h[5] = {0, 0, 0, 0, 0};
@@ -690,7 +691,8 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
             else CUDA_TRY(ar.take(reinterpret_cast<void**>(&d_y[l]), (size_t)nb * g.gh[l] * g.gw[l] * g.D[l] * 4));
         }
         rc = encode_device(g, d_boxes + (size_t)b0 * max_boxes * 5, nb, max_boxes, d_y, num_sms, st,
-                           reinterpret_cast<int*>(d_meta + 4), d_meta, Alloc{&ar, st});
+                           reinterpret_cast<int*>(d_meta + 4), d_meta, Alloc{&ar, st},
+                           (flags & MGD_FLAG_TF_COMPAT) != 0);
         if (rc) return rc;
         for (int l = 0; l < g.L && !zero_copy; ++l) {
             const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];

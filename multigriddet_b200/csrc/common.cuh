@@ -40,6 +40,7 @@ struct EncodeArgs {
     int* table;                       // layer-major owner table: [l][b][cell]
     int* big_tables;                  // (B, 2, cells) scratch when the tables exceed shared memory, else nullptr
     BoxRec* recs;                     // (B, N)
+    int tf_compat;                    // 1: tf_preprocess_true_boxes semantics (MGD_FLAG_TF_COMPAT)
     int* status;                      // bit0: class >= C, bit1: negative class on a valid box
     unsigned long long* stats;        // [valid boxes, skipped writes, positive cells, -]
 };

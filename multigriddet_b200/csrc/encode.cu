@@ -66,6 +66,22 @@ __device__ __forceinline__ int match_anchor(const HeadGeom& g, float bw, float b
     return best;
 }
 
+// tf_preprocess_true_boxes (generators.py:2811-2931): float32 IoL with the Keras epsilon
+// in the denominator, no rounding, first maximum over the layer-major anchor list
+__device__ __forceinline__ int match_anchor_tf(const HeadGeom& g, float bw, float bh)
+{
+    int best = 0;
+    float top = -INFINITY;
+    const float box_area = __fmul_rn(bw, bh);
+    for (int i = 0; i < g.K; ++i) {
+        const float aw = g.anc32[i][0], ah = g.anc32[i][1];
+        const float inter = __fmul_rn(fminf(bw, aw), fminf(bh, ah));
+        const float iol = __fdiv_rn(inter, __fadd_rn(fmaxf(box_area, __fmul_rn(aw, ah)), 1e-7f));
+        if (iol > top) { top = iol; best = i; }
+    }
+    return best;
+}
+
 // packed per-box placement kept in shared memory between the phases
 __device__ __forceinline__ int pack_place(int layer, int col, int row)
 {
@@ -99,87 +115,138 @@ encode_assign_kernel(const __grid_constant__ EncodeArgs a)
     unsigned int n_valid = 0, n_skipped = 0, n_pos = 0;
     int status = 0;
 
-    // ---- phase A: per-box record + cover table --------------------------------
-    for (int t = tid; t < a.N; t += kAssignThreads) {
-        const float* bx = a.boxes + ((size_t)b * a.N + t) * 5;
-        const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3], cf = bx[4];
-        if (!(cf < (float)g.C)) status |= 1;                         // :3409, every row
-        const float bw = __fsub_rn(x2, x1), bh = __fsub_rn(y2, y1);  // :3416
-        int pl = -1;
-        if (!(__fmul_rn(bw, bh) <= 0.0f)) {                          // :3431
+    if (a.tf_compat) {
+        // ---- TensorFlow semantics (generators.py:2696-3390), one pass ----------------------
+        // exact centre, unrounded float32 IoL, every in-bounds cell of the 3x3 block written
+        // (the occupancy test reads a still-empty tensor, :3245), duplicates resolved like
+        // tensor_scatter_nd_update on the CPU: the highest box index wins.  Stored xy =
+        // [-kj + frac(cy), -ki + frac(cx)] (:3337-3339): rec.fx / rec.fy hold the swapped
+        // fractions so the fill kernel is the same.  No class-range error: one_hot leaves
+        // the class channels zero for ids outside [0, C) (:3351) -> hot_class = objectness.
+        for (int t = tid; t < a.N; t += kAssignThreads) {
+            const float* bx = a.boxes + ((size_t)b * a.N + t) * 5;
+            const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3], cf = bx[4];
+            const float bw = __fsub_rn(x2, x1), bh = __fsub_rn(y2, y1);          // :2731
+            if (!(__fmul_rn(bw, bh) > 0.0f)) continue;                            // :2757
             ++n_valid;
-            const int cls = (int)cf;                                 // astype('int32')
-            if (cls < 0) status |= 2;
-            // (x1+x2)//2 on float32 == floor((x1+x2)/2): the halving is exact
-            const float cxp = floorf(__fmul_rn(__fadd_rn(x1, x2), 0.5f));   // :3415
-            const float cyp = floorf(__fmul_rn(__fadd_rn(y1, y2), 0.5f));
-            const int ga = match_anchor(g, bw, bh);
+            const float cxp = __fmul_rn(__fadd_rn(x1, x2), 0.5f);                 // :2730 (/2.0 exact)
+            const float cyp = __fmul_rn(__fadd_rn(y1, y2), 0.5f);
+            const int ga = match_anchor_tf(g, bw, bh);
             int layer = 0;
             while (layer + 1 < g.L && ga >= g.anchor_first[layer + 1]) ++layer;
             const int k = ga - g.anchor_first[layer];
-            // :3438-3439  f32 * (G/S as float64) -> float64 (NumPy 2 promotion)
-            const double gx = __dmul_rn((double)cxp, __ddiv_rn((double)g.gh[layer], (double)g.in_h));
-            const double gy = __dmul_rn((double)cyp, __ddiv_rn((double)g.gw[layer], (double)g.in_w));
-            const int col = (int)fmin(fmax(gx, -4.0), 1.0e6);        // int(): truncation
-            const int row = (int)fmin(fmax(gy, -4.0), 1.0e6);
+            const int gh = g.gh[layer], gw = g.gw[layer];
+            const float cx = __fmul_rn(cxp, __fdiv_rn((float)gw, (float)g.in_w)); // :2960-2965
+            const float cy = __fmul_rn(cyp, __fdiv_rn((float)gh, (float)g.in_h));
+            const int col = (int)fminf(fmaxf(cx, -4.0f), 1.0e6f);                 // tf.cast: truncation
+            const int row = (int)fminf(fmaxf(cy, -4.0f), 1.0e6f);
             BoxRec rec;
-            rec.fx = __dsub_rn(gx, (double)col);
-            rec.fy = __dsub_rn(gy, (double)row);
-            if (!g.anchors_f64) {                                    // :3446-3449
-                const float rw = __fdiv_rn(bw, g.anc32[ga][0]);
-                const float rh = __fdiv_rn(bh, g.anc32[ga][1]);
-                // NumPy's float32 log is libm logf there; log in double rounded once
-                // to float reproduces it (<= 1 ulp away in ~0.4% of inputs)
-                rec.tw = (float)log(rw < 1e-3f ? 1e-3 : (double)rw);
-                rec.th = (float)log(rh < 1e-3f ? 1e-3 : (double)rh);
-            } else {
-                const double rw = __ddiv_rn((double)bw, g.anc64[ga][0]);
-                const double rh = __ddiv_rn((double)bh, g.anc64[ga][1]);
-                rec.tw = (float)log(rw < 1e-3 ? 1e-3 : rw);
-                rec.th = (float)log(rh < 1e-3 ? 1e-3 : rh);
-            }
+            rec.fx = (double)__fsub_rn(cy, (float)row);                           // channel 0 gets ty
+            rec.fy = (double)__fsub_rn(cx, (float)col);                           // channel 1 gets tx
+            const float rw = fmaxf(__fdiv_rn(bw, g.anc32[ga][0]), 1e-3f);         // :3330-3333
+            const float rh = fmaxf(__fdiv_rn(bh, g.anc32[ga][1]), 1e-3f);
+            rec.tw = (float)log((double)rw);
+            rec.th = (float)log((double)rh);
             rec.hot_anchor = 5 + k;
-            rec.hot_class = 5 + g.na[layer] + max(cls, 0);
+            // tf.cast(float -> int32) truncates; out-of-range ids light no class channel
+            const int cls = (cf >= 0.0f && cf < 2.0e9f) ? (int)cf : -1;
+            rec.hot_class = (cls >= 0 && cls < g.C) ? 5 + g.na[layer] + cls : 4;
             a.recs[(size_t)b * a.N + t] = rec;
-            pl = pack_place(layer, col, row);
-            const int g0 = g.gh[layer], g1 = g.gw[layer];
-            const int c0 = (pl & 0x3fff) - 2, r0 = ((pl >> 14) & 0x3fff) - 2;
             #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
                 #pragma unroll
                 for (int dy = -1; dy <= 1; ++dy) {
-                    const int cc = c0 + dx, rr = r0 + dy;
-                    if (cc >= 0 && cc < g0 && rr >= 0 && rr < g1)
-                        atomicMin(&cover[g.cell_off[layer] + rr * g1 + cc], t);
+                    const int cc = col + dx, rr = row + dy;
+                    if (cc >= 0 && cc < gw && rr >= 0 && rr < gh)
+                        atomicMax(&owner[g.cell_off[layer] + rr * gw + cc],
+                                  t * 16 + (dx + 1) * 3 + (dy + 1));
                 }
             }
         }
-        place[t] = pl;
-    }
-    __syncthreads();
+        __syncthreads();
+    } else {
+        // ---- phase A: per-box record + cover table --------------------------------
+        for (int t = tid; t < a.N; t += kAssignThreads) {
+            const float* bx = a.boxes + ((size_t)b * a.N + t) * 5;
+            const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3], cf = bx[4];
+            if (!(cf < (float)g.C)) status |= 1;                         // :3409, every row
+            const float bw = __fsub_rn(x2, x1), bh = __fsub_rn(y2, y1);  // :3416
+            int pl = -1;
+            if (!(__fmul_rn(bw, bh) <= 0.0f)) {                          // :3431
+                ++n_valid;
+                const int cls = (int)cf;                                 // astype('int32')
+                if (cls < 0) status |= 2;
+                // (x1+x2)//2 on float32 == floor((x1+x2)/2): the halving is exact
+                const float cxp = floorf(__fmul_rn(__fadd_rn(x1, x2), 0.5f));   // :3415
+                const float cyp = floorf(__fmul_rn(__fadd_rn(y1, y2), 0.5f));
+                const int ga = match_anchor(g, bw, bh);
+                int layer = 0;
+                while (layer + 1 < g.L && ga >= g.anchor_first[layer + 1]) ++layer;
+                const int k = ga - g.anchor_first[layer];
+                // :3438-3439  f32 * (G/S as float64) -> float64 (NumPy 2 promotion)
+                const double gx = __dmul_rn((double)cxp, __ddiv_rn((double)g.gh[layer], (double)g.in_h));
+                const double gy = __dmul_rn((double)cyp, __ddiv_rn((double)g.gw[layer], (double)g.in_w));
+                const int col = (int)fmin(fmax(gx, -4.0), 1.0e6);        // int(): truncation
+                const int row = (int)fmin(fmax(gy, -4.0), 1.0e6);
+                BoxRec rec;
+                rec.fx = __dsub_rn(gx, (double)col);
+                rec.fy = __dsub_rn(gy, (double)row);
+                if (!g.anchors_f64) {                                    // :3446-3449
+                    const float rw = __fdiv_rn(bw, g.anc32[ga][0]);
+                    const float rh = __fdiv_rn(bh, g.anc32[ga][1]);
+                    // NumPy's float32 log is libm logf there; log in double rounded once
+                    // to float reproduces it (<= 1 ulp away in ~0.4% of inputs)
+                    rec.tw = (float)log(rw < 1e-3f ? 1e-3 : (double)rw);
+                    rec.th = (float)log(rh < 1e-3f ? 1e-3 : (double)rh);
+                } else {
+                    const double rw = __ddiv_rn((double)bw, g.anc64[ga][0]);
+                    const double rh = __ddiv_rn((double)bh, g.anc64[ga][1]);
+                    rec.tw = (float)log(rw < 1e-3 ? 1e-3 : rw);
+                    rec.th = (float)log(rh < 1e-3 ? 1e-3 : rh);
+                }
+                rec.hot_anchor = 5 + k;
+                rec.hot_class = 5 + g.na[layer] + max(cls, 0);
+                a.recs[(size_t)b * a.N + t] = rec;
+                pl = pack_place(layer, col, row);
+                const int g0 = g.gh[layer], g1 = g.gw[layer];
+                const int c0 = (pl & 0x3fff) - 2, r0 = ((pl >> 14) & 0x3fff) - 2;
+                #pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    #pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int cc = c0 + dx, rr = r0 + dy;
+                        if (cc >= 0 && cc < g0 && rr >= 0 && rr < g1)
+                            atomicMin(&cover[g.cell_off[layer] + rr * g1 + cc], t);
+                    }
+                }
+            }
+            place[t] = pl;
+        }
+        __syncthreads();
 
-    // ---- phase B: sequential skip rule per box, owner = last writer -----------
-    for (int t = tid; t < a.N; t += kAssignThreads) {
-        const int pl = place[t];
-        if (pl < 0) continue;
-        const int layer = pl >> 28;
-        const int c0 = (pl & 0x3fff) - 2, r0 = ((pl >> 14) & 0x3fff) - 2;
-        const int g0 = g.gh[layer], g1 = g.gw[layer];
-        int written = 0;
-        #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {                           // :3454 x outer
+        // ---- phase B: sequential skip rule per box, owner = last writer -----------
+        for (int t = tid; t < a.N; t += kAssignThreads) {
+            const int pl = place[t];
+            if (pl < 0) continue;
+            const int layer = pl >> 28;
+            const int c0 = (pl & 0x3fff) - 2, r0 = ((pl >> 14) & 0x3fff) - 2;
+            const int g0 = g.gh[layer], g1 = g.gw[layer];
+            int written = 0;
             #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {                       // :3456 y inner
-                const int cc = c0 + dx, rr = r0 + dy;
-                if (cc < 0 || cc >= g0 || rr < 0 || rr >= g1) continue;   // :3459-3462
-                const int cell = g.cell_off[layer] + rr * g1 + cc;
-                if (cover[cell] < t && written >= 3) { ++n_skipped; continue; }   // :3463
-                ++written;
-                atomicMax(&owner[cell], t * 16 + (dx + 1) * 3 + (dy + 1));
+            for (int dx = -1; dx <= 1; ++dx) {                           // :3454 x outer
+                #pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {                       // :3456 y inner
+                    const int cc = c0 + dx, rr = r0 + dy;
+                    if (cc < 0 || cc >= g0 || rr < 0 || rr >= g1) continue;   // :3459-3462
+                    const int cell = g.cell_off[layer] + rr * g1 + cc;
+                    if (cover[cell] < t && written >= 3) { ++n_skipped; continue; }   // :3463
+                    ++written;
+                    atomicMax(&owner[cell], t * 16 + (dx + 1) * 3 + (dy + 1));
+                }
             }
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- phase C: publish the owner codes, layer-major ------------------------
     const int rec_base = b * a.N * 16;

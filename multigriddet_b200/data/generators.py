@@ -51,32 +51,38 @@ def preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, multi_a
 
 
 def tf_preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, multi_anchor_assign,
-                             grid_shapes, debug_aug_pipeline=False):
-    """Signature-compatible stand-in for the reference's ``@tf.function`` encoder
-    (generators.py:2696-3390).
+                             grid_shapes, debug_aug_pipeline=False, semantics="tf_compat"):
+    """Drop-in for the reference's ``@tf.function`` encoder (generators.py:2696-3390),
+    its default training path.
 
-    It computes the *NumPy-path* semantics (the runnable, self-consistent encoder,
-    SURVEY.md section 0): floor-divided centres, rounded-IoL anchor choice and the
-    sequential occupancy rule.  The TF path differs from that in known ways (exact
-    centres, no IoL rounding, last box wins every contested cell, x/y fractions
-    swapped -- SURVEY.md 8a-3); those are NOT reproduced and parity against real
-    TensorFlow is unpinned (TF is not installed here).
+    ``semantics="tf_compat"`` (default) reproduces what that function computes, which is
+    NOT what ``preprocess_true_boxes`` computes: exact box centres,
+    unrounded IoL with the Keras epsilon, every in-bounds cell of the 3x3 block written,
+    the highest box index wins a contested cell (CPU ``tensor_scatter_nd_update`` order),
+    xy stored as ``[-dcol + frac(cy), -drow + frac(cx)]``, no class-range error.  Parity
+    against real TensorFlow is UNPINNED: TF is not installed in this image and no
+    reference test pins more than one symmetric box; the oracle is a line-by-line
+    restatement (``oracle.mgd_oracle.encode_targets_tf_compat``).
+    ``semantics="numpy"`` routes to the NumPy encoder's self-consistent rules instead.
 
     A ctypes library cannot be traced into a TF graph: inside ``dataset.map`` call
     it through ``tf.py_function`` / ``tf.numpy_function``.  TensorFlow tensors are
     accepted eagerly via DLPack when TF is present; NumPy and torch CUDA tensors
     always work.  Returns the same container type it was given.
     """
-    del debug_aug_pipeline
+    del debug_aug_pipeline, multi_anchor_assign
+    anchors = _as_host_anchors(anchors)
+    anchors = [np.asarray(a, dtype=np.float32) for a in anchors]      # tf.constant(..., float32), :1446
+    shape = tuple(int(v) for v in np.asarray(input_shape).reshape(-1)[:2])
+    if grid_shapes is not None:
+        grid_shapes = [(int(g[0]), int(g[1])) for g in grid_shapes]
     tf_mod = type(true_boxes).__module__.split(".")[0] == "tensorflow"
     if tf_mod:
         import tensorflow as tf            # only reachable where TF exists
         boxes = np.from_dlpack(tf.experimental.dlpack.to_dlpack(true_boxes)) \
             if hasattr(np, "from_dlpack") else true_boxes.numpy()
-        shape = tuple(int(v) for v in np.asarray(input_shape).reshape(-1)[:2])
-        y = preprocess_true_boxes(boxes, shape, anchors, num_classes, multi_anchor_assign,
-                                  grid_shapes)
+        y = engine.encode_targets(boxes, shape, anchors, int(num_classes), grid_shapes,
+                                  semantics=semantics)
         return [tf.convert_to_tensor(t) for t in y]
-    shape = tuple(int(v) for v in np.asarray(input_shape).reshape(-1)[:2])
-    return preprocess_true_boxes(true_boxes, shape, anchors, num_classes, multi_anchor_assign,
-                                 grid_shapes)
+    return engine.encode_targets(true_boxes, shape, anchors, int(num_classes), grid_shapes,
+                                 semantics=semantics)

@@ -67,8 +67,10 @@ def post_config(max_boxes=100, confidence=0.1, nms_threshold=0.5, nms_method="di
 # ------------------------------------------------------------------------------
 
 def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=None,
-                   out=None, sync=True, return_stats=False):
-    """Multi-grid y_true encoder (reference ``preprocess_true_boxes`` semantics).
+                   out=None, sync=True, return_stats=False, semantics="numpy"):
+    """Multi-grid y_true encoder.  ``semantics="numpy"``: the reference's
+    ``preprocess_true_boxes``; ``"tf_compat"``: its TensorFlow encoder
+    ``tf_preprocess_true_boxes`` (MGD_FLAG_TF_COMPAT, include/mgd.h).
 
     true_boxes: (B, N, 5) NumPy array (any dtype) or torch CUDA float32 tensor.
     Returns a list of L arrays/tensors (B, Gh, Gw, 5+A+C) float32 in the same
@@ -77,6 +79,9 @@ def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=No
     at the next ``poll_status``.
     """
     lib = _lib.load()
+    if semantics not in ("numpy", "tf_compat"):
+        raise ValueError(f"semantics must be 'numpy' or 'tf_compat', got {semantics!r}")
+    mode = _lib.FLAG_TF_COMPAT if semantics == "tf_compat" else 0
     cfg = _lib.make_head_config(anchors, num_classes, input_shape, grid_shapes)
     L = cfg.num_layers
     stats = (ctypes.c_longlong * 4)()
@@ -96,7 +101,7 @@ def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=No
         rc = lib.mgd_encode_targets(ctypes.byref(cfg), ctypes.c_void_p(boxes.data_ptr()), B, N,
                                     ptrs, _lib.MEM_DEVICE, dev,
                                     ctypes.c_void_p(_torch_stream(dev)),
-                                    _lib.FLAG_SYNC if sync else 0, stats)
+                                    (_lib.FLAG_SYNC if sync else 0) | mode, stats)
     else:
         boxes = np.ascontiguousarray(np.asarray(true_boxes), dtype=np.float32)
         if boxes.ndim != 3 or boxes.shape[2] != 5:
@@ -108,7 +113,7 @@ def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=No
         ptrs = _lib.ptr_array([o.ctypes.data for o in out])
         rc = lib.mgd_encode_targets(ctypes.byref(cfg), ctypes.c_void_p(boxes.ctypes.data), B, N,
                                     ptrs, _lib.MEM_HOST, _current_device(), None,
-                                    _lib.FLAG_SYNC, stats)
+                                    _lib.FLAG_SYNC | mode, stats)
     _lib.raise_for_status(rc)
     if return_stats:
         return out, {"n_valid_boxes": int(stats[0]), "n_skipped_writes": int(stats[1]),

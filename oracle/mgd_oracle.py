@@ -142,6 +142,96 @@ def encode_targets(true_boxes, input_shape, anchors, num_classes,
     return y_true
 
 
+def encode_targets_tf_compat(true_boxes, input_shape, anchors, num_classes, grid_shapes=None,
+                             return_stats=False):
+    """The TensorFlow encoder's semantics -- generators.py:2696-3390
+    (``tf_preprocess_true_boxes``, the reference's default training path).
+
+    PARITY UNPINNED: TensorFlow is not installed in this image and no reference test
+    pins this function beyond one symmetric box (tests/test_9cell_alignment.py), so this
+    is a line-by-line restatement of the TF ops in float32 NumPy, not a checked one.
+    It differs from the NumPy encoder above in every one of these points:
+
+    * centre = (x1y1 + x2y2) / 2.0, no floor (:2730); valid <=> w*h > 0 (:2757);
+    * IoL = inter / (max(area_box, area_anchor) + 1e-7), float32, no rounding (:2823-2825);
+      layer = first argmax of the per-layer maxima, anchor = first argmax inside that
+      layer (:2882-2931) == first global argmax;
+    * cell: col = int(cx), row = int(cy) with cx = x * (grid_w / input_w) in float32
+      (:2960-2979);
+    * every in-bounds cell of the 3x3 block is written: the occupancy rule reads a
+      tensor that is still all zero (:3245, one scatter per layer :3370) so it never fires;
+    * stored xy = [-kj + ty, -ki + tx] with ki the ROW offset, kj the COLUMN offset,
+      tx = frac(cx), ty = frac(cy) (:2978-2979, :3337-3339): channel 0 carries the column
+      offset plus the fractional ROW position and vice versa;
+    * duplicates inside one ``tensor_scatter_nd_update`` (:3370): last update wins on
+      CPU, i.e. the highest box index covering the cell (GPU/XLA order is unspecified);
+    * no class-range assertion: ``tf.one_hot`` (:3351) leaves the class channels zero
+      for ids outside [0, C).
+    """
+    tb = np.array(np.asarray(true_boxes), dtype=np.float32)
+    B, N = tb.shape[0], tb.shape[1]
+    num_layers = len(anchors)
+    in_h, in_w = int(input_shape[0]), int(input_shape[1])
+    if grid_shapes is None:
+        grid_shapes = default_grid_shapes(np.array(input_shape, dtype=np.int32), num_layers)
+    f32 = np.float32
+    centre = (tb[..., 0:2] + tb[..., 2:4]) / f32(2.0)                # :2730
+    extent = tb[..., 2:4] - tb[..., 0:2]                             # :2731
+    cls_all = tb[..., 4].astype(np.int32)                            # :2732 tf.cast truncates
+    area = extent[..., 0] * extent[..., 1]
+    valid = area > 0.0                                               # :2757
+    table = np.concatenate([np.asarray(a, dtype=np.float32) for a in anchors], axis=0)
+    counts = [len(a) for a in anchors]
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    inter = np.minimum(extent[:, :, None, :], table[None, None])     # :2811
+    inter_area = inter[..., 0] * inter[..., 1]
+    anchor_area = table[:, 0] * table[:, 1]
+    largest = np.maximum(area[..., None], anchor_area[None, None])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        iols = inter_area / (largest + f32(1e-7))                    # :2825 keras epsilon
+    per_layer_max = np.stack([iols[..., s:s + c].max(-1) for s, c in zip(starts, counts)], -1)
+    layer_of = per_layer_max.argmax(-1)                              # :2895 first maximum
+    anchor_in = np.stack([iols[..., s:s + c].argmax(-1) for s, c in zip(starts, counts)], -1)
+    widths = [5 + counts[l] + num_classes for l in range(num_layers)]
+    y_true = [np.zeros((B, int(grid_shapes[l][0]), int(grid_shapes[l][1]), widths[l]),
+                       dtype=np.float32) for l in range(num_layers)]
+    n_valid = int(valid.sum())
+    for b in range(B):
+        for t in range(N):                                           # ascending: last write wins
+            if not valid[b, t]:
+                continue
+            layer = int(layer_of[b, t])
+            k = int(anchor_in[b, t, layer])
+            gh, gw = int(grid_shapes[layer][0]), int(grid_shapes[layer][1])
+            cx = centre[b, t, 0] * (f32(gw) / f32(in_w))             # :2960-2965 float32
+            cy = centre[b, t, 1] * (f32(gh) / f32(in_h))
+            col, row = int(cx), int(cy)                              # :2974-2975 truncation
+            tx = f32(cx - f32(col))
+            ty = f32(cy - f32(row))
+            aw, ah = table[starts[layer] + k]
+            tw = np.log(np.maximum(extent[b, t, 0] / aw, f32(1e-3))) # :3330-3333
+            th = np.log(np.maximum(extent[b, t, 1] / ah, f32(1e-3)))
+            cls = int(cls_all[b, t])
+            for ki in (-1, 0, 1):                                    # :2993 row offset, outer
+                for kj in (-1, 0, 1):                                # column offset, inner
+                    rr, cc = row + ki, col + kj
+                    if rr < 0 or rr >= gh or cc < 0 or cc >= gw:     # :3083-3091
+                        continue
+                    rowv = y_true[layer][b, rr, cc]
+                    rowv[:] = 0.0                                    # the update replaces the row
+                    rowv[0] = f32(-kj) + ty                          # :3337
+                    rowv[1] = f32(-ki) + tx                          # :3338
+                    rowv[2] = tw
+                    rowv[3] = th
+                    rowv[4] = 1.0
+                    rowv[5 + k] = 1.0
+                    if 0 <= cls < num_classes:                       # tf.one_hot :3351
+                        rowv[5 + counts[layer] + cls] = 1.0
+    if return_stats:
+        return y_true, {"n_valid_boxes": n_valid, "n_skipped_writes": 0}
+    return y_true
+
+
 def encode_targets_parallel_scheme(true_boxes, input_shape, anchors, num_classes,
                                    grid_shapes=None):
     """The order-free formulation the CUDA encoder uses (encode):
