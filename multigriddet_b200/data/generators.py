@@ -62,7 +62,7 @@ def tf_preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, mult
     xy stored as ``[-dcol + frac(cy), -drow + frac(cx)]``, no class-range error.  Parity
     against real TensorFlow is UNPINNED: TF is not installed in this image and no
     reference test pins more than one symmetric box; the oracle is a line-by-line
-    restatement (``oracle.mgd_oracle.encode_targets_tf_compat``).
+    restatement of the TF ops (see tests/test_tf_compat.py).
     ``semantics="numpy"`` routes to the NumPy encoder's self-consistent rules instead.
 
     A ctypes library cannot be traced into a TF graph: inside ``dataset.map`` call
