@@ -355,7 +355,7 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": dk["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": dk["frac"],
                 "traffic": traffic * dk["images_per_launch"] if traffic else None,
-                "peak_source": peak_src,
+                "peak_source": peak_src, "frac_of_nominal_8tbs": dk["achieved_gbs"] / 8000.0,
                 "algorithmic_bytes_per_image": BYTES_ENCODE if dominant == "encode_fill" else BYTES_DECODE,
                 "step_frac_of_hbm_peak": (BYTES_ENCODE + BYTES_DECODE) * B * args.steps
                                          / (ms / 1e3) / 1e9 / peak}
@@ -392,12 +392,35 @@ def run_b200(args):
             return fd.result()
 
         e2e_step()
+        e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             res = e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+
+        # what the link itself does with the same bytes: one bulk H2D and one bulk D2H of the
+        # step's tensors, concurrently, from the same pinned buffers (no kernels, no chunking)
+        d_in = [torch.empty_like(p, device=device) for p in h_preds]
+        d_outb = [torch.empty_like(y, device=device) for y in h_y]
+        s_up, s_dn = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+
+        def link_step():
+            with torch.cuda.stream(s_up):
+                for d, h in zip(d_in, h_preds):
+                    d.copy_(h, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                for h, d in zip(h_y, d_outb):
+                    h.copy_(d, non_blocking=True)
+        link_step()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            link_step()
+        torch.cuda.synchronize()
+        dt_link = (time.perf_counter() - t1) / args.e2e_steps
+        del d_in, d_outb
         te = torch.tensor([dt], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -408,6 +431,12 @@ def run_b200(args):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "batch": Be, "steps": args.e2e_steps,
                "detections_last_step": int(res["counts"].sum()),
+               "pcie": {"bound": "pcie", "bidirectional_copy_ms": dt_link * 1e3,
+                        "achieved_gbs": (h2d + d2h) / (dt / args.e2e_steps) / 1e9,
+                        "peak_gbs": (h2d + d2h) / dt_link / 1e9,
+                        "frac": dt_link / (dt / args.e2e_steps),
+                        "note": "peak = the same bytes as two bare bulk copies (H2D || D2H) on this "
+                                "box, measured right after; rank 0's link"},
                "note": "pinned host buffers; encode and decode calls issued concurrently from two "
                        "host threads (both PCIe directions busy); host<->device copies inside"}
         pool.shutdown()
