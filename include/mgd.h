@@ -220,6 +220,45 @@ MGD_API int mgd_soft_nms(const double *boxes, const double *scores, int n, doubl
                  int memory, int device, void *stream, int flags);
 
 /*
+ * Detection-to-ground-truth matching for mAP: TP / FP flags of every detection at
+ * several IoU thresholds.  Replaces match_predictions_to_gt_cached and
+ * match_predictions_to_gt (multigriddet/evaluation/metrics.py:147-218, 73-144) with the
+ * IoU they consume (calculate_iou_matrix :28-70; BoxUtils.box_iou utils/boxes.py:16-58),
+ * called per (class, threshold) from calculate_map (:541-815).  Ground truth is only
+ * shared inside one (image, class) group, so images are matched independently.
+ *
+ *   det_boxes (batch, max_dets, 4) float64, det_scores (batch, max_dets) float64,
+ *   det_classes (batch, max_dets) int32, det_counts (batch,) int32 -- the padded layout
+ *   mgd_decode_nms emits;  gt_boxes (batch, max_gt, 4) float64, gt_classes (batch, max_gt)
+ *   int32, gt_counts (batch,) int32;  iou_thresholds: num_thresholds host doubles.
+ *   iou_mode  MGD_IOU_CORNER: boxes are xyxy, a ground truth is a candidate only if its
+ *             IoU beats 0 (the cached matcher, the default path of calculate_map);
+ *             MGD_IOU_CENTRE: the four numbers are read as [x, y, w, h] centre format and
+ *             the first maximum wins even at IoU 0 (the un-cached matcher, which the
+ *             reference uses for > 10000 predictions and for the per-scale APs).
+ *   tp         (num_thresholds, batch, max_dets) uint8: 1 = true positive, 0 = false
+ *              positive (padding slots 0), in detection-slot order
+ *   matched_gt (num_thresholds, batch, max_dets) int32 or NULL: index of the claimed
+ *              ground truth, -1 for false positives
+ * Detections of an image are visited in descending score; equal scores: later slot first
+ * (np.argsort(scores)[::-1] of a stable sort).
+ */
+enum { MGD_IOU_CORNER = 0, MGD_IOU_CENTRE = 1 };
+MGD_API int mgd_match_detections(const double *det_boxes, const double *det_scores,
+                         const int *det_classes, const int *det_counts, int batch, int max_dets,
+                         const double *gt_boxes, const int *gt_classes, const int *gt_counts,
+                         int max_gt, const double *iou_thresholds, int num_thresholds,
+                         int iou_mode, unsigned char *tp, int *matched_gt,
+                         int memory, int device, void *stream, int flags);
+
+/*
+ * IoU matrix of two sets of xyxy boxes.  Replaces calculate_iou_matrix
+ * (multigriddet/evaluation/metrics.py:28-70).  out (n, m) float64.
+ */
+MGD_API int mgd_iou_matrix(const double *boxes1, int n, const double *boxes2, int m, double *out,
+                   int memory, int device, void *stream, int flags);
+
+/*
  * Deferred device-side status of asynchronous calls issued by this thread on
  * `device` (class-range errors found by the encode kernel).  Synchronises `stream`.
  */

@@ -1132,6 +1132,124 @@ int mgd_soft_nms(const double* boxes, const double* scores, int n, double sigma,
     return MGD_OK;
 }
 
+int mgd_match_detections(const double* det_boxes, const double* det_scores, const int* det_classes,
+                         const int* det_counts, int batch, int max_dets, const double* gt_boxes,
+                         const int* gt_classes, const int* gt_counts, int max_gt,
+                         const double* iou_thresholds, int num_thresholds, int iou_mode,
+                         unsigned char* tp, int* matched_gt, int memory, int device, void* stream,
+                         int flags)
+{
+    int rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (batch < 0 || max_dets < 0 || max_gt < 0)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "batch, max_dets and max_gt must be >= 0");
+    if (num_thresholds < 1 || num_thresholds > MGD_MAX_IOU_THRESHOLDS || !iou_thresholds)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "num_thresholds must be in [1, %d]", MGD_MAX_IOU_THRESHOLDS);
+    if (iou_mode != MGD_IOU_CORNER && iou_mode != MGD_IOU_CENTRE)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "iou_mode must be MGD_IOU_CORNER or MGD_IOU_CENTRE");
+    if (max_dets > 65535) return fail(MGD_ERR_UNSUPPORTED, "max_dets per image must be <= 65535");
+    if ((size_t)max_dets * 2 + (size_t)max_gt / 8 > 48 * 1024)
+        return fail(MGD_ERR_UNSUPPORTED, "max_dets / max_gt too large for one warp's shared memory");
+    if (batch > 0 && (!det_counts || !gt_counts || !tp))
+        return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    if ((long long)batch * max_dets > 0 && (!det_boxes || !det_scores || !det_classes))
+        return fail(MGD_ERR_INVALID_ARGUMENT, "NULL detection tensor");
+    if ((long long)batch * max_gt > 0 && (!gt_boxes || !gt_classes))
+        return fail(MGD_ERR_INVALID_ARGUMENT, "NULL ground-truth tensor");
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    if (batch == 0) return MGD_OK;
+    const bool host = memory == MGD_MEM_HOST;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (host) {
+        cudaStream_t* ss;
+        if ((rc = host_streams(device, &ss, nullptr))) return rc;
+        st = ss[0];
+    }
+    MatchArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = batch; a.M = max_dets; a.N = max_gt; a.T = num_thresholds; a.mode = iou_mode;
+    for (int t = 0; t < num_thresholds; ++t) a.thr[t] = iou_thresholds[t];
+    const size_t nd = (size_t)batch * max_dets, ng = (size_t)batch * max_gt;
+    const size_t n_out = (size_t)num_thresholds * nd;
+    // staging (host memory) / scratch: one block, 8-byte fields first
+    const size_t off_dsc = nd * 32, off_gbox = off_dsc + nd * 8, off_who = off_gbox + ng * 32;
+    const size_t off_dcl = off_who + n_out * 4, off_gcl = off_dcl + nd * 4, off_dcn = off_gcl + ng * 4;
+    const size_t off_gcn = off_dcn + (size_t)batch * 4, off_ctr = off_gcn + (size_t)batch * 4;
+    const size_t off_tp = off_ctr + 16, total = off_tp + n_out;
+    unsigned char* buf;
+    CUDA_TRY(pool_malloc(&buf, host ? total : 64, st));
+    int* d_ctr = reinterpret_cast<int*>(host ? buf + off_ctr : buf);
+    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(int), st));
+    if (host) {
+        auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+            return bytes ? cudaMemcpyAsync(buf + off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+        };
+        CUDA_TRY(up(0, det_boxes, nd * 32));
+        CUDA_TRY(up(off_dsc, det_scores, nd * 8));
+        CUDA_TRY(up(off_gbox, gt_boxes, ng * 32));
+        CUDA_TRY(up(off_dcl, det_classes, nd * 4));
+        CUDA_TRY(up(off_gcl, gt_classes, ng * 4));
+        CUDA_TRY(up(off_dcn, det_counts, (size_t)batch * 4));
+        CUDA_TRY(up(off_gcn, gt_counts, (size_t)batch * 4));
+        a.det_boxes = reinterpret_cast<const double*>(buf);
+        a.det_scores = reinterpret_cast<const double*>(buf + off_dsc);
+        a.gt_boxes = reinterpret_cast<const double*>(buf + off_gbox);
+        a.det_classes = reinterpret_cast<const int*>(buf + off_dcl);
+        a.gt_classes = reinterpret_cast<const int*>(buf + off_gcl);
+        a.det_counts = reinterpret_cast<const int*>(buf + off_dcn);
+        a.gt_counts = reinterpret_cast<const int*>(buf + off_gcn);
+        a.tp = buf + off_tp;
+        a.matched = matched_gt ? reinterpret_cast<int*>(buf + off_who) : nullptr;
+    } else {
+        a.det_boxes = det_boxes; a.det_scores = det_scores; a.det_classes = det_classes;
+        a.det_counts = det_counts; a.gt_boxes = gt_boxes; a.gt_classes = gt_classes;
+        a.gt_counts = gt_counts; a.tp = tp; a.matched = matched_gt;
+    }
+    a.next_image = d_ctr;
+    CUDA_TRY(launch_match(a, num_sms, st));
+    if (host) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (n_out) CUDA_TRY(cudaMemcpy(tp, buf + off_tp, n_out, cudaMemcpyDeviceToHost));
+        if (matched_gt && n_out) CUDA_TRY(cudaMemcpy(matched_gt, buf + off_who, n_out * 4, cudaMemcpyDeviceToHost));
+    }
+    CUDA_TRY(cudaFreeAsync(buf, st));
+    if (!host && (flags & MGD_FLAG_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
+    return MGD_OK;
+}
+
+int mgd_iou_matrix(const double* boxes1, int n, const double* boxes2, int m, double* out, int memory,
+                   int device, void* stream, int flags)
+{
+    int rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (n < 0 || m < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n and m must be >= 0");
+    if ((long long)n * m > 0 && (!boxes1 || !boxes2 || !out)) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    if ((long long)n * m == 0) return MGD_OK;
+    const bool host = memory == MGD_MEM_HOST;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!host) {
+        CUDA_TRY(launch_iou_matrix(boxes1, n, boxes2, m, out, st));
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    cudaStream_t* ss;
+    if ((rc = host_streams(device, &ss, nullptr))) return rc;
+    st = ss[0];
+    double* buf;
+    const size_t nn = (size_t)n * 4, mm = (size_t)m * 4, oo = (size_t)n * m;
+    CUDA_TRY(pool_malloc(&buf, (nn + mm + oo) * 8, st));
+    CUDA_TRY(cudaMemcpyAsync(buf, boxes1, nn * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(buf + nn, boxes2, mm * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(launch_iou_matrix(buf, n, buf + nn, m, buf + nn + mm, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaMemcpy(out, buf + nn + mm, oo * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFreeAsync(buf, st));
+    return MGD_OK;
+}
+
 }  // extern "C"
 
 // ---- DLPack adapters ---------------------------------------------------------------

@@ -105,6 +105,25 @@ struct NmsArgs {
     unsigned long long* stats;        // [candidates, detections]
 };
 
+// ---- mAP matching -----------------------------------------------------------
+#define MGD_MAX_IOU_THRESHOLDS 16
+struct MatchArgs {
+    int B, M, N, T;
+    const double* det_boxes;          // (B, M, 4)
+    const double* det_scores;         // (B, M)
+    const int* det_classes;           // (B, M)
+    const int* det_counts;            // (B,)
+    const double* gt_boxes;           // (B, N, 4)
+    const int* gt_classes;            // (B, N)
+    const int* gt_counts;             // (B,)
+    double thr[MGD_MAX_IOU_THRESHOLDS];
+    int mode;                         // 0: corner IoU, candidate must beat 0 (cached matcher);
+                                      // 1: centre-format IoU, first maximum (un-cached matcher)
+    unsigned char* tp;                // (T, B, M)
+    int* matched;                     // (T, B, M) or nullptr
+    int* next_image;                  // work counter, zeroed by the caller
+};
+
 // per-kernel CUDA-event timing (mgd_profile_begin / mgd_profile_end)
 enum ProfKind { PROF_ENCODE_ASSIGN = 0, PROF_ENCODE_FILL = 1, PROF_DECODE_COMPACT = 2,
                 PROF_NMS = 3, PROF_OTHER = 4, PROF_KINDS = 5 };
@@ -121,5 +140,8 @@ int nms_smem_capacity();
 size_t nms_kept_bytes(int max_boxes);
 cudaError_t launch_decode_dense(const DecodeArgs& a, const int* image_hw, double* out,
                                 cudaStream_t stream);
+cudaError_t launch_match(const MatchArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_iou_matrix(const double* b1, int n, const double* b2, int m, double* out,
+                              cudaStream_t stream);
 cudaError_t launch_keep_from_index(const int* index, const int* counts, int max_keep, int* keep,
                                    int* n_keep, cudaStream_t stream);

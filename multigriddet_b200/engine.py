@@ -349,3 +349,67 @@ def profile_end():
     n = (ctypes.c_longlong * len(PROFILE_KINDS))()
     _lib.raise_for_status(_lib.load().mgd_profile_end(ms, n))
     return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(PROFILE_KINDS)}
+
+
+# ------------------------------------------------------------------------------
+# mAP matching (reference multigriddet/evaluation/metrics.py)
+# ------------------------------------------------------------------------------
+
+def match_detections(det_boxes, det_scores, det_classes, det_counts, gt_boxes, gt_classes, gt_counts,
+                     iou_thresholds, iou_mode="corner", return_matched=False, sync=True):
+    """TP flags of padded per-image detections against padded per-image ground truth
+    (``mgd_match_detections``).  NumPy arrays (host) or torch CUDA tensors (device).
+
+    det_boxes (B, M, 4), det_scores (B, M), det_classes (B, M), det_counts (B,),
+    gt_boxes (B, N, 4), gt_classes (B, N), gt_counts (B,).  Returns ``tp`` (T, B, M) uint8
+    (and ``matched_gt`` (T, B, M) int32 when asked) in the same memory space.
+    """
+    lib = _lib.load()
+    mode = {"corner": _lib.IOU_CORNER, "centre": _lib.IOU_CENTRE, "center": _lib.IOU_CENTRE}[iou_mode]
+    thr = np.ascontiguousarray(np.asarray(iou_thresholds, dtype=np.float64).reshape(-1))
+    T = int(thr.shape[0])
+    thr_p = thr.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    if _is_torch(det_boxes):
+        import torch
+        dev = det_boxes.device
+        f64 = lambda x: x.to(device=dev, dtype=torch.float64).contiguous()
+        i32 = lambda x: x.to(device=dev, dtype=torch.int32).contiguous()
+        db, ds, dc, dn = f64(det_boxes), f64(det_scores), i32(det_classes), i32(det_counts)
+        gb, gc, gn = f64(gt_boxes), i32(gt_classes), i32(gt_counts)
+        B, M, N = int(ds.shape[0]), int(ds.shape[1]), int(gc.shape[1])
+        tp = torch.empty((T, B, M), dtype=torch.uint8, device=dev)
+        who = torch.empty((T, B, M), dtype=torch.int32, device=dev) if return_matched else None
+        p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None and x.numel() else None
+        idx = dev.index or 0
+        rc = lib.mgd_match_detections(p(db), p(ds), p(dc), p(dn), B, M, p(gb), p(gc), p(gn), N, thr_p, T,
+                                      mode, p(tp), p(who), _lib.MEM_DEVICE, idx,
+                                      ctypes.c_void_p(_torch_stream(idx)), _lib.FLAG_SYNC if sync else 0)
+    else:
+        f64 = lambda x: np.ascontiguousarray(np.asarray(x), dtype=np.float64)
+        i32 = lambda x: np.ascontiguousarray(np.asarray(x), dtype=np.int32)
+        db, ds, dc, dn = f64(det_boxes), f64(det_scores), i32(det_classes), i32(det_counts)
+        gb, gc, gn = f64(gt_boxes), i32(gt_classes), i32(gt_counts)
+        B, M, N = ds.shape[0], ds.shape[1], gc.shape[1]
+        tp = np.zeros((T, B, M), dtype=np.uint8)
+        who = np.full((T, B, M), -1, dtype=np.int32) if return_matched else None
+        p = lambda x: ctypes.c_void_p(x.ctypes.data) if x is not None and x.size else None
+        rc = lib.mgd_match_detections(p(db), p(ds), p(dc), p(dn), B, M, p(gb), p(gc), p(gn), N, thr_p, T,
+                                      mode, p(tp), p(who), _lib.MEM_HOST, _current_device(), None,
+                                      _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    return (tp, who) if return_matched else tp
+
+
+def iou_matrix(boxes1, boxes2):
+    """(n, m) float64 IoU matrix of xyxy boxes (``mgd_iou_matrix``), NumPy in / out."""
+    lib = _lib.load()
+    b1 = np.ascontiguousarray(np.asarray(boxes1, dtype=np.float64).reshape(-1, 4))
+    b2 = np.ascontiguousarray(np.asarray(boxes2, dtype=np.float64).reshape(-1, 4))
+    out = np.zeros((b1.shape[0], b2.shape[0]), dtype=np.float64)
+    if out.size:
+        rc = lib.mgd_iou_matrix(ctypes.c_void_p(b1.ctypes.data), b1.shape[0],
+                                ctypes.c_void_p(b2.ctypes.data), b2.shape[0],
+                                ctypes.c_void_p(out.ctypes.data), _lib.MEM_HOST, _current_device(),
+                                None, _lib.FLAG_SYNC)
+        _lib.raise_for_status(rc)
+    return out

@@ -174,12 +174,83 @@ def nms_cases():
     print("nms cases written")
 
 
+def synth_eval_set(seed, B, M, N, C, ties=False):
+    """Padded detections / ground truth shaped like an evaluation run: detections are
+    jittered copies of ground-truth boxes (int32 xyxy like _convert_to_xyxy emits) with
+    mostly-correct classes, ground truth is float xyxy."""
+    rng = np.random.default_rng(seed)
+    gtb = np.zeros((B, N, 4)); gtc = np.zeros((B, N), np.int32); gtn = rng.integers(0, N + 1, B).astype(np.int32)
+    db = np.zeros((B, M, 4)); ds = np.zeros((B, M)); dc = np.zeros((B, M), np.int32)
+    dn = rng.integers(0, M + 1, B).astype(np.int32)
+    for b in range(B):
+        xy = rng.uniform(0, 400, (N, 2)); wh = np.exp(rng.normal(np.log(60), 0.9, (N, 2))).clip(6, 300)
+        gtb[b] = np.concatenate([xy, xy + wh], 1)
+        gtc[b] = rng.integers(0, C, N)
+        for i in range(M):
+            j = int(rng.integers(0, N))
+            db[b, i] = np.round(gtb[b, j] + rng.normal(0, 0.12, 4) * np.tile(wh[j], 2))
+            dc[b, i] = gtc[b, j] if rng.random() < 0.8 else rng.integers(0, C)
+        ds[b] = np.round(rng.uniform(0.05, 1, M), 2) if ties else rng.uniform(0.001, 1, M)
+    return db, ds, dc, dn, gtb, gtc, gtn
+
+
+def metrics_cases():
+    """tests/golden/metrics_cases.npz: the reference's matcher flags, APs and calculate_map
+    results (multigriddet/evaluation/metrics.py) on synthetic evaluation sets."""
+    import contextlib, io
+    from oracle import metrics_oracle as MO
+    M = ref_loader.load_metrics()
+    store = {}
+    thr = [0.5, 0.55, 0.6, 0.65, 0.7, 0.75, 0.8, 0.85, 0.9, 0.95]
+    cases = [("a", 1, 12, 40, 15, 5, False), ("b", 2, 5, 100, 30, 3, False), ("ties", 3, 8, 12, 6, 2, True)]
+    store["names"] = np.array([c[0] for c in cases])
+    store["thresholds"] = np.array(thr)
+    for name, seed, B, Mx, N, C, ties in cases:
+        db, ds, dc, dn, gtb, gtc, gtn = synth_eval_set(seed, B, Mx, N, C, ties)
+        preds, gts = MO.to_dicts(db.astype(np.int32), ds, dc, dn, gtb, gtc, gtn)
+        for k, v in (("db", db), ("ds", ds), ("dc", dc), ("dn", dn), ("gtb", gtb), ("gtc", gtc), ("gtn", gtn)):
+            store[f"{name}_{k}"] = v
+        store[f"{name}_C"] = np.array(C)
+        for cached in (True, False):
+            tag = "cached" if cached else "plain"
+            for c in range(C):
+                cp = [p for p in preds if p["class"] == c]
+                cg = [g for g in gts if g["class"] == c]
+                cache = M.compute_iou_cache_for_class(preds, gts, c) if cached else None
+                for t, th in enumerate(thr):
+                    if cp:
+                        r = (M.match_predictions_to_gt_cached(cp, cg, th, cache) if cached
+                             else M.match_predictions_to_gt(cp, cg, th))
+                        store[f"{name}_{tag}_c{c}_t{t}_tp"] = np.asarray(r[0], bool)
+                        store[f"{name}_{tag}_c{c}_t{t}_scores"] = np.asarray(r[2], np.float64)
+                    ap = (M.calculate_ap_for_class_cached(preds, gts, c, th, cache) if cached
+                          else M.calculate_ap_for_class(preds, gts, c, th))
+                    store[f"{name}_{tag}_c{c}_t{t}_ap"] = np.array(float(ap))
+            with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+                res = M.calculate_map(preds, gts, C, use_parallel=False, cache_ious=cached)
+                res_voc = M.calculate_map(preds, gts, C, iou_thresholds=[0.5], method="voc",
+                                          use_parallel=False, cache_ious=cached, compute_per_scale=False)
+            for key in ("mAP", "mAP50", "mAP75", "APS", "APM", "APL", "APS50", "APM50", "APL50"):
+                store[f"{name}_{tag}_map_{key}"] = np.array(float(res[key]))
+            store[f"{name}_{tag}_map_voc50"] = np.array(float(res_voc["mAP50"]))
+            print("metrics", name, tag, {k: round(float(res[k]), 4) for k in ("mAP", "mAP50", "APS", "APM", "APL")})
+        n1, n2 = int(dn[0]), int(gtn[0])
+        store[f"{name}_ioumat"] = M.calculate_iou_matrix(db[0, :max(n1, 1)], gtb[0, :max(n2, 1)])
+    np.savez_compressed(os.path.join(OUT, "metrics_cases.npz"), **store)
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found at " + ref_loader.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
-    encode_cases()
-    decode_cases()
-    nms_cases()
+    only = sys.argv[1:] or ["encode", "decode", "nms", "metrics"]
+    if "encode" in only:
+        encode_cases()
+    if "decode" in only:
+        decode_cases()
+    if "nms" in only:
+        nms_cases()
+    if "metrics" in only:
+        metrics_cases()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {total / 1e6:.2f} MB in {OUT}")

@@ -119,3 +119,29 @@ def load_postprocess():
         WeightedBoxesFusion=names["wbf"].WeightedBoxesFusion)
     _cache["post"] = ns
     return ns
+
+
+def load_metrics():
+    """Return the reference's ``multigriddet/evaluation/metrics.py`` module (pure NumPy /
+    Python; its ``..utils.boxes`` import needs the stub ``tensorflow`` only at import)."""
+    if "metrics" in _cache:
+        return _cache["metrics"]
+    if "tensorflow" not in sys.modules:
+        sys.modules["tensorflow"] = types.ModuleType("tensorflow")
+    pkg_root = os.path.join(REFERENCE_ROOT, "multigriddet")
+    for pkg, sub in (("_mgd_ref", pkg_root), ("_mgd_ref.utils", os.path.join(pkg_root, "utils")),
+                     ("_mgd_ref.evaluation", os.path.join(pkg_root, "evaluation"))):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = [sub]
+            sys.modules[pkg] = m
+    out = None
+    for full, rel in (("_mgd_ref.utils.boxes", ("utils", "boxes.py")),
+                      ("_mgd_ref.evaluation.metrics", ("evaluation", "metrics.py"))):
+        spec = importlib.util.spec_from_file_location(full, os.path.join(pkg_root, *rel))
+        module = importlib.util.module_from_spec(spec)
+        sys.modules[full] = module
+        spec.loader.exec_module(module)
+        out = module
+    _cache["metrics"] = out
+    return out
