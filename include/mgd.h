@@ -265,6 +265,24 @@ MGD_API int mgd_iou_matrix(const double *boxes1, int n, const double *boxes2, in
 MGD_API int mgd_poll_status(int device, void *stream);
 
 /*
+ * Page-locked host memory for tensors that cross the boundary as MGD_MEM_HOST.  The
+ * reference returns fresh NumPy arrays from every call (generators.py:3425-3429,
+ * multigrid_decode.py:409-422); arrays in pageable memory move at ~6-11 GB/s through the
+ * driver's bounce buffer, page-locked ones at the link rate (~55 GB/s), so the Python
+ * shim allocates its outputs here and recycles them.  Portable across CUDA contexts.
+ */
+#include <stddef.h>
+MGD_API int mgd_host_alloc(size_t bytes, void **ptr);
+MGD_API int mgd_host_free(void *ptr);
+
+/*
+ * Host-memory calls stage through device buffers cached per (host thread, device); this
+ * returns the calling thread's cached buffers to the driver.  Optional: they are reused
+ * by the thread's next call and sized by the largest batch chunk (<= ~0.5 GB).
+ */
+MGD_API int mgd_release_workspace(void);
+
+/*
  * Per-kernel timing for the calling thread (observability; the reference only has
  * wall-clock prints, evaluator.py:496-525).  Between begin and end every kernel
  * the library launches for this thread is bracketed by CUDA events on the

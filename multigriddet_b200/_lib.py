@@ -69,7 +69,8 @@ _LLP = ctypes.POINTER(ctypes.c_longlong)
 EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targets",
            "mgd_decode_nms", "mgd_decode_dense", "mgd_nms", "mgd_soft_nms", "mgd_wbf", "mgd_poll_status",
            "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack", "mgd_profile_begin",
-           "mgd_profile_end", "mgd_match_detections", "mgd_iou_matrix")
+           "mgd_profile_end", "mgd_match_detections", "mgd_iou_matrix", "mgd_host_alloc",
+           "mgd_host_free", "mgd_release_workspace")
 
 
 def load():
@@ -138,6 +139,11 @@ def load():
     lib.mgd_iou_matrix.argtypes = [
         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
         ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.mgd_host_alloc.restype = ctypes.c_int
+    lib.mgd_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+    lib.mgd_host_free.restype = ctypes.c_int
+    lib.mgd_host_free.argtypes = [ctypes.c_void_p]
+    lib.mgd_release_workspace.restype = ctypes.c_int
     lib.mgd_profile_begin.restype = ctypes.c_int
     lib.mgd_profile_end.restype = ctypes.c_int
     lib.mgd_profile_end.argtypes = [_DP, _LLP]
@@ -190,3 +196,74 @@ def make_head_config(anchors, num_classes, input_shape, grid_shapes=None) -> Hea
 
 def ptr_array(ptrs):
     return (ctypes.c_void_p * len(ptrs))(*[ctypes.c_void_p(int(p)) for p in ptrs])
+
+
+class PinnedPool:
+    """Recycling allocator of page-locked NumPy arrays (``mgd_host_alloc``).
+
+    ``empty(shape, dtype)`` returns an ordinary ndarray whose memory is page-locked; when
+    the array (and every view of it) is garbage collected the block goes back to the
+    pool and is handed to the next request of the same size, so a training / evaluation
+    loop that drops its previous batch allocates nothing in steady state.  The pool never
+    holds more than ``cap_bytes`` of page-locked memory in total (in use + idle; env
+    ``MGD_PINNED_CAP_MB``, default 4096): a caller that keeps every result alive gets
+    pageable ``np.empty`` arrays once the cap is reached, as does a host without a GPU.
+    """
+
+    def __init__(self, cap_bytes=None):
+        import threading
+        if cap_bytes is None:
+            cap_bytes = int(os.environ.get("MGD_PINNED_CAP_MB", "4096")) << 20
+        self._lock = threading.Lock()
+        self._free = {}
+        self._idle = 0
+        self._total = 0
+        self.cap_bytes = cap_bytes
+
+    def _give_back(self, ptr, nbytes):
+        with self._lock:
+            self._free.setdefault(nbytes, []).append(ptr)
+            self._idle += nbytes
+
+    def _trim(self, need):
+        """Free idle blocks (largest first) until ``need`` more bytes fit under the cap."""
+        victims = []
+        with self._lock:
+            for size in sorted(self._free, reverse=True):
+                lst = self._free[size]
+                while lst and self._total + need > self.cap_bytes:
+                    victims.append(lst.pop())
+                    self._idle -= size
+                    self._total -= size
+        for ptr in victims:
+            load().mgd_host_free(ctypes.c_void_p(ptr))
+
+    def empty(self, shape, dtype):
+        import weakref
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        if nbytes < (1 << 16):                    # tiny arrays: not worth a page-locked block
+            return np.empty(shape, dtype)
+        ptr = None
+        with self._lock:
+            lst = self._free.get(nbytes)
+            if lst:
+                ptr = lst.pop()
+                self._idle -= nbytes
+        if ptr is None:
+            if self._total + nbytes > self.cap_bytes:
+                self._trim(nbytes)
+            if self._total + nbytes > self.cap_bytes:
+                return np.empty(shape, dtype)
+            out = ctypes.c_void_p()
+            if load().mgd_host_alloc(nbytes, ctypes.byref(out)) != OK or not out.value:
+                return np.empty(shape, dtype)
+            ptr = out.value
+            with self._lock:
+                self._total += nbytes
+        buf = (ctypes.c_char * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._give_back, ptr, nbytes)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+pinned = PinnedPool()

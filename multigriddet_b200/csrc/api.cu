@@ -9,6 +9,7 @@
 #include <chrono>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -487,6 +488,13 @@ struct HostStreams {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     Arena chunk[2];          // staging + scratch of the chunk in flight on s[i]
     Arena call;              // per-call tensors (boxes, output slab, status words)
+    // page-locked bounce buffers for PAGEABLE caller memory: the driver's own pageable
+    // path is one memcpy thread (~11 GB/s); several threads filling a page-locked chunk
+    // while the previous chunk is on the link reach ~3x that
+    unsigned char* bounce[2] = {nullptr, nullptr};
+    size_t bounce_cap[2] = {0, 0};
+    cudaEvent_t bounce_done[2] = {nullptr, nullptr};
+    bool bounce_busy[2] = {false, false};
 };
 thread_local HostStreams t_streams[64];
 
@@ -500,6 +508,61 @@ int host_streams(int device, cudaStream_t** out, cudaEvent_t** ev, HostStreams**
     }
     *out = hs.s;
     if (ev) *ev = hs.ev;
+    return MGD_OK;
+}
+
+// true when the driver knows nothing about p: ordinary pageable host memory
+bool is_pageable(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+int host_copy_threads()
+{
+    static int n = -1;
+    if (n < 0) {
+        const char* e = getenv("MGD_HOST_COPY_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        n = e ? atoi(e) : (hw >= 32 ? 8 : (hw >= 8 ? hw / 4 : 2));   // a quarter of the cores, 2..8
+        if (hw > 0 && n > hw) n = hw;
+        if (n < 1) n = 1;
+    }
+    return n;
+}
+
+void parallel_copy(void* dst, const void* src, size_t bytes)
+{
+    const int n = bytes < (8u << 20) ? 1 : host_copy_threads();
+    if (n == 1) { memcpy(dst, src, bytes); return; }
+    const size_t part = ((bytes / n) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> workers;
+    for (int i = 1; i < n; ++i) {
+        const size_t off = (size_t)i * part;
+        if (off >= bytes) break;
+        const size_t len = off + part < bytes ? part : bytes - off;
+        workers.emplace_back([=] { memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+    }
+    memcpy(dst, src, part < bytes ? part : bytes);
+    for (std::thread& t : workers) t.join();
+}
+
+// page-locked bounce slot of at least `bytes`, idle (its previous H2D has completed)
+int bounce_slot(HostStreams* hs, int slot, size_t bytes, unsigned char** out)
+{
+    if (hs->bounce_busy[slot]) {
+        CUDA_TRY(cudaEventSynchronize(hs->bounce_done[slot]));
+        hs->bounce_busy[slot] = false;
+    }
+    if (hs->bounce_cap[slot] < bytes) {
+        if (hs->bounce[slot]) CUDA_TRY(cudaFreeHost(hs->bounce[slot]));
+        hs->bounce[slot] = nullptr; hs->bounce_cap[slot] = 0;
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&hs->bounce[slot]), bytes, cudaHostAllocPortable));
+        hs->bounce_cap[slot] = bytes;
+    }
+    if (!hs->bounce_done[slot]) CUDA_TRY(cudaEventCreateWithFlags(&hs->bounce_done[slot], cudaEventDisableTiming));
+    *out = hs->bounce[slot];
     return MGD_OK;
 }
 
@@ -555,6 +618,44 @@ int mgd_version(void) { return MGD_VERSION; }
 const char* mgd_last_error(void) { return t_error.c_str(); }
 
 int mgd_device_count(void) { return device_count_quiet(); }
+
+int mgd_host_alloc(size_t bytes, void** ptr)
+{
+    if (!ptr) return fail(MGD_ERR_INVALID_ARGUMENT, "ptr is NULL");
+    *ptr = nullptr;
+    if (device_count_quiet() == 0)
+        return fail(MGD_ERR_NO_DEVICE, "no CUDA device: page-locked memory is not available");
+    CUDA_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return MGD_OK;
+}
+
+int mgd_host_free(void* ptr)
+{
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return MGD_OK;
+}
+
+int mgd_release_workspace(void)
+{
+    // staging arenas of the calling thread (host-memory entry points), all devices
+    int cur = 0;
+    const bool have = cudaGetDevice(&cur) == cudaSuccess;
+    for (int d = 0; d < 64; ++d) {
+        HostStreams& hs = t_streams[d];
+        if (hs.chunk[0].blocks.empty() && hs.chunk[1].blocks.empty() && hs.call.blocks.empty() &&
+            !hs.bounce[0] && !hs.bounce[1]) continue;
+        if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+        for (int i = 0; i < 2; ++i) if (hs.s[i]) cudaStreamSynchronize(hs.s[i]);
+        hs.chunk[0].release(); hs.chunk[1].release(); hs.call.release();
+        for (int i = 0; i < 2; ++i) {
+            if (hs.bounce[i]) cudaFreeHost(hs.bounce[i]);
+            hs.bounce[i] = nullptr; hs.bounce_cap[i] = 0; hs.bounce_busy[i] = false;
+        }
+    }
+    if (have) cudaSetDevice(cur);
+    cudaGetLastError();
+    return MGD_OK;
+}
 
 int mgd_profile_begin(void)
 {
@@ -801,6 +902,10 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
         zero_copy = z_pred[l] != nullptr;
     }
     // (still chunked: kernels of other calls get onto the SMs between the chunks)
+    // pageable predictions: bounce through page-locked chunks filled by several threads
+    bool pageable = !zero_copy && host_copy_threads() > 1 &&
+                    (size_t)batch * g.cells * g.D[0] * 4 >= (32u << 20);
+    for (int l = 0; l < g.L && pageable; ++l) pageable = is_pageable(preds[l]);
     int k = 0;
     for (int b0 = 0; b0 < batch; b0 += step, ++k) {
         const int nb = batch - b0 < step ? batch - b0 : step;
@@ -808,12 +913,29 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
         Arena& ar = hs->chunk[k & 1];
         ar.reset();
         float* d_pred[MGD_MAX_LAYERS];
+        unsigned char* bounce = nullptr;
+        size_t bounce_off = 0;
+        if (pageable) {
+            size_t need = 0;
+            for (int l = 0; l < g.L; ++l) need += (((size_t)nb * g.gh[l] * g.gw[l] * g.D[l] * 4) + 255) & ~(size_t)255;
+            if ((rc = bounce_slot(hs, k & 1, need, &bounce))) return rc;
+        }
         for (int l = 0; l < g.L; ++l) {
             const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
             if (zero_copy) { d_pred[l] = const_cast<float*>(z_pred[l]) + (size_t)b0 * per; continue; }
-            CUDA_TRY(ar.take(reinterpret_cast<void**>(&d_pred[l]), (size_t)nb * per * 4));
-            CUDA_TRY(cudaMemcpyAsync(d_pred[l], preds[l] + (size_t)b0 * per, (size_t)nb * per * 4,
-                                     cudaMemcpyHostToDevice, st));
+            const size_t bytes = (size_t)nb * per * 4;
+            CUDA_TRY(ar.take(reinterpret_cast<void**>(&d_pred[l]), bytes));
+            const void* src = preds[l] + (size_t)b0 * per;
+            if (bounce) {
+                parallel_copy(bounce + bounce_off, src, bytes);
+                src = bounce + bounce_off;
+                bounce_off += (bytes + 255) & ~(size_t)255;
+            }
+            CUDA_TRY(cudaMemcpyAsync(d_pred[l], src, bytes, cudaMemcpyHostToDevice, st));
+        }
+        if (bounce) {
+            CUDA_TRY(cudaEventRecord(hs->bounce_done[k & 1], st));
+            hs->bounce_busy[k & 1] = true;
         }
         rc = decode_nms_device(g, *post, d_pred, nb, d_hw ? d_hw + 2 * (size_t)b0 : nullptr,
                                reinterpret_cast<double*>(d_out + off_xywh) + (size_t)b0 * M * 4,

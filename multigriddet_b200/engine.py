@@ -108,8 +108,10 @@ def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=No
             raise ValueError(f"true_boxes must be (B, N, 5), got {boxes.shape}")
         B, N = boxes.shape[0], boxes.shape[1]
         if out is None:
-            out = [np.empty((B, cfg.grid_h[l], cfg.grid_w[l], 5 + cfg.num_anchors[l] + cfg.num_classes),
-                            dtype=np.float32) for l in range(L)]
+            # page-locked, recycled: pageable outputs crawl through the driver's bounce buffer
+            out = [_lib.pinned.empty((B, cfg.grid_h[l], cfg.grid_w[l],
+                                      5 + cfg.num_anchors[l] + cfg.num_classes), np.float32)
+                   for l in range(L)]
         ptrs = _lib.ptr_array([o.ctypes.data for o in out])
         rc = lib.mgd_encode_targets(ctypes.byref(cfg), ctypes.c_void_p(boxes.ctypes.data), B, N,
                                     ptrs, _lib.MEM_HOST, _current_device(), None,
@@ -196,7 +198,7 @@ def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_
     else:
         npreds = [np.ascontiguousarray(np.asarray(p), dtype=np.float32) for p in preds]
         for k in want:
-            out[k] = np.empty(spec[k][0], dtype=spec[k][1])
+            out[k] = _lib.pinned.empty(spec[k][0], spec[k][1])
         out["counts"] = np.empty((B,), dtype=np.int32)
         addr = lambda k: ctypes.c_void_p(out[k].ctypes.data) if k in out else None
         rc = lib.mgd_decode_nms(

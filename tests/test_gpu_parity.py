@@ -548,3 +548,34 @@ def test_decode_equal_scores_follow_the_cell_index_rule(c_oracle):
     got = engine.decode_nms(const, (S2, S2), (S2, S2), anchors, C2, **kw)
     same, bits_off = _compare_detections(got, ref, 2)
     assert same == 2 and bits_off == 0
+
+
+def test_pinned_output_pool_recycles_and_respects_its_cap():
+    import gc
+    from multigriddet_b200 import _lib
+    pool = _lib.PinnedPool(cap_bytes=3 << 20)
+    a = pool.empty((1 << 18,), np.float32)            # 1 MiB page-locked
+    addr = a.ctypes.data
+    assert pool._total == 1 << 20 and pool._idle == 0
+    v = a[10:20]
+    del a; gc.collect()
+    assert pool._idle == 0                            # a view keeps the block alive
+    del v; gc.collect()
+    assert pool._idle == 1 << 20
+    b = pool.empty((1 << 18,), np.float32)
+    assert b.ctypes.data == addr and pool._idle == 0  # same block again
+    c = pool.empty((1 << 19,), np.float32)            # 2 MiB: fits under the 3 MiB cap
+    d = pool.empty((1 << 18,), np.float32)            # cap reached: pageable fallback
+    assert pool._total == 3 << 20 and d.flags["OWNDATA"]
+    del b; gc.collect()
+    e = pool.empty((1 << 19,), np.float32)            # idle 1 MiB block is trimmed, 2 MiB does not fit
+    assert e.flags["OWNDATA"] and pool._total == 2 << 20
+    del c, d, e
+    # the drop-in's fresh outputs come from the shared pool and are valid NumPy arrays
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(1, 8, 20, 416, 20)
+    y1 = engine.encode_targets(boxes, (416, 416), anchors, 20)
+    keep = [t.copy() for t in y1]
+    del y1; gc.collect()
+    y2 = engine.encode_targets(boxes, (416, 416), anchors, 20)
+    assert all(np.array_equal(p, q) for p, q in zip(keep, y2))

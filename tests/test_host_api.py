@@ -81,3 +81,14 @@ def test_synth_is_deterministic_and_tie_free():
     assert valid.any() and (a[valid][:, 4] < 80).all() and (a[..., :4] >= 0).all() and (a[..., :4] <= 608).all()
     shapes = synth.image_shapes(1, 16)
     assert shapes.shape == (16, 2) and shapes.dtype == np.int32
+
+
+def test_pinned_pool_hands_out_plain_arrays_without_a_gpu():
+    from multigriddet_b200 import _lib
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    pool = _lib.PinnedPool(cap_bytes=1 << 30)
+    a = pool.empty((512, 512), np.float32)           # mgd_host_alloc -> MGD_ERR_NO_DEVICE -> np.empty
+    assert a.shape == (512, 512) and a.dtype == np.float32 and pool._total == 0
+    a[:] = 1.0
