@@ -85,12 +85,42 @@ def gather_detections(local: Dict, dst: Optional[int] = None) -> Optional[Dict[s
     return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
 
 
+def gather_detections_device(local: Dict) -> Dict:
+    """Device-side gather: every rank ends with the whole batch's padded detection
+    tensors in ITS OWN device memory (one all-gather of <= 2.8 KB per image
+    over NVLink with the NCCL backend; CPU tensors with gloo).  ``local`` holds torch
+    tensors of this rank's shard; shards may differ by one image, so they are padded to
+    the largest shard for the collective and trimmed afterwards."""
+    import torch
+    d = _dist()
+    keys = [k for k, v in local.items() if hasattr(v, "detach") and not k.startswith("_")]
+    if d is None or d.get_world_size() == 1:
+        return {k: local[k] for k in keys}
+    ws = d.get_world_size()
+    n_local = int(local["counts"].shape[0])
+    sizes = torch.zeros(ws, dtype=torch.int64, device=local["counts"].device)
+    sizes[d.get_rank()] = n_local
+    d.all_reduce(sizes)
+    sizes = [int(v) for v in sizes.tolist()]
+    n_max = max(sizes)
+    out = {}
+    for k in keys:
+        t = local[k].contiguous()
+        if n_local < n_max:
+            pad = torch.zeros((n_max - n_local,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            t = torch.cat([t, pad], 0)
+        parts = [torch.empty_like(t) for _ in range(ws)]
+        d.all_gather(parts, t)
+        out[k] = torch.cat([p[:n] for p, n in zip(parts, sizes)], 0)
+    return out
+
+
 class ShardedGridPath:
     """Runs the hot path on this rank's slice of a global batch.
 
     ``encode`` returns the local ``y_true`` shard (never gathered); ``decode_nms``
-    returns the gathered detections of the whole batch (or the local ones with
-    ``gather=False``).  ``compute`` is injectable so the plumbing is testable on a
+    returns the gathered detections of the whole batch (host NumPy arrays; torch tensors
+    gathered device-to-device with ``gather="device"``; the local ones with ``gather=False``).  ``compute`` is injectable so the plumbing is testable on a
     CPU box (tests pass the oracle); by default it is ``multigriddet_b200.engine``.
     """
 
@@ -121,4 +151,6 @@ class ShardedGridPath:
             shapes = shapes[sl] if shapes.shape[0] == n else shapes
         det = self.compute.decode_nms([p[sl] for p in global_preds], shapes, self.input_shape,
                                       self.anchors, self.num_classes, **kw)
+        if gather == "device":
+            return gather_detections_device(det)
         return gather_detections(det, dst) if gather else det

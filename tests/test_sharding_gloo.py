@@ -62,6 +62,12 @@ def _worker(rank, world, port, out_dir):
     everyone = path.decode_nms(preds, shapes, **kw)                 # all_gather
     only0 = path.decode_nms(preds, shapes, dst=0, **kw)             # gather to rank 0
     assert (only0 is None) == (rank != 0)
+    # tensor gather (NCCL over NVLink on the GPU box, gloo here): unequal shards 4 + 3
+    local = path.decode_nms(preds, shapes, gather=False, **kw)
+    dev = sharding.gather_detections_device({k: torch.from_numpy(np.ascontiguousarray(v))
+                                             for k, v in local.items()})
+    for k, v in everyone.items():
+        assert np.array_equal(dev[k].numpy(), v), k
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), y0=y_local[0], lo=lo, hi=hi,
              **{"all_" + k: v for k, v in everyone.items()})
     dist.barrier()
