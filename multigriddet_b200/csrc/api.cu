@@ -287,11 +287,18 @@ int check_memory_arg(int memory)
     return MGD_OK;
 }
 
+int env_chunk(const char* name)
+{
+    const char* e = getenv(name);            // (read per call: tests shrink the chunks)
+    return e ? atoi(e) : 0;
+}
+
 // images per internal chunk: keeps the per-chunk scratch (owner table / candidate
 // lists) around 32 MB so it stays L2-resident between the two kernels that share it
 int chunk_images(const HeadGeom& g, int batch)
 {
     long long n = (32ll << 20) / ((long long)g.cells * 4);
+    if (const int e = env_chunk("MGD_ENCODE_CHUNK_IMAGES")) n = e;
     if (n < 1) n = 1;
     if (n > batch) n = batch;
     return (int)n;
@@ -302,6 +309,7 @@ int chunk_images(const HeadGeom& g, int batch)
 int decode_chunk_images(const HeadGeom& g, int batch)
 {
     long long n = (1ll << 30) / ((long long)g.cells * (long long)sizeof(Cand));
+    if (const int e = env_chunk("MGD_DECODE_CHUNK_IMAGES")) n = e;
     if (n < 1) n = 1;
     if (n > batch) n = batch;
     return (int)n;

@@ -579,3 +579,47 @@ def test_pinned_output_pool_recycles_and_respects_its_cap():
     del y1; gc.collect()
     y2 = engine.encode_targets(boxes, (416, 416), anchors, 20)
     assert all(np.array_equal(p, q) for p, q in zip(keep, y2))
+
+
+def test_bench_sized_batch_and_internal_chunk_boundaries(c_oracle):
+    """2 048 images at COCO 608 (half of configs[4]'s per-GPU batch, 5.5 GB of head outputs):
+    the encoder crosses its internal 1 106-image chunk boundary and must equal the C oracle on
+    every cell; decode + NMS must equal the C oracle on every image.  Then the same data
+    with the internal chunks forced down to 96 / 160 images must give identical results."""
+    import os
+    import torch
+    S, C, B, N = 608, 80, 2048, 100
+    anchors = synth.coco_anchors(np.float32)
+    base = synth.synth_boxes(41, 512, N, S, C)
+    boxes = np.concatenate([base, base[::-1], base[:, ::-1], base[::-1, ::-1]], 0)[:B].copy()
+    d_boxes = torch.from_numpy(boxes).cuda()
+    yt, st = engine.encode_targets(d_boxes, (S, S), anchors, C, return_stats=True)
+    ref, rst = c_oracle.encode_targets(boxes, (S, S), anchors, C, return_stats=True)
+    assert st["n_valid_boxes"] == rst["n_valid_boxes"] and st["n_skipped_writes"] == rst["n_skipped_writes"]
+    for a, r in zip(yt, ref):
+        _assert_encode_equal([a.cpu().numpy()], [r])
+    del ref
+    preds = [torch.empty((B, g, g, 88), dtype=torch.float32, device="cuda") for g in (19, 38, 76)]
+    for b0 in range(0, B, 256):
+        pl = synth.planted_head_outputs([y[b0:b0 + 256] for y in yt], 3, seed=100 + b0)
+        for dst, src in zip(preds, pl):
+            dst[b0:b0 + 256].copy_(src)
+    shapes = synth.image_shapes(3, B, mixed=True)
+    kw = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method="diou")
+    got = engine.decode_nms(preds, torch.from_numpy(shapes).cuda(), (S, S), anchors, C, **kw)
+    got = {k: v.cpu().numpy() for k, v in got.items() if hasattr(v, "cpu")}
+    for b0 in range(0, B, 512):                       # oracle in slices: bounded host memory
+        sl = slice(b0, b0 + 512)
+        r = c_oracle.decode_nms([p[sl].cpu().numpy() for p in preds], shapes[sl], (S, S), anchors, C, **kw)
+        same, bits_off = _compare_detections({k: v[sl] for k, v in got.items()}, r, 512)
+        assert same == 512 and bits_off == 0
+    os.environ["MGD_ENCODE_CHUNK_IMAGES"], os.environ["MGD_DECODE_CHUNK_IMAGES"] = "96", "160"
+    try:
+        yt2 = engine.encode_targets(d_boxes[:500], (S, S), anchors, C)
+        assert all(torch.equal(a[:500], b) for a, b in zip(yt, yt2))
+        got2 = engine.decode_nms([p[:500] for p in preds], torch.from_numpy(shapes[:500]).cuda(),
+                                 (S, S), anchors, C, **kw)
+        for k in ("boxes_xywh", "boxes_xyxy", "scores", "classes", "index", "counts"):
+            assert np.array_equal(got2[k].cpu().numpy(), got[k][:500]), k
+    finally:
+        del os.environ["MGD_ENCODE_CHUNK_IMAGES"], os.environ["MGD_DECODE_CHUNK_IMAGES"]
