@@ -503,6 +503,22 @@ struct HostStreams {
     size_t bounce_cap[2] = {0, 0};
     cudaEvent_t bounce_done[2] = {nullptr, nullptr};
     bool bounce_busy[2] = {false, false};
+    // a host thread that ends gives its staging back (errors ignored: at process exit the
+    // CUDA runtime may already be gone)
+    ~HostStreams()
+    {
+        if (!s[0] && !s[1] && chunk[0].blocks.empty() && chunk[1].blocks.empty() &&
+            call.blocks.empty() && !bounce[0] && !bounce[1]) return;
+        for (int i = 0; i < 2; ++i) if (s[i]) cudaStreamSynchronize(s[i]);
+        chunk[0].release(); chunk[1].release(); call.release();
+        for (int i = 0; i < 2; ++i) {
+            if (bounce[i]) cudaFreeHost(bounce[i]);
+            if (bounce_done[i]) cudaEventDestroy(bounce_done[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            if (s[i]) cudaStreamDestroy(s[i]);
+        }
+        cudaGetLastError();
+    }
 };
 thread_local HostStreams t_streams[64];
 
