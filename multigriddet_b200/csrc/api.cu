@@ -804,6 +804,22 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
         zero_copy = z_y[l] != nullptr;
     }
     if (zero_copy) step = batch;
+    // pageable y_true (the caller's own unpinned arrays): D2H into page-locked bounce chunks,
+    // then several threads copy a finished chunk out while the next one is on the link
+    bool pageable = !zero_copy && host_copy_threads() > 1 &&
+                    (size_t)batch * g.cells * g.D[0] * 4 >= (32u << 20);
+    for (int l = 0; l < g.L && pageable; ++l) pageable = is_pageable(y_true[l]);
+    struct CopyOut { bool live = false; size_t off[MGD_MAX_LAYERS], bytes[MGD_MAX_LAYERS]; float* dst[MGD_MAX_LAYERS]; };
+    CopyOut pending[2];
+    auto drain = [&](int slot) -> int {
+        CopyOut& c = pending[slot];
+        if (!c.live) return MGD_OK;
+        CUDA_TRY(cudaEventSynchronize(hs->bounce_done[slot]));
+        hs->bounce_busy[slot] = false;
+        for (int l = 0; l < g.L; ++l) parallel_copy(c.dst[l], hs->bounce[slot] + c.off[l], c.bytes[l]);
+        c.live = false;
+        return MGD_OK;
+    };
     int k = 0;
     for (int b0 = 0; b0 < batch; b0 += step, ++k) {
         const int nb = batch - b0 < step ? batch - b0 : step;
@@ -819,11 +835,35 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
                            reinterpret_cast<int*>(d_meta + 4), d_meta, Alloc{&ar, st},
                            (flags & MGD_FLAG_TF_COMPAT) != 0);
         if (rc) return rc;
+        unsigned char* bounce = nullptr;
+        if (pageable) {
+            if ((rc = drain(k & 1))) return rc;
+            size_t need = 0;
+            for (int l = 0; l < g.L; ++l) need += (((size_t)nb * g.gh[l] * g.gw[l] * g.D[l] * 4) + 255) & ~(size_t)255;
+            if ((rc = bounce_slot(hs, k & 1, need, &bounce))) return rc;
+        }
+        size_t bounce_off = 0;
         for (int l = 0; l < g.L && !zero_copy; ++l) {
             const size_t per = (size_t)g.gh[l] * g.gw[l] * g.D[l];
-            CUDA_TRY(cudaMemcpyAsync(y_true[l] + (size_t)b0 * per, d_y[l], (size_t)nb * per * 4,
-                                     cudaMemcpyDeviceToHost, st));
+            const size_t bytes = (size_t)nb * per * 4;
+            float* dst = y_true[l] + (size_t)b0 * per;
+            if (bounce) {
+                CopyOut& c = pending[k & 1];
+                c.off[l] = bounce_off; c.bytes[l] = bytes; c.dst[l] = dst;
+                dst = reinterpret_cast<float*>(bounce + bounce_off);
+                bounce_off += (bytes + 255) & ~(size_t)255;
+            }
+            CUDA_TRY(cudaMemcpyAsync(dst, d_y[l], bytes, cudaMemcpyDeviceToHost, st));
         }
+        if (bounce) {
+            CUDA_TRY(cudaEventRecord(hs->bounce_done[k & 1], st));
+            hs->bounce_busy[k & 1] = true;
+            pending[k & 1].live = true;
+        }
+    }
+    if (pageable) {
+        if ((rc = drain(k & 1))) return rc;           // the older of the two chunks in flight first
+        if ((rc = drain((k + 1) & 1))) return rc;
     }
     tr.mark("chunks enqueued");
     CUDA_TRY(cudaEventRecord(ev[1], ss[1]));
