@@ -252,6 +252,42 @@ MGD_API int mgd_match_detections(const double *det_boxes, const double *det_scor
                          int memory, int device, void *stream, int flags);
 
 /*
+ * Box-side pre-step of the encoder, over a batch (so the (B, N, 5) tensor mgd_encode_targets
+ * consumes can be produced on the device).
+ *
+ * mgd_reshape_boxes replaces reshape_boxes (multigriddet/data/augmentation.py:112-164),
+ * called per image from the legacy loader (data/generators.py:2435, 2463): scale into the
+ * padded image and add the paste offset (boxes * padding / src + d), optional horizontal /
+ * vertical flip, clip (x1, y1 >= 0; x2 <= target_w; y2 <= target_h), drop boxes whose width
+ * or height is <= 1.  Survivors keep their order (the reference's np.random.shuffle of the
+ * rows, :146, is the caller's business: pass the rows in the order wanted), the rest of each
+ * image's N slots is zero.
+ *   boxes   (batch, max_boxes, 5) [x1, y1, x2, y2, class]; MGD_BOXES_I32: int32, every
+ *           stored coordinate truncated toward zero like NumPy's float -> int32 assignment
+ *           (the legacy loader's dtype, generators.py:2429); MGD_BOXES_F64: float64
+ *   counts  (batch,) int32 valid rows per image, or NULL = all max_boxes rows
+ *   params  (batch, 10) int32: src_w, src_h, target_w, target_h, padding_w, padding_h, dx, dy,
+ *           horizontal_flip, vertical_flip
+ *   out     (batch, max_boxes, 5) same dtype; out_f32: optional float32 copy (the encoder's
+ *           input dtype); out_counts (batch,) int32 or NULL
+ *
+ * mgd_mosaic_merge_boxes replaces merge_mosaic_bboxes (augmentation.py:606-667) under
+ * random_mosaic_augment (:670-746): output image b takes the boxes of source images
+ * params[b][0..3] (top-left, bottom-left, bottom-right, top-right), cuts them at
+ * (crop_x, crop_y) = params[b][4..5], drops boxes left narrower than max(10, 1% of the
+ * image), concatenates in (quadrant, row) order and keeps the first max_boxes.
+ *   boxes (num_sources, max_boxes, 5) float64 (zero rows = padding); params (batch, 6) int32
+ */
+enum { MGD_BOXES_I32 = 0, MGD_BOXES_F64 = 1 };
+MGD_API int mgd_reshape_boxes(const void *boxes, int boxes_dtype, const int *counts,
+                      const int *params, int batch, int max_boxes, void *out, float *out_f32,
+                      int *out_counts, int memory, int device, void *stream, int flags);
+MGD_API int mgd_mosaic_merge_boxes(const double *boxes, int num_sources, int max_boxes,
+                           const int *params, int batch, int height, int width, double *out,
+                           float *out_f32, int *out_counts,
+                           int memory, int device, void *stream, int flags);
+
+/*
  * IoU matrix of two sets of xyxy boxes.  Replaces calculate_iou_matrix
  * (multigriddet/evaluation/metrics.py:28-70).  out (n, m) float64.
  */

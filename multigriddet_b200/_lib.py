@@ -21,6 +21,7 @@ FLAG_SYNC = 1
 FLAG_TF_COMPAT = 2
 NMS_IOU, NMS_DIOU, NMS_SOFT, NMS_WBF = 0, 1, 2, 3
 IOU_CORNER, IOU_CENTRE = 0, 1
+BOXES_I32, BOXES_F64 = 0, 1
 
 OK, ERR_INVALID_ARGUMENT, ERR_CLASS_RANGE, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = range(6)
 
@@ -70,7 +71,7 @@ EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targ
            "mgd_decode_nms", "mgd_decode_dense", "mgd_nms", "mgd_soft_nms", "mgd_wbf", "mgd_poll_status",
            "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack", "mgd_profile_begin",
            "mgd_profile_end", "mgd_match_detections", "mgd_iou_matrix", "mgd_host_alloc",
-           "mgd_host_free", "mgd_release_workspace")
+           "mgd_host_free", "mgd_release_workspace", "mgd_reshape_boxes", "mgd_mosaic_merge_boxes")
 
 
 def load():
@@ -139,6 +140,16 @@ def load():
     lib.mgd_iou_matrix.argtypes = [
         ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
         ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.mgd_reshape_boxes.restype = ctypes.c_int
+    lib.mgd_reshape_boxes.argtypes = [
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+        ctypes.c_int]
+    lib.mgd_mosaic_merge_boxes.restype = ctypes.c_int
+    lib.mgd_mosaic_merge_boxes.argtypes = [
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+        ctypes.c_void_p, ctypes.c_int]
     lib.mgd_host_alloc.restype = ctypes.c_int
     lib.mgd_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
     lib.mgd_host_free.restype = ctypes.c_int

@@ -1404,6 +1404,103 @@ int mgd_match_detections(const double* det_boxes, const double* det_scores, cons
     return MGD_OK;
 }
 
+int mgd_reshape_boxes(const void* boxes, int boxes_dtype, const int* counts, const int* params,
+                      int batch, int max_boxes, void* out, float* out_f32, int* out_counts,
+                      int memory, int device, void* stream, int flags)
+{
+    int rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (batch < 0 || max_boxes < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "batch and max_boxes must be >= 0");
+    if (boxes_dtype != MGD_BOXES_I32 && boxes_dtype != MGD_BOXES_F64)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "boxes_dtype must be MGD_BOXES_I32 or MGD_BOXES_F64");
+    const size_t n = (size_t)batch * max_boxes * 5;
+    if (batch > 0 && !params) return fail(MGD_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (n > 0 && (!boxes || !out)) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    if (batch == 0) return MGD_OK;
+    const size_t esz = boxes_dtype == MGD_BOXES_I32 ? 4 : 8;
+    BoxOpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = batch; a.N = max_boxes;
+    if (memory == MGD_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)stream;
+        a.in = boxes; a.counts = counts; a.params = params; a.out = out; a.out_f32 = out_f32;
+        a.out_counts = out_counts;
+        CUDA_TRY(launch_reshape_boxes(a, boxes_dtype == MGD_BOXES_I32, st));
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    cudaStream_t* ss;
+    if ((rc = host_streams(device, &ss, nullptr))) return rc;
+    cudaStream_t st = ss[0];
+    // staging: in | out (8-byte fields first) | out_f32 | params | counts | out_counts
+    const size_t off_out = (n * esz + 7) & ~(size_t)7, off_f32 = off_out + ((n * esz + 7) & ~(size_t)7);
+    const size_t off_par = off_f32 + n * 4, off_cnt = off_par + (size_t)batch * 40;
+    const size_t off_ocn = off_cnt + (size_t)batch * 4, total = off_ocn + (size_t)batch * 4;
+    unsigned char* buf;
+    CUDA_TRY(pool_malloc(&buf, total, st));
+    if (n) CUDA_TRY(cudaMemcpyAsync(buf, boxes, n * esz, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(buf + off_par, params, (size_t)batch * 40, cudaMemcpyHostToDevice, st));
+    if (counts) CUDA_TRY(cudaMemcpyAsync(buf + off_cnt, counts, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+    a.in = buf; a.out = buf + off_out; a.out_f32 = reinterpret_cast<float*>(buf + off_f32);
+    a.params = reinterpret_cast<const int*>(buf + off_par);
+    a.counts = counts ? reinterpret_cast<const int*>(buf + off_cnt) : nullptr;
+    a.out_counts = reinterpret_cast<int*>(buf + off_ocn);
+    CUDA_TRY(launch_reshape_boxes(a, boxes_dtype == MGD_BOXES_I32, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n) CUDA_TRY(cudaMemcpy(out, buf + off_out, n * esz, cudaMemcpyDeviceToHost));
+    if (out_f32 && n) CUDA_TRY(cudaMemcpy(out_f32, buf + off_f32, n * 4, cudaMemcpyDeviceToHost));
+    if (out_counts) CUDA_TRY(cudaMemcpy(out_counts, buf + off_ocn, (size_t)batch * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFreeAsync(buf, st));
+    return MGD_OK;
+}
+
+int mgd_mosaic_merge_boxes(const double* boxes, int num_sources, int max_boxes, const int* params,
+                           int batch, int height, int width, double* out, float* out_f32,
+                           int* out_counts, int memory, int device, void* stream, int flags)
+{
+    int rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (batch < 0 || max_boxes < 0 || num_sources < 0)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "batch, num_sources and max_boxes must be >= 0");
+    const size_t n_in = (size_t)num_sources * max_boxes * 5, n = (size_t)batch * max_boxes * 5;
+    if (batch > 0 && !params) return fail(MGD_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (n > 0 && (!out || (n_in > 0 && !boxes))) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    if (batch == 0) return MGD_OK;
+    BoxOpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = batch; a.N = max_boxes; a.n_src = num_sources; a.height = height; a.width = width;
+    if (memory == MGD_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)stream;
+        a.in = boxes; a.params = params; a.out = out; a.out_f32 = out_f32; a.out_counts = out_counts;
+        CUDA_TRY(launch_mosaic_merge(a, st));
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    cudaStream_t* ss;
+    if ((rc = host_streams(device, &ss, nullptr))) return rc;
+    cudaStream_t st = ss[0];
+    const size_t off_out = n_in * 8, off_f32 = off_out + n * 8, off_par = off_f32 + n * 4;
+    const size_t off_ocn = off_par + (size_t)batch * 24, total = off_ocn + (size_t)batch * 4;
+    unsigned char* buf;
+    CUDA_TRY(pool_malloc(&buf, total, st));
+    if (n_in) CUDA_TRY(cudaMemcpyAsync(buf, boxes, n_in * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(buf + off_par, params, (size_t)batch * 24, cudaMemcpyHostToDevice, st));
+    a.in = buf; a.out = buf + off_out; a.out_f32 = reinterpret_cast<float*>(buf + off_f32);
+    a.params = reinterpret_cast<const int*>(buf + off_par);
+    a.out_counts = reinterpret_cast<int*>(buf + off_ocn);
+    CUDA_TRY(launch_mosaic_merge(a, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n) CUDA_TRY(cudaMemcpy(out, buf + off_out, n * 8, cudaMemcpyDeviceToHost));
+    if (out_f32 && n) CUDA_TRY(cudaMemcpy(out_f32, buf + off_f32, n * 4, cudaMemcpyDeviceToHost));
+    if (out_counts) CUDA_TRY(cudaMemcpy(out_counts, buf + off_ocn, (size_t)batch * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaFreeAsync(buf, st));
+    return MGD_OK;
+}
+
 int mgd_iou_matrix(const double* boxes1, int n, const double* boxes2, int m, double* out, int memory,
                    int device, void* stream, int flags)
 {

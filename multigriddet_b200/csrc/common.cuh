@@ -124,6 +124,18 @@ struct MatchArgs {
     int* next_image;                  // work counter, zeroed by the caller
 };
 
+// ---- box-side pre-step of the encoder (reshape_boxes / merge_mosaic_bboxes) ---
+struct BoxOpArgs {
+    int B, N;                         // output images, box slots per image
+    const void* in;                   // reshape: (B, N, 5) int32 | float64; mosaic: (n_src, N, 5) float64
+    const int* counts;                // reshape: valid rows per image or nullptr (= N)
+    const int* params;                // reshape: (B, 10); mosaic: (B, 6)
+    int n_src, height, width;         // mosaic: source images, mosaic image size
+    void* out;                        // (B, N, 5) in the input dtype
+    float* out_f32;                   // optional float32 copy (what the encoder consumes)
+    int* out_counts;                  // (B,) or nullptr
+};
+
 // per-kernel CUDA-event timing (mgd_profile_begin / mgd_profile_end)
 enum ProfKind { PROF_ENCODE_ASSIGN = 0, PROF_ENCODE_FILL = 1, PROF_DECODE_COMPACT = 2,
                 PROF_NMS = 3, PROF_OTHER = 4, PROF_KINDS = 5 };
@@ -143,5 +155,7 @@ cudaError_t launch_decode_dense(const DecodeArgs& a, const int* image_hw, double
 cudaError_t launch_match(const MatchArgs& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_iou_matrix(const double* b1, int n, const double* b2, int m, double* out,
                               cudaStream_t stream);
+cudaError_t launch_reshape_boxes(const BoxOpArgs& a, int boxes_i32, cudaStream_t stream);
+cudaError_t launch_mosaic_merge(const BoxOpArgs& a, cudaStream_t stream);
 cudaError_t launch_keep_from_index(const int* index, const int* counts, int max_keep, int* keep,
                                    int* n_keep, cudaStream_t stream);

@@ -415,3 +415,91 @@ def iou_matrix(boxes1, boxes2):
                                 None, _lib.FLAG_SYNC)
         _lib.raise_for_status(rc)
     return out
+
+
+# ------------------------------------------------------------------------------
+# box-side pre-step of the encoder (reference multigriddet/data/augmentation.py)
+# ------------------------------------------------------------------------------
+
+def reshape_boxes_batch(boxes, params, counts=None, want_f32=True, sync=True):
+    """``reshape_boxes`` over a batch (``mgd_reshape_boxes``).
+
+    boxes (B, N, 5) int32 or float64, NumPy or torch CUDA; params (B, 10) int32
+    ``[src_w, src_h, target_w, target_h, padding_w, padding_h, dx, dy, hflip, vflip]``;
+    counts (B,) valid rows or None.  Returns ``(out, out_f32 or None, out_counts)`` in the same
+    memory space; ``out_f32`` is what ``encode_targets`` takes.
+    """
+    lib = _lib.load()
+    if _is_torch(boxes):
+        import torch
+        dev = boxes.device
+        i32 = boxes.dtype == torch.int32
+        b = boxes.contiguous() if i32 else boxes.to(torch.float64).contiguous()
+        B, N = int(b.shape[0]), int(b.shape[1])
+        par = torch.as_tensor(params).to(device=dev, dtype=torch.int32).contiguous()
+        cnt = None if counts is None else torch.as_tensor(counts).to(device=dev, dtype=torch.int32).contiguous()
+        out = torch.empty_like(b)
+        o32 = torch.empty((B, N, 5), dtype=torch.float32, device=dev) if want_f32 else None
+        ocn = torch.empty((B,), dtype=torch.int32, device=dev)
+        p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None and x.numel() else None
+        idx = dev.index or 0
+        rc = lib.mgd_reshape_boxes(p(b), _lib.BOXES_I32 if i32 else _lib.BOXES_F64, p(cnt), p(par), B, N,
+                                   p(out), p(o32), p(ocn), _lib.MEM_DEVICE, idx,
+                                   ctypes.c_void_p(_torch_stream(idx)), _lib.FLAG_SYNC if sync else 0)
+    else:
+        b = np.asarray(boxes)
+        i32 = b.dtype == np.int32
+        b = np.ascontiguousarray(b, dtype=np.int32 if i32 else np.float64)
+        B, N = b.shape[0], b.shape[1]
+        par = np.ascontiguousarray(np.asarray(params), dtype=np.int32).reshape(B, 10)
+        cnt = None if counts is None else np.ascontiguousarray(np.asarray(counts), dtype=np.int32)
+        out = np.zeros_like(b)
+        o32 = np.zeros((B, N, 5), dtype=np.float32) if want_f32 else None
+        ocn = np.zeros((B,), dtype=np.int32)
+        p = lambda x: ctypes.c_void_p(x.ctypes.data) if x is not None and x.size else None
+        rc = lib.mgd_reshape_boxes(p(b), _lib.BOXES_I32 if i32 else _lib.BOXES_F64, p(cnt), p(par), B, N,
+                                   p(out), p(o32), p(ocn), _lib.MEM_HOST, _current_device(), None,
+                                   _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    return out, o32, ocn
+
+
+def mosaic_merge_boxes_batch(boxes, sample_index, crop_xy, image_size, want_f32=True, sync=True):
+    """``merge_mosaic_bboxes`` for a batch of mosaics (``mgd_mosaic_merge_boxes``).
+
+    boxes (n_src, N, 5) float64 (zero rows = padding); sample_index (B, 4) source image of
+    each quadrant (top-left, bottom-left, bottom-right, top-right); crop_xy (B, 2);
+    image_size (height, width).  Returns ``(out (B, N, 5) f64, out_f32 or None, counts)``.
+    """
+    lib = _lib.load()
+    H, W = int(image_size[0]), int(image_size[1])
+    if _is_torch(boxes):
+        import torch
+        dev = boxes.device
+        b = boxes.to(torch.float64).contiguous()
+        n_src, N = int(b.shape[0]), int(b.shape[1])
+        par = torch.cat([torch.as_tensor(sample_index).reshape(-1, 4).to(dev),
+                         torch.as_tensor(crop_xy).reshape(-1, 2).to(dev)], 1).to(torch.int32).contiguous()
+        B = int(par.shape[0])
+        out = torch.empty((B, N, 5), dtype=torch.float64, device=dev)
+        o32 = torch.empty((B, N, 5), dtype=torch.float32, device=dev) if want_f32 else None
+        ocn = torch.empty((B,), dtype=torch.int32, device=dev)
+        p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None and x.numel() else None
+        idx = dev.index or 0
+        rc = lib.mgd_mosaic_merge_boxes(p(b), n_src, N, p(par), B, H, W, p(out), p(o32), p(ocn),
+                                        _lib.MEM_DEVICE, idx, ctypes.c_void_p(_torch_stream(idx)),
+                                        _lib.FLAG_SYNC if sync else 0)
+    else:
+        b = np.ascontiguousarray(np.asarray(boxes), dtype=np.float64)
+        n_src, N = b.shape[0], b.shape[1]
+        par = np.ascontiguousarray(np.concatenate([np.asarray(sample_index).reshape(-1, 4),
+                                                   np.asarray(crop_xy).reshape(-1, 2)], 1), dtype=np.int32)
+        B = par.shape[0]
+        out = np.zeros((B, N, 5), dtype=np.float64)
+        o32 = np.zeros((B, N, 5), dtype=np.float32) if want_f32 else None
+        ocn = np.zeros((B,), dtype=np.int32)
+        p = lambda x: ctypes.c_void_p(x.ctypes.data) if x is not None and x.size else None
+        rc = lib.mgd_mosaic_merge_boxes(p(b), n_src, N, p(par), B, H, W, p(out), p(o32), p(ocn),
+                                        _lib.MEM_HOST, _current_device(), None, _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    return out, o32, ocn

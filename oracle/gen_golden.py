@@ -239,11 +239,54 @@ def metrics_cases():
     np.savez_compressed(os.path.join(OUT, "metrics_cases.npz"), **store)
 
 
+def synth_box_transform_cases(seed, n_cases, N=24):
+    """Random inputs for reshape_boxes / merge_mosaic_bboxes (shared by the golden generator
+    and the tests)."""
+    rng = np.random.default_rng(seed)
+    reshape, mosaic = [], []
+    for _ in range(n_cases):
+        n = int(rng.integers(0, N + 1))
+        sw, sh = int(rng.integers(200, 1400)), int(rng.integers(200, 1400))
+        tw = th = int(rng.choice([320, 416, 608]))
+        pw, ph = int(rng.integers(100, int(tw * 1.3))), int(rng.integers(100, int(th * 1.3)))
+        dx, dy = int(rng.integers(-120, 200)), int(rng.integers(-120, 200))
+        xy = rng.uniform(0, [sw, sh], (n, 2)); wh = rng.uniform(1, [sw / 2, sh / 2], (n, 2))
+        b = np.concatenate([xy, np.minimum(xy + wh, [sw, sh]), rng.integers(0, 80, (n, 1))], 1)
+        reshape.append(dict(boxes=b, src=(sw, sh), target=(tw, th), padding=(pw, ph), offset=(dx, dy),
+                            hflip=bool(rng.integers(0, 2)), vflip=bool(rng.integers(0, 2))))
+        bx = np.zeros((4, N, 5))
+        for q in range(4):
+            m = int(rng.integers(0, N + 1))
+            xy = rng.uniform(0, tw, (m, 2)); wh = np.exp(rng.normal(np.log(50), 1.0, (m, 2))).clip(2, tw)
+            bx[q, :m] = np.concatenate([xy, np.minimum(xy + wh, tw), rng.integers(0, 80, (m, 1))], 1)
+        mosaic.append(dict(boxes=bx, crop=(int(rng.integers(int(tw * .2), int(tw * .8))),
+                                           int(rng.integers(int(th * .2), int(th * .8)))), size=(th, tw)))
+    return reshape, mosaic
+
+
+def boxes_cases():
+    """tests/golden/boxes_cases.npz: the reference's reshape_boxes (shuffle disabled) and
+    merge_mosaic_bboxes on random inputs."""
+    R = ref_loader.load_box_transforms()
+    reshape, mosaic = synth_box_transform_cases(77, 40)
+    store = {"n_cases": np.array(len(reshape))}
+    for i, c in enumerate(reshape):
+        for tag, dt in (("i32", np.int32), ("f64", np.float64)):
+            out = R.reshape_boxes(c["boxes"].astype(dt), c["src"], c["target"], c["padding"], c["offset"],
+                                  c["hflip"], c["vflip"])
+            store[f"r{i}_{tag}"] = np.asarray(out).reshape(-1, 5)
+    for i, c in enumerate(mosaic):
+        store[f"m{i}"] = R.merge_mosaic_bboxes(c["boxes"], c["crop"][0], c["crop"][1], c["size"])
+    np.savez_compressed(os.path.join(OUT, "boxes_cases.npz"), **store)
+    print("boxes cases written:", sum(len(store[f"r{i}_i32"]) for i in range(len(reshape))), "reshaped rows,",
+          sum(int((store[f"m{i}"][:, 2] > 0).sum()) for i in range(len(mosaic))), "mosaic rows")
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found at " + ref_loader.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
-    only = sys.argv[1:] or ["encode", "decode", "nms", "metrics"]
+    only = sys.argv[1:] or ["encode", "decode", "nms", "metrics", "boxes"]
     if "encode" in only:
         encode_cases()
     if "decode" in only:
@@ -252,5 +295,7 @@ if __name__ == "__main__":
         nms_cases()
     if "metrics" in only:
         metrics_cases()
+    if "boxes" in only:
+        boxes_cases()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {total / 1e6:.2f} MB in {OUT}")

@@ -629,3 +629,75 @@ def fragility_report(preds, image_shape, model_image_size, anchors, num_classes,
     return {"threshold_grazing": graze, "fragile_score_pairs": close_pairs,
             "metric_grazing": metric_graze,
             "fragile": bool(graze or close_pairs or metric_graze)}
+
+
+# --------------------------------------------------------------------------
+# box-side pre-step of the encoder  (multigriddet/data/augmentation.py:112-164, 606-667)
+# --------------------------------------------------------------------------
+
+def reshape_boxes(boxes, src_shape, target_shape, padding_shape, offset,
+                  horizontal_flip=False, vertical_flip=False):
+    """``reshape_boxes`` (augmentation.py:112-164) WITHOUT the row shuffle of :146 and without
+    modifying the caller's array.  int32 boxes keep NumPy's float -> int32 store (truncation
+    toward zero) exactly where the reference assigns into the int array (:149-150)."""
+    b = np.array(boxes)
+    if len(b) == 0:
+        return b
+    src_w, src_h = src_shape
+    target_w, target_h = target_shape
+    padding_w, padding_h = padding_shape
+    dx, dy = offset
+    b[:, [0, 2]] = b[:, [0, 2]] * padding_w / src_w + dx
+    b[:, [1, 3]] = b[:, [1, 3]] * padding_h / src_h + dy
+    if horizontal_flip:
+        b[:, [0, 2]] = target_w - b[:, [2, 0]]
+    if vertical_flip:
+        b[:, [1, 3]] = target_h - b[:, [3, 1]]
+    b[:, 0:2][b[:, 0:2] < 0] = 0
+    b[:, 2][b[:, 2] > target_w] = target_w
+    b[:, 3][b[:, 3] > target_h] = target_h
+    w = b[:, 2] - b[:, 0]
+    h = b[:, 3] - b[:, 1]
+    return b[np.logical_and(w > 1, h > 1)]
+
+
+def merge_mosaic_bboxes(bboxes, crop_x, crop_y, image_size):
+    """``merge_mosaic_bboxes`` (augmentation.py:606-667): quadrant order top-left,
+    bottom-left, bottom-right, top-right."""
+    bboxes = np.asarray(bboxes, dtype=np.float64)
+    max_boxes = bboxes.shape[1]
+    height, width = image_size
+    merged = []
+    for q in range(4):
+        for box in bboxes[q]:
+            x1, y1, x2, y2 = box[0], box[1], box[2], box[3]
+            cut_y = y2 > crop_y and y1 < crop_y
+            cut_x = x2 > crop_x and x1 < crop_x
+            if q == 0:
+                if y1 > crop_y or x1 > crop_x:
+                    continue
+                if cut_y: y2 = crop_y
+                if cut_x: x2 = crop_x
+            elif q == 1:
+                if y2 < crop_y or x1 > crop_x:
+                    continue
+                if cut_y: y1 = crop_y
+                if cut_x: x2 = crop_x
+            elif q == 2:
+                if y2 < crop_y or x2 < crop_x:
+                    continue
+                if cut_y: y1 = crop_y
+                if cut_x: x1 = crop_x
+            else:
+                if y1 > crop_y or x2 < crop_x:
+                    continue
+                if cut_y: y2 = crop_y
+                if cut_x: x1 = crop_x
+            if abs(x2 - x1) < max(10, width * 0.01) or abs(y2 - y1) < max(10, height * 0.01):
+                continue
+            merged.append([x1, y1, x2, y2, box[4]])
+    merged = merged[:max_boxes]
+    out = np.zeros((max_boxes, 5))
+    if merged:
+        out[:len(merged)] = merged
+    return out

@@ -145,3 +145,46 @@ def load_metrics():
         out = module
     _cache["metrics"] = out
     return out
+
+
+def load_box_transforms():
+    """The reference's ``reshape_boxes`` and ``merge_mosaic_bboxes`` (pure NumPy;
+    ``augmentation.py`` itself imports cv2 / PIL / imgaug, so the two ``FunctionDef`` nodes
+    are cut out with ``ast`` like the encoder).  ``reshape_boxes`` shuffles its rows with
+    ``np.random.shuffle`` (:146); the returned wrapper runs it with the shuffle disabled so
+    results are comparable row by row (and on a copy: the reference writes in place)."""
+    if "boxes" in _cache:
+        return _cache["boxes"]
+    import numpy as np
+    path = os.path.join(REFERENCE_ROOT, "multigriddet", "data", "augmentation.py")
+    with open(path, "r") as fh, warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)       # a docstring of that file has "\ "
+        tree = ast.parse(fh.read(), filename=path)
+    names = ("reshape_boxes", "merge_mosaic_bboxes")
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    if len(picked) != len(names):
+        raise RuntimeError("reference box transforms not found in " + path)
+
+    class _NoShuffleRandom:
+        @staticmethod
+        def shuffle(_):
+            return None
+
+    class _Np:
+        """NumPy with ``random.shuffle`` turned into a no-op."""
+        random = _NoShuffleRandom()
+
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+    scope = {"np": _Np()}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), scope)
+    raw = scope["reshape_boxes"]
+
+    def reshape_boxes(boxes, *a, **k):
+        return raw(np.array(boxes), *a, **k)
+
+    ns = types.SimpleNamespace(reshape_boxes=reshape_boxes,
+                               merge_mosaic_bboxes=scope["merge_mosaic_bboxes"])
+    _cache["boxes"] = ns
+    return ns

@@ -1,0 +1,140 @@
+"""Box-side pre-step of the encoder: reference
+multigriddet/data/augmentation.py reshape_boxes (:112-164) and merge_mosaic_bboxes (:606-667).
+
+CPU: the oracle restatement against golden vectors produced by the REAL reference
+(tests/golden/boxes_cases.npz; reshape_boxes with its row shuffle disabled) and against the
+reference executed live where /root/reference exists.  GPU: mgd_reshape_boxes /
+mgd_mosaic_merge_boxes against both, and the device pipeline boxes -> reshape -> encode.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mgd_oracle as O
+from oracle import ref_loader
+from oracle.gen_golden import synth_box_transform_cases
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "boxes_cases.npz")
+
+
+def _golden_cases():
+    z = np.load(GOLD)
+    reshape, mosaic = synth_box_transform_cases(77, int(z["n_cases"]))
+    return z, reshape, mosaic
+
+
+def test_oracle_matches_reference_golden():
+    z, reshape, mosaic = _golden_cases()
+    for i, c in enumerate(reshape):
+        for tag, dt in (("i32", np.int32), ("f64", np.float64)):
+            got = O.reshape_boxes(c["boxes"].astype(dt), c["src"], c["target"], c["padding"], c["offset"],
+                                  c["hflip"], c["vflip"])
+            assert np.array_equal(np.asarray(got).reshape(-1, 5), z[f"r{i}_{tag}"]), (i, tag)
+    for i, c in enumerate(mosaic):
+        assert np.array_equal(O.merge_mosaic_bboxes(c["boxes"], *c["crop"], c["size"]), z[f"m{i}"]), i
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="needs /root/reference (build container)")
+def test_oracle_matches_live_reference_on_fresh_seeds():
+    R = ref_loader.load_box_transforms()
+    reshape, mosaic = synth_box_transform_cases(5, 60)
+    for c in reshape:
+        for dt in (np.int32, np.float64, np.float32):
+            a = (c["boxes"].astype(dt), c["src"], c["target"], c["padding"], c["offset"], c["hflip"], c["vflip"])
+            assert np.array_equal(np.asarray(R.reshape_boxes(*a)), np.asarray(O.reshape_boxes(*a)))
+    for c in mosaic:
+        assert np.array_equal(R.merge_mosaic_bboxes(c["boxes"], *c["crop"], c["size"]),
+                              O.merge_mosaic_bboxes(c["boxes"], *c["crop"], c["size"]))
+
+
+def _reshape_batch_inputs(cases, dt, N):
+    B = len(cases)
+    boxes = np.zeros((B, N, 5), dt)
+    counts = np.zeros(B, np.int32)
+    params = np.zeros((B, 10), np.int32)
+    for b, c in enumerate(cases):
+        n = len(c["boxes"])
+        boxes[b, :n] = c["boxes"].astype(dt)
+        counts[b] = n
+        params[b] = [*c["src"], *c["target"], *c["padding"], *c["offset"], int(c["hflip"]), int(c["vflip"])]
+    return boxes, counts, params
+
+
+@pytest.mark.gpu
+def test_gpu_reshape_boxes_against_golden_and_oracle():
+    import torch
+    from multigriddet_b200 import engine
+    from multigriddet_b200.data import reshape_boxes
+    z, reshape, _ = _golden_cases()
+    N = 24
+    for tag, dt in (("i32", np.int32), ("f64", np.float64)):
+        boxes, counts, params = _reshape_batch_inputs(reshape, dt, N)
+        for dev in (False, True):
+            args = (torch.from_numpy(boxes).cuda(), params, counts) if dev else (boxes, params, counts)
+            out, o32, cnt = engine.reshape_boxes_batch(*args)
+            if dev:
+                out, o32, cnt = out.cpu().numpy(), o32.cpu().numpy(), cnt.cpu().numpy()
+            for i in range(len(reshape)):
+                ref = z[f"r{i}_{tag}"]
+                assert cnt[i] == len(ref) and np.array_equal(out[i, :cnt[i]], ref), (tag, dev, i)
+                assert not out[i, cnt[i]:].any()
+                assert np.array_equal(o32[i], out[i].astype(np.float32))
+        for i, c in enumerate(reshape[:8]):                        # the single-image drop-in
+            got = reshape_boxes(c["boxes"].astype(dt), c["src"], c["target"], c["padding"], c["offset"],
+                                c["hflip"], c["vflip"])
+            assert got.dtype == dt and np.array_equal(np.asarray(got).reshape(-1, 5), z[f"r{i}_{tag}"])
+    assert len(reshape_boxes(np.zeros((0, 5), np.int32), (10, 10), (5, 5), (5, 5), (0, 0))) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_mosaic_merge_against_golden_and_oracle():
+    import torch
+    from multigriddet_b200 import engine
+    from multigriddet_b200.data import merge_mosaic_bboxes
+    z, _, mosaic = _golden_cases()
+    for i, c in enumerate(mosaic):
+        assert np.array_equal(merge_mosaic_bboxes(c["boxes"], *c["crop"], c["size"]), z[f"m{i}"]), i
+    # batch form: 16 mosaics drawing their four samples from a batch of 16 images; cap at N
+    rng = np.random.default_rng(3)
+    N, S = 12, 416
+    src = np.zeros((16, N, 5))
+    for b in range(16):
+        m = int(rng.integers(4, N + 1))
+        xy = rng.uniform(0, S, (m, 2)); wh = rng.uniform(20, 200, (m, 2))
+        src[b, :m] = np.concatenate([xy, np.minimum(xy + wh, S), rng.integers(0, 20, (m, 1))], 1)
+    idx = np.stack([rng.permutation(16)[:4] for _ in range(16)])
+    crop = rng.integers(int(S * .2), int(S * .8), (16, 2))
+    ref = np.stack([O.merge_mosaic_bboxes(src[idx[b]], int(crop[b, 0]), int(crop[b, 1]), (S, S)) for b in range(16)])
+    for dev in (False, True):
+        out, o32, cnt = engine.mosaic_merge_boxes_batch(torch.from_numpy(src).cuda() if dev else src, idx, crop, (S, S))
+        if dev:
+            out, o32, cnt = out.cpu().numpy(), o32.cpu().numpy(), cnt.cpu().numpy()
+        assert np.array_equal(out, ref)
+        assert np.array_equal(cnt, (ref[..., 2] > 0).sum(1)) and cnt.max() == N      # the cap is hit
+        assert np.array_equal(o32, ref.astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_device_pipeline_reshape_then_encode():
+    """int32 annotation boxes -> reshape on the device -> float32 (B, N, 5) -> encoder, no host hop."""
+    import torch
+    from multigriddet_b200 import engine, synth
+    S, C, N = 416, 80, 24
+    reshape, _ = synth_box_transform_cases(9, 32)
+    for c in reshape:
+        c["target"] = (S, S)
+    boxes, counts, params = _reshape_batch_inputs(reshape, np.int32, N)
+    anchors = synth.coco_anchors(np.float32)
+    _, d32, _ = engine.reshape_boxes_batch(torch.from_numpy(boxes).cuda(), params, counts, sync=False)
+    got = engine.encode_targets(d32, (S, S), anchors, C)
+    host = np.zeros((len(reshape), N, 5), np.float32)
+    for b, c in enumerate(reshape):
+        r = np.asarray(O.reshape_boxes(c["boxes"].astype(np.int32), c["src"], c["target"], c["padding"],
+                                       c["offset"], c["hflip"], c["vflip"])).reshape(-1, 5)
+        host[b, :len(r)] = r
+    ref = O.encode_targets(host, (S, S), anchors, C)
+    for g, r in zip(got, ref):
+        g = g.cpu().numpy()
+        assert np.array_equal(g[..., 4:], r[..., 4:]) and np.array_equal(g[..., :2], r[..., :2])
+        np.testing.assert_allclose(g[..., 2:4], r[..., 2:4], rtol=1e-5, atol=1e-6)
