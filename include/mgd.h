@@ -252,6 +252,26 @@ MGD_API int mgd_match_detections(const double *det_boxes, const double *det_scor
                          int memory, int device, void *stream, int flags);
 
 /*
+ * Loss-side ignore mask.  Replaces MultiGridLoss._compute_ignore_mask and
+ * _compute_iou_batch (multigriddet/losses/multigrid_loss.py:494-703, 445-492), called once
+ * per layer from the loss (:316).  Forward only: the reference casts the mask from a
+ * boolean and wraps the two IoU maps in stop_gradient.  PARITY UNPINNED (TensorFlow graph
+ * code; restated op by op in float32, reference quirks included -- see csrc/loss.cu).
+ *
+ *   y_pred, y_true  num_layers pointers, each (batch, grid_h, grid_w, 5+A_l+C) float32
+ *   ignore_mask          (batch, grid_h, grid_w, 1) float32 per layer: 1 where the best IoU of
+ *                        the cell's predicted boxes with the image's ground truth on that
+ *                        layer exceeds ignore_thresh and the cell is not positive
+ *   assigned_anchor_iou  same shape: IoU of the assigned anchor's box on positive cells, else 0
+ *   max_iou_map          same shape: best IoU over the anchors
+ *   eps                  Keras epsilon of the reference (1e-7)
+ */
+MGD_API int mgd_ignore_mask(const mgd_head_config *cfg, const float *const *y_pred,
+                    const float *const *y_true, int batch, double ignore_thresh, double eps,
+                    float *const *ignore_mask, float *const *assigned_anchor_iou,
+                    float *const *max_iou_map, int memory, int device, void *stream, int flags);
+
+/*
  * Box-side pre-step of the encoder, over a batch (so the (B, N, 5) tensor mgd_encode_targets
  * consumes can be produced on the device).
  *

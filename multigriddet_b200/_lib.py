@@ -71,7 +71,8 @@ EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targ
            "mgd_decode_nms", "mgd_decode_dense", "mgd_nms", "mgd_soft_nms", "mgd_wbf", "mgd_poll_status",
            "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack", "mgd_profile_begin",
            "mgd_profile_end", "mgd_match_detections", "mgd_iou_matrix", "mgd_host_alloc",
-           "mgd_host_free", "mgd_release_workspace", "mgd_reshape_boxes", "mgd_mosaic_merge_boxes")
+           "mgd_host_free", "mgd_release_workspace", "mgd_reshape_boxes", "mgd_mosaic_merge_boxes",
+           "mgd_ignore_mask")
 
 
 def load():
@@ -149,6 +150,12 @@ def load():
     lib.mgd_mosaic_merge_boxes.argtypes = [
         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+        ctypes.c_void_p, ctypes.c_int]
+    lib.mgd_ignore_mask.restype = ctypes.c_int
+    lib.mgd_ignore_mask.argtypes = [
+        ctypes.POINTER(HeadConfig), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+        ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p),
+        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
         ctypes.c_void_p, ctypes.c_int]
     lib.mgd_host_alloc.restype = ctypes.c_int
     lib.mgd_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]

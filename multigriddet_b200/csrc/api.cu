@@ -1404,6 +1404,81 @@ int mgd_match_detections(const double* det_boxes, const double* det_scores, cons
     return MGD_OK;
 }
 
+int mgd_ignore_mask(const mgd_head_config* cfg, const float* const* y_pred,
+                    const float* const* y_true, int batch, double ignore_thresh, double eps,
+                    float* const* ignore_mask, float* const* assigned_anchor_iou,
+                    float* const* max_iou_map, int memory, int device, void* stream, int flags)
+{
+    HeadGeom g;
+    int rc = build_geom(cfg, &g);
+    if (rc) return rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (batch < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "batch must be >= 0");
+    if (!y_pred || !y_true || !ignore_mask || !assigned_anchor_iou || !max_iou_map)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor list");
+    for (int l = 0; l < g.L && batch > 0; ++l)
+        if (!y_pred[l] || !y_true[l] || !ignore_mask[l] || !assigned_anchor_iou[l] || !max_iou_map[l])
+            return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor for layer %d", l);
+    int num_sms;
+    if ((rc = prepare_device(device, &num_sms))) return rc;
+    if (batch == 0) return MGD_OK;
+    const bool host = memory == MGD_MEM_HOST;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (host) {
+        cudaStream_t* ss;
+        if ((rc = host_streams(device, &ss, nullptr))) return rc;
+        st = ss[0];
+    }
+    LossArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = g; a.B = batch; a.ignore_thresh = (float)ignore_thresh; a.eps = (float)eps;
+    // scratch: ground-truth lists; host memory: staged tensors as well
+    const size_t n_gt = (size_t)batch * g.cells * 2;
+    size_t in_floats = 0, out_floats = 0;
+    for (int l = 0; l < g.L; ++l) {
+        in_floats += (size_t)batch * g.gh[l] * g.gw[l] * g.D[l];
+        out_floats += (size_t)batch * g.gh[l] * g.gw[l];
+    }
+    const size_t off_area = n_gt * 16, off_cnt = off_area + n_gt * 4;
+    const size_t off_in = (off_cnt + (size_t)batch * g.L * 4 + 15) & ~(size_t)15;
+    const size_t total = off_in + (host ? (2 * in_floats + 3 * out_floats) * 4 : 0);
+    unsigned char* buf;
+    CUDA_TRY(pool_malloc(&buf, total, st));
+    a.gt_boxes = buf;
+    a.gt_area = reinterpret_cast<float*>(buf + off_area);
+    a.gt_count = reinterpret_cast<int*>(buf + off_cnt);
+    float* cursor = reinterpret_cast<float*>(buf + off_in);
+    for (int l = 0; l < g.L; ++l) {
+        const size_t n_in = (size_t)batch * g.gh[l] * g.gw[l] * g.D[l];
+        const size_t n_out = (size_t)batch * g.gh[l] * g.gw[l];
+        if (host) {
+            CUDA_TRY(cudaMemcpyAsync(cursor, y_pred[l], n_in * 4, cudaMemcpyHostToDevice, st));
+            a.y_pred[l] = cursor; cursor += n_in;
+            CUDA_TRY(cudaMemcpyAsync(cursor, y_true[l], n_in * 4, cudaMemcpyHostToDevice, st));
+            a.y_true[l] = cursor; cursor += n_in;
+            a.ignore[l] = cursor; cursor += n_out;
+            a.assigned[l] = cursor; cursor += n_out;
+            a.max_iou[l] = cursor; cursor += n_out;
+        } else {
+            a.y_pred[l] = y_pred[l]; a.y_true[l] = y_true[l];
+            a.ignore[l] = ignore_mask[l]; a.assigned[l] = assigned_anchor_iou[l]; a.max_iou[l] = max_iou_map[l];
+        }
+    }
+    CUDA_TRY(launch_ignore_mask(a, st));
+    if (host) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int l = 0; l < g.L; ++l) {
+            const size_t n_out = (size_t)batch * g.gh[l] * g.gw[l] * 4;
+            CUDA_TRY(cudaMemcpy(ignore_mask[l], a.ignore[l], n_out, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(assigned_anchor_iou[l], a.assigned[l], n_out, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(max_iou_map[l], a.max_iou[l], n_out, cudaMemcpyDeviceToHost));
+        }
+    }
+    CUDA_TRY(cudaFreeAsync(buf, st));
+    if (!host && (flags & MGD_FLAG_SYNC)) CUDA_TRY(cudaStreamSynchronize(st));
+    return MGD_OK;
+}
+
 int mgd_reshape_boxes(const void* boxes, int boxes_dtype, const int* counts, const int* params,
                       int batch, int max_boxes, void* out, float* out_f32, int* out_counts,
                       int memory, int device, void* stream, int flags)

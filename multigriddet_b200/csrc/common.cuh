@@ -136,6 +136,21 @@ struct BoxOpArgs {
     int* out_counts;                  // (B,) or nullptr
 };
 
+// ---- loss-side ignore mask (multigrid_loss.py:494-703) ------------------------
+struct LossArgs {
+    HeadGeom g;
+    int B;
+    const float* y_pred[MGD_MAX_LAYERS];   // (B, gh, gw, D) raw head outputs
+    const float* y_true[MGD_MAX_LAYERS];   // (B, gh, gw, D) encoder targets
+    float ignore_thresh, eps;
+    float* ignore[MGD_MAX_LAYERS];         // (B, gh, gw, 1)
+    float* assigned[MGD_MAX_LAYERS];       // (B, gh, gw, 1) IoU of the assigned anchor, 0 on negatives
+    float* max_iou[MGD_MAX_LAYERS];        // (B, gh, gw, 1) best IoU over anchors
+    void* gt_boxes;                        // scratch: (B, cells, 2) x 16 B corner boxes (raw | unique)
+    float* gt_area;                        // scratch: (B, cells, 2)
+    int* gt_count;                         // scratch: (B, L) unique ground-truth boxes
+};
+
 // per-kernel CUDA-event timing (mgd_profile_begin / mgd_profile_end)
 enum ProfKind { PROF_ENCODE_ASSIGN = 0, PROF_ENCODE_FILL = 1, PROF_DECODE_COMPACT = 2,
                 PROF_NMS = 3, PROF_OTHER = 4, PROF_KINDS = 5 };
@@ -157,5 +172,6 @@ cudaError_t launch_iou_matrix(const double* b1, int n, const double* b2, int m, 
                               cudaStream_t stream);
 cudaError_t launch_reshape_boxes(const BoxOpArgs& a, int boxes_i32, cudaStream_t stream);
 cudaError_t launch_mosaic_merge(const BoxOpArgs& a, cudaStream_t stream);
+cudaError_t launch_ignore_mask(const LossArgs& a, cudaStream_t stream);
 cudaError_t launch_keep_from_index(const int* index, const int* counts, int max_keep, int* keep,
                                    int* n_keep, cudaStream_t stream);

@@ -503,3 +503,44 @@ def mosaic_merge_boxes_batch(boxes, sample_index, crop_xy, image_size, want_f32=
                                         _lib.MEM_HOST, _current_device(), None, _lib.FLAG_SYNC)
     _lib.raise_for_status(rc)
     return out, o32, ocn
+
+
+# ------------------------------------------------------------------------------
+# loss-side ignore mask (reference multigriddet/losses/multigrid_loss.py:494-703)
+# ------------------------------------------------------------------------------
+
+def ignore_masks(y_preds, y_trues, anchors, input_shape, num_classes, ignore_thresh=0.5, eps=1e-7,
+                 sync=True):
+    """Per layer ``(ignore_mask, assigned_anchor_iou, max_iou_map)``, each (B, G, G, 1) float32
+    (``mgd_ignore_mask``).  Lists of NumPy arrays (host) or torch CUDA tensors (device)."""
+    lib = _lib.load()
+    L = len(y_preds)
+    grids = [(int(p.shape[1]), int(p.shape[2])) for p in y_preds]
+    cfg = _lib.make_head_config([np.asarray(a, dtype=np.float32) for a in anchors], num_classes,
+                                input_shape, grids)
+    B = int(y_preds[0].shape[0])
+    outs = []
+    if _is_torch(y_preds[0]):
+        import torch
+        dev = y_preds[0].device
+        yp = [t.to(torch.float32).contiguous() for t in y_preds]
+        yt = [t.to(device=dev, dtype=torch.float32).contiguous() for t in y_trues]
+        for gh, gw in grids:
+            outs.append(tuple(torch.empty((B, gh, gw, 1), dtype=torch.float32, device=dev) for _ in range(3)))
+        ptr = lambda ts: _lib.ptr_array([t.data_ptr() for t in ts])
+        idx = dev.index or 0
+        rc = lib.mgd_ignore_mask(ctypes.byref(cfg), ptr(yp), ptr(yt), B, float(ignore_thresh), float(eps),
+                                 ptr([o[0] for o in outs]), ptr([o[1] for o in outs]), ptr([o[2] for o in outs]),
+                                 _lib.MEM_DEVICE, idx, ctypes.c_void_p(_torch_stream(idx)),
+                                 _lib.FLAG_SYNC if sync else 0)
+    else:
+        yp = [np.ascontiguousarray(np.asarray(t), dtype=np.float32) for t in y_preds]
+        yt = [np.ascontiguousarray(np.asarray(t), dtype=np.float32) for t in y_trues]
+        for gh, gw in grids:
+            outs.append(tuple(np.zeros((B, gh, gw, 1), dtype=np.float32) for _ in range(3)))
+        ptr = lambda ts: _lib.ptr_array([t.ctypes.data for t in ts])
+        rc = lib.mgd_ignore_mask(ctypes.byref(cfg), ptr(yp), ptr(yt), B, float(ignore_thresh), float(eps),
+                                 ptr([o[0] for o in outs]), ptr([o[1] for o in outs]), ptr([o[2] for o in outs]),
+                                 _lib.MEM_HOST, _current_device(), None, _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    return outs

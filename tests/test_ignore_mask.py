@@ -1,0 +1,86 @@
+"""Loss-side ignore mask: reference
+multigriddet/losses/multigrid_loss.py:494-703.
+
+PARITY UNPINNED against the reference: it is TensorFlow graph code, TensorFlow is not
+installed here and no reference test pins its outputs.  The CPU tests check the oracle
+restatement (oracle/loss_oracle.py) against hand-derived properties; the GPU tests check
+the CUDA path against that oracle: IoU maps to 1e-5, masks exactly except on cells whose
+best IoU lies within 1e-5 of the threshold (TF's float32 tanh / sigmoid / exp are not
+promised to match libm bit for bit, so neither side may claim those).
+"""
+import numpy as np
+import pytest
+
+from multigriddet_b200 import synth
+from oracle import loss_oracle as LO
+from oracle import mgd_oracle as O
+
+
+def _inputs(seed, B, N, S, C, noise=0.05):
+    import torch
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(seed, B, N, S, C)
+    y = O.encode_targets(boxes, (S, S), anchors, C)
+    preds = [p.numpy() for p in synth.planted_head_outputs([torch.from_numpy(a) for a in y], 3, seed)]
+    rng = np.random.default_rng(seed)
+    for p in preds:                                        # spread the IoUs away from 1
+        p[..., 0:4] += rng.normal(0, noise, p[..., 0:4].shape).astype(np.float32)
+    return anchors, y, preds
+
+
+def test_oracle_properties():
+    S, C = 160, 20
+    anchors, y, preds = _inputs(0, 3, 8, S, C)
+    for l, (ig, asg, mx) in enumerate(LO.ignore_masks(preds, y, anchors, (S, S))):
+        pos = y[l][..., 4:5] > 0.5
+        assert ig.shape == asg.shape == mx.shape == pos.shape and ig.dtype == np.float32
+        assert not (ig[pos] != 0).any()                    # positives are never ignored
+        assert set(np.unique(ig)) <= {0.0, 1.0}
+        assert np.all(asg[~pos] == 0) and np.all(asg <= mx + 1e-7)
+        assert np.all((mx >= 0) & (mx <= 1.0 + 1e-6))
+        assert np.array_equal(ig[~pos] == 1, mx[~pos] > 0.5)
+    # an image without boxes: every map is zero (multigrid_loss.py:634-642)
+    empty = [np.zeros_like(t[:1]) for t in y]
+    for ig, asg, mx in LO.ignore_masks([p[:1] for p in preds], empty, anchors, (S, S)):
+        assert not ig.any() and not asg.any() and not mx.any()
+    # a prediction that reproduces its own target exactly has IoU 1 with it:
+    # raw xy = 0 activates to tanh(0) + sigmoid(0) = 0.5, raw wh = the stored log ratio
+    t = np.zeros((1, 5, 5, 5 + 3 + C), np.float32)
+    t[0, 2, 3, :5] = [0.5, 0.5, 0.1, -0.2, 1.0]
+    t[0, 2, 3, 5 + 1] = 1.0
+    p = np.zeros_like(t)
+    p[0, 2, 3, 2:4] = [0.1, -0.2]
+    ig, asg, mx = LO.ignore_mask_layer(p, t, anchors[0], (S, S))
+    assert asg[0, 2, 3, 0] == pytest.approx(1.0, abs=1e-6) and ig[0, 2, 3, 0] == 0
+    # the 'ij' meshgrid quirk: the ROW index feeds the x channel
+    t2 = np.zeros_like(t); t2[0, 1, 4, :5] = [0.5, 0.5, 0.0, 0.0, 1.0]; t2[0, 1, 4, 5] = 1.0
+    p2 = np.zeros_like(t)
+    _, _, mx2 = LO.ignore_mask_layer(p2, t2, np.array([[8, 8], [4, 4], [2, 2]], np.float32), (S, S))
+    best = np.unravel_index(np.argmax(mx2[0, ..., 0]), (5, 5))
+    assert best == (1, 4)                                  # same tensor position: the offset is consistent
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,B,N,S,C", [(1, 6, 12, 160, 20), (2, 4, 60, 416, 20), (3, 3, 100, 608, 80)])
+def test_gpu_ignore_mask_matches_oracle(seed, B, N, S, C):
+    import torch
+    from multigriddet_b200 import engine
+    from multigriddet_b200.losses import compute_ignore_mask
+    anchors, y, preds = _inputs(seed, B, N, S, C)
+    ref = LO.ignore_masks(preds, y, anchors, (S, S), ignore_thresh=0.5)
+    for dev in (False, True):
+        yp = [torch.from_numpy(p).cuda() for p in preds] if dev else preds
+        yt = [torch.from_numpy(t).cuda() for t in y] if dev else y
+        got = engine.ignore_masks(yp, yt, anchors, (S, S), C, ignore_thresh=0.5)
+        n_flagged = 0
+        for (ig, asg, mx), (rig, rasg, rmx) in zip(got, ref):
+            if dev:
+                ig, asg, mx = ig.cpu().numpy(), asg.cpu().numpy(), mx.cpu().numpy()
+            np.testing.assert_allclose(mx, rmx, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(asg, rasg, rtol=1e-5, atol=1e-6)
+            sure = np.abs(rmx - 0.5) > 1e-5
+            assert np.array_equal(ig[sure], rig[sure])
+            n_flagged += int(rig.sum())
+        assert n_flagged > 0
+    one = compute_ignore_mask(preds[1], y[1], anchors[1], (S, S))
+    np.testing.assert_allclose(one[2], ref[1][2], rtol=1e-5, atol=1e-6)
