@@ -183,10 +183,27 @@ def raise_for_status(rc: int) -> None:
     raise MgdError(msg)
 
 
+_cfg_cache: dict = {}
+
+
 def make_head_config(anchors, num_classes, input_shape, grid_shapes=None) -> HeadConfig:
     """``anchors``: list of (A_l, 2) arrays; their dtype picks the arithmetic path
-    (float64 only if the caller's anchors are float64, like NumPy promotion)."""
+    (float64 only if the caller's anchors are float64, like NumPy promotion).
+    Memoised on the values (the evaluator builds the same geometry for every image)."""
     arrs = [np.asarray(a) for a in anchors]
+    key = (tuple((a.dtype.str, a.shape, a.tobytes()) for a in arrs), int(num_classes),
+           int(input_shape[0]), int(input_shape[1]),
+           None if grid_shapes is None else tuple((int(g[0]), int(g[1])) for g in grid_shapes))
+    hit = _cfg_cache.get(key)
+    if hit is not None:
+        return hit
+    cfg = _make_head_config(arrs, num_classes, input_shape, grid_shapes)
+    if len(_cfg_cache) < 256:
+        _cfg_cache[key] = cfg
+    return cfg
+
+
+def _make_head_config(arrs, num_classes, input_shape, grid_shapes=None) -> HeadConfig:
     num_layers = len(arrs)
     if not 1 <= num_layers <= MGD_MAX_LAYERS:
         raise ValueError(f"between 1 and {MGD_MAX_LAYERS} layers supported, got {num_layers}")

@@ -81,6 +81,34 @@ __device__ __forceinline__ double clipd(double v, double lo, double hi)
     return v < lo ? lo : (v > hi ? hi : v);
 }
 
+// Approximate pair metric on float32 outer boxes [x1, y1, x2, y2].
+// Returns 1 (suppress), 0 (keep) or -1 (undecided: evaluate the exact formula).
+// Error bound: every coordinate is within eps = 1.2e-7 * L of the float64 one (L = largest
+// coordinate magnitude of the image's boxes).  With iw, ih >= tmin = 1e-3 * L:
+//   |dIoU|        <= 6 eps (1/iw + 1/ih)              <= 1.5e-3
+//   |d dist/diag| <= 8 eps / sqrt(diag), sqrt(diag) >= tmin  =>  <= 1e-3
+// plus a few float32 roundings (1e-6): total < 3e-3, decided only beyond 1e-2.
+__device__ __forceinline__ int approx_verdict(const float4& a, const float4& b, float thr, bool diou,
+                                              float tmin)
+{
+    const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x);
+    const float ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
+    if (!(iw >= tmin && ih >= tmin)) return -1;
+    const float inter = iw * ih;
+    const float uni = ((a.z - a.x) * (a.w - a.y) + (b.z - b.x) * (b.w - b.y)) - inter;
+    float m = __fdividef(inter, uni + 1e-8f);
+    if (diou) {
+        const float dxc = 0.5f * ((a.x + a.z) - (b.x + b.z));
+        const float dyc = 0.5f * ((a.y + a.w) - (b.y + b.w));
+        const float ex = fmaxf(a.z, b.z) - fminf(a.x, b.x);
+        const float ey = fmaxf(a.w, b.w) - fminf(a.y, b.y);
+        m -= __fdividef(dxc * dxc + dyc * dyc, (ex * ex + ey * ey) + 1e-8f);
+    }
+    if (m > thr + 1e-2f) return 1;
+    if (m < thr - 1e-2f) return 0;
+    return -1;                                   // also every NaN
+}
+
 __global__ void __launch_bounds__(kThreads)
 nms_kernel(const __grid_constant__ NmsArgs a)
 {
@@ -94,6 +122,7 @@ nms_kernel(const __grid_constant__ NmsArgs a)
     __shared__ unsigned long long c_mask[kChunk];
     __shared__ int c_new[kChunk];
     __shared__ int s_kept, s_new;
+    __shared__ unsigned s_scale;              // bits of the largest coordinate magnitude (float)
     extern __shared__ __align__(16) unsigned char dyn[];
     const int b = blockIdx.x;
     unsigned char* kept_mem = a.kept_scratch ? a.kept_scratch + (size_t)b * a.kept_scratch_stride : dyn;
@@ -150,8 +179,18 @@ nms_kernel(const __grid_constant__ NmsArgs a)
         }
     }
     // ---- 1. sort ---------------------------------------------------------------
-    if (tid == 0) { s_kept = 0; s_new = 0; }
+    if (tid == 0) { s_kept = 0; s_new = 0; s_scale = 0u; }
     __syncthreads();
+    {
+        // coordinate scale of this image's boxes, for the float32 level of the pair test
+        float sc = 0.f;
+        for (int i = tid; i < M; i += kThreads) {
+            const float4 o = outer_box(boxes[i]);
+            sc = fmaxf(sc, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+        }
+        // non-negative floats order like their bit patterns; NaN (0x7fc00000) and inf sort on top
+        atomicMax(&s_scale, __float_as_uint(sc));
+    }
     for (int k = 2; k <= mpad; k <<= 1) {
         for (int jj = k >> 1; jj > 0; jj >>= 1) {
             for (int i = tid; i < mpad; i += kThreads) {
@@ -168,6 +207,11 @@ nms_kernel(const __grid_constant__ NmsArgs a)
     }
 
     // ---- 2. chunked greedy pass ----------------------------------------------------
+    // pair test in three levels like nms_warp_kernel: outer-box overlap, approximate float32
+    // metric (decides when further than 1e-2 from the threshold), exact float64 formula
+    const float scale_f = __uint_as_float(s_scale);
+    const float tmin = scale_f < 3.0e38f ? 1e-3f * scale_f : __int_as_float(0x7f800000);
+    const float thr_f = (float)a.thr;
     for (int c0 = 0; c0 < M; c0 += kChunk) {
         const int kept = s_kept;
         if (kept >= a.max_boxes) break;
@@ -204,7 +248,8 @@ nms_kernel(const __grid_constant__ NmsArgs a)
                 if (a.per_class && k_cls[k] != ccls) continue;
                 const float4 ko = k_out[k];
                 if (pretest && (ko.z <= co.x || co.z <= ko.x || ko.w <= co.y || co.w <= ko.y)) continue;
-                dead = suppresses(k_box[k], cb, a.thr, diou);
+                const int v = approx_verdict(ko, co, thr_f, diou, tmin);
+                dead = v < 0 ? suppresses(k_box[k], cb, a.thr, diou) : v != 0;
             }
             if (dead) c_alive[mem] = 0;
         }
@@ -219,7 +264,8 @@ nms_kernel(const __grid_constant__ NmsArgs a)
                 if (a.per_class && c_cls[i] != ccls) continue;
                 const float4 io = c_out[i];
                 if (pretest && (io.z <= co.x || co.z <= io.x || io.w <= co.y || co.w <= io.y)) continue;
-                if (suppresses(c_box[i], cb, a.thr, diou)) atomicOr(&c_mask[i], 1ull << mem);
+                const int v = approx_verdict(io, co, thr_f, diou, tmin);
+                if (v < 0 ? suppresses(c_box[i], cb, a.thr, diou) : v != 0) atomicOr(&c_mask[i], 1ull << mem);
             }
         }
         __syncthreads();
@@ -329,34 +375,6 @@ __host__ __device__ inline size_t nms_warp_bytes(int cap, int kept_cap)
     // keys / greedy state | sorted position u16[cap]
     const size_t b = nms_warp_key_bytes(cap, kept_cap) + (size_t)cap * 2;
     return (b + 15) & ~(size_t)15;
-}
-
-// Approximate pair metric on float32 outer boxes [x1, y1, x2, y2].
-// Returns 1 (suppress), 0 (keep) or -1 (undecided: evaluate the exact formula).
-// Error bound: every coordinate is within eps = 1.2e-7 * L of the float64 one (L = largest
-// coordinate magnitude of the image's boxes).  With iw, ih >= tmin = 1e-3 * L:
-//   |dIoU|        <= 6 eps (1/iw + 1/ih)              <= 1.5e-3
-//   |d dist/diag| <= 8 eps / sqrt(diag), sqrt(diag) >= tmin  =>  <= 1e-3
-// plus a few float32 roundings (1e-6): total < 3e-3, decided only beyond 1e-2.
-__device__ __forceinline__ int approx_verdict(const float4& a, const float4& b, float thr, bool diou,
-                                              float tmin)
-{
-    const float iw = fminf(a.z, b.z) - fmaxf(a.x, b.x);
-    const float ih = fminf(a.w, b.w) - fmaxf(a.y, b.y);
-    if (!(iw >= tmin && ih >= tmin)) return -1;
-    const float inter = iw * ih;
-    const float uni = ((a.z - a.x) * (a.w - a.y) + (b.z - b.x) * (b.w - b.y)) - inter;
-    float m = __fdividef(inter, uni + 1e-8f);
-    if (diou) {
-        const float dxc = 0.5f * ((a.x + a.z) - (b.x + b.z));
-        const float dyc = 0.5f * ((a.y + a.w) - (b.y + b.w));
-        const float ex = fmaxf(a.z, b.z) - fminf(a.x, b.x);
-        const float ey = fmaxf(a.w, b.w) - fminf(a.y, b.y);
-        m -= __fdividef(dxc * dxc + dyc * dyc, (ex * ex + ey * ey) + 1e-8f);
-    }
-    if (m > thr + 1e-2f) return 1;
-    if (m < thr - 1e-2f) return 0;
-    return -1;                                   // also every NaN
 }
 
 // bit k set <=> kept box k0 + k may overlap the lane's box (and shares its class in
@@ -1087,7 +1105,13 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
     // every image with <= 1024 candidates, nms_kernel the rest
     static int env_off = -1;
     if (env_off < 0) { const char* e = getenv("MGD_NMS_NO_WARP_KERNEL"); env_off = e ? atoi(e) : 0; }
-    if (a.cand && nms_warp_bytes(kWarpCapLarge, a.max_boxes) <= 32 * 1024 && !env_off) {
+    // A warp per image wins on throughput (4 096 images in one resident wave: 0.54 ms), a CTA
+    // per image on latency (103 us against 206 us for one image).  Measured crossover at COCO
+    // 608, ~770 candidates per image: 1 536 images 372 vs 389 us, 2 048 images 469 vs 413 us.
+    // Small batches (the evaluator's one image per call) therefore take the CTA kernel.
+    const char* e_min = getenv("MGD_NMS_WARP_MIN_IMAGES");      // (read per launch: tests force either kernel)
+    const int warp_min = e_min ? atoi(e_min) : 1664;
+    if (a.cand && nms_warp_bytes(kWarpCapLarge, a.max_boxes) <= 32 * 1024 && !env_off && a.B >= warp_min) {
         auto run = [&](auto kernel, int cap, int min_count) -> cudaError_t {
             static int env_pad = -1;
             if (env_pad < 0) { const char* e = getenv("MGD_NMS_SMEM_PAD"); env_pad = e ? atoi(e) : 0; }

@@ -2,7 +2,7 @@
 import os, sys, time, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) == 1:
-    for mode, mb in (("1", 128), ("1", 32), ("1", 512)):
+    for mode, mb in (("0", 128), ("0", 64), ("0", 32), ("0", 16)):
         env = dict(os.environ, MGD_HOST_ZEROCOPY=mode if mode != "raw" else "0", MGD_HOST_CHUNK_MB=str(mb))
         subprocess.run([sys.executable, __file__, mode], env=env)
     sys.exit(0)

@@ -40,8 +40,18 @@ def test_encode_known_answers_through_the_dropin():
     G.assert_encode_matches([a[None] for a in y], G.dense_y_true(z, prefix="c0_"), exact_floats=False)
 
 
+@pytest.fixture(params=["cta_per_image", "warp_per_image"])
+def nms_kernel_choice(request):
+    """Both NMS kernels against the reference's golden detections (the library would pick
+    the CTA-per-image kernel for batches this small)."""
+    import os
+    os.environ["MGD_NMS_WARP_MIN_IMAGES"] = "1" if request.param == "warp_per_image" else "1000000"
+    yield request.param
+    del os.environ["MGD_NMS_WARP_MIN_IMAGES"]
+
+
 @pytest.mark.parametrize("path", G.files("decode"))
-def test_postprocess_against_reference_golden(path):
+def test_postprocess_against_reference_golden(path, nms_kernel_choice):
     z = np.load(path)
     anchors = G.anchors_of(z)
     S, C = int(z["S"]), int(z["C"])

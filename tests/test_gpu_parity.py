@@ -184,8 +184,18 @@ DECODE_CASES = [
 ]
 
 
+@pytest.fixture(params=["cta_per_image", "warp_per_image"])
+def nms_kernel_choice(request):
+    """The library picks the NMS kernel by batch size (a CTA per image below ~900 images, a
+    warp per image above); the parity cases are small, so force each kernel in turn."""
+    import os
+    os.environ["MGD_NMS_WARP_MIN_IMAGES"] = "1" if request.param == "warp_per_image" else "1000000"
+    yield request.param
+    del os.environ["MGD_NMS_WARP_MIN_IMAGES"]
+
+
 @pytest.mark.parametrize("S,C,B,N,dt,method,per_class,conf,thr,mixed", DECODE_CASES)
-def test_decode_nms_matches_oracle(c_oracle, S, C, B, N, dt, method, per_class, conf, thr, mixed):
+def test_decode_nms_matches_oracle(c_oracle, nms_kernel_choice, S, C, B, N, dt, method, per_class, conf, thr, mixed):
     anchors = synth.coco_anchors(dt)
     preds = _planted(21, B, S, C, N, anchors, c_oracle)
     shapes = synth.image_shapes(4, B, mixed=mixed, square=(S, S))
@@ -202,7 +212,7 @@ def test_decode_nms_matches_oracle(c_oracle, S, C, B, N, dt, method, per_class, 
     assert got["stats"]["n_detections"] == int(ref["counts"].sum())
 
 
-def test_decode_sigmoid_mode_and_no_rescore(c_oracle):
+def test_decode_sigmoid_mode_and_no_rescore(c_oracle, nms_kernel_choice):
     S, C, B = 608, 80, 6
     anchors = synth.coco_anchors(np.float32)
     preds = _planted(8, B, S, C, 80, anchors, c_oracle)
@@ -215,7 +225,7 @@ def test_decode_sigmoid_mode_and_no_rescore(c_oracle):
         assert same == B and bits_off == 0
 
 
-def test_decode_dense_random_worst_case(c_oracle):
+def test_decode_dense_random_worst_case(c_oracle, nms_kernel_choice):
     """Every cell is a candidate (7581 per image): global-memory sort path, early exit."""
     S, C, B = 608, 80, 3
     anchors = synth.coco_anchors(np.float32)
@@ -375,7 +385,7 @@ def test_decode_large_max_boxes_paths(c_oracle, max_boxes):
     assert same == B and bits_off == 0
 
 
-def test_decode_mixed_candidate_counts_one_launch(c_oracle):
+def test_decode_mixed_candidate_counts_one_launch(c_oracle, nms_kernel_choice):
     """Images with 0, a few, ~500 and ~7500 candidates in one batch: every NMS tier
     (warp kernel phases, CTA kernel with shared / global sort) runs in the same call."""
     import torch
@@ -514,7 +524,7 @@ def test_wbf_matches_oracle(c_oracle):
             np.testing.assert_allclose(got["boxes_xywh"][b, :k], ref[b]["boxes_xywh"], rtol=RTOL, atol=1e-4)
 
 
-def test_decode_equal_scores_follow_the_cell_index_rule(c_oracle):
+def test_decode_equal_scores_follow_the_cell_index_rule(c_oracle, nms_kernel_choice):
     """Exactly equal scores: lower cell index first, on the warp-per-image NMS path
     (<= 1024 candidates).  Rows are duplicated across cells so whole runs of candidates tie."""
     S, C, B = 608, 80, 6
