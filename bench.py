@@ -406,13 +406,34 @@ def run_b200(args):
             return engine.decode_nms(np_preds, hw_np, (S, S), anchors, C,
                                      want=("boxes_xyxy", "scores", "classes"), **POST)
 
-        def e2e_step():
+        def e2e_concurrent():
             fe, fd = pool.submit(e2e_encode), pool.submit(e2e_decode)
             fe.result()
             return fd.result()
 
-        e2e_step()
-        e2e_step()
+        def e2e_sequential():
+            e2e_encode()
+            return e2e_decode()
+
+        # How to issue the two independent calls is the caller's choice and depends on the
+        # host: alone on its link a GPU moves both directions at once (concurrent wins); with
+        # several GPUs saturating the host's memory interface the directions only get in each
+        # other's way (measured on a 4-GPU box: 77 ms back to back, 123 ms concurrent).  Time
+        # both on warm-up steps, all ranks together, and use the faster one.
+        trial = {}
+        for name, fn in (("concurrent", e2e_concurrent), ("sequential", e2e_sequential)):
+            fn()
+            barrier()
+            tt = time.perf_counter()
+            fn()
+            fn()
+            torch.cuda.synchronize()
+            tv = torch.tensor([time.perf_counter() - tt], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            trial[name] = float(tv.item()) / 2
+        issue = min(trial, key=trial.get)
+        e2e_step = e2e_concurrent if issue == "concurrent" else e2e_sequential
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -457,8 +478,10 @@ def run_b200(args):
                         "frac": dt_link / (dt / args.e2e_steps),
                         "note": "peak = the same bytes as two bare bulk copies (H2D || D2H) on this "
                                 "box, measured right after; rank 0's link"},
-               "note": "pinned host buffers; encode and decode calls issued concurrently from two "
-                       "host threads (both PCIe directions busy); host<->device copies inside"}
+               "issue": issue, "issue_trial_ms": {k: v * 1e3 for k, v in trial.items()},
+               "note": "pinned host buffers, host<->device copies inside; the two calls of a step are "
+                       "issued concurrently from two host threads or back to back, whichever the "
+                       "warm-up steps found faster on this host (see issue / issue_trial_ms)"}
         pool.shutdown()
         del h_preds, h_y, np_preds, np_y
 
