@@ -109,7 +109,60 @@ __device__ __forceinline__ int approx_verdict(const float4& a, const float4& b, 
     return -1;                                   // also every NaN
 }
 
-__global__ void __launch_bounds__(kThreads)
+// Top-K window for images with more candidates than the shared-memory sort holds.  Greedy NMS
+// visits candidates in descending score and stops at max_boxes kept, so a prefix of the
+// order is usually all it ever looks at.  A 1 024-bin histogram of the float32 score bits
+// (8 bins per octave) gives the lowest bin T such that the candidates in bins >= T number
+// at most kSortSmem; exactly those are gathered (unsorted) into key / val.  Every selected
+// candidate outranks every other one, so NMS on the selection is a prefix of the full
+// result: if it ends with max_boxes kept (or everything was selected) it IS the result,
+// otherwise the caller repeats with all candidates.  Returns the number selected (uniform).
+__device__ int select_top_window(const Cand* cand, int M, unsigned long long* key,
+                                 unsigned long long* val, int* hist, int* scan, int* s_n, int* s_bin)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 1024; i += kThreads) hist[i] = 0;
+    if (tid == 0) { *s_n = 0; *s_bin = 1024; }
+    __syncthreads();
+    for (int i = tid; i < M; i += kThreads)
+        atomicAdd(&hist[min(__float_as_uint(cand[i].score) >> 20, 1023u)], 1);
+    __syncthreads();
+    // suffix sums over threads: thread t owns bins [4t, 4t + 4)
+    const int mine = hist[4 * tid] + hist[4 * tid + 1] + hist[4 * tid + 2] + hist[4 * tid + 3];
+    scan[tid] = mine;
+    __syncthreads();
+    for (int off = 1; off < kThreads; off <<= 1) {
+        const int v = scan[tid] + (tid + off < kThreads ? scan[tid + off] : 0);
+        __syncthreads();
+        scan[tid] = v;
+        __syncthreads();
+    }
+    const int above = scan[tid] - mine;                  // candidates in bins of higher threads
+    if (above <= kSortSmem && scan[tid] > kSortSmem) {   // the boundary lies inside my four bins
+        int acc = above, bin = 4 * tid + 4;
+        for (int q = 3; q >= 0; --q) {
+            if (acc + hist[4 * tid + q] > kSortSmem) break;
+            acc += hist[4 * tid + q];
+            bin = 4 * tid + q;
+        }
+        *s_bin = bin;                                    // lowest bin that still fits
+    }
+    __syncthreads();
+    const unsigned lo = (unsigned)*s_bin;
+    __syncthreads();                                     // hist (aliases val) is dead from here
+    for (int i = tid; i < M; i += kThreads) {
+        const Cand cd = cand[i];
+        if (min(__float_as_uint(cd.score) >> 20, 1023u) >= lo) {
+            const int slot = atomicAdd(s_n, 1);
+            key[slot] = score_key((double)cd.score);
+            val[slot] = ((unsigned long long)(unsigned)cd.index << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    return *s_n;
+}
+
+__global__ void __launch_bounds__(kThreads, 3)
 nms_kernel(const __grid_constant__ NmsArgs a)
 {
     __shared__ unsigned long long s_key[kSortSmem];
@@ -138,59 +191,73 @@ nms_kernel(const __grid_constant__ NmsArgs a)
                                : reinterpret_cast<const BoxD*>(a.in_boxes);
     const bool diou = a.use_diou != 0;
 
+    __shared__ uint64_t s_tab[MGD_EXP2F_N];
+    __shared__ int s_scan[kThreads];
+    __shared__ int s_sel_n, s_sel_bin;
+    if (cand) {
+        if (tid < MGD_EXP2F_N) s_tab[tid] = mgd_exp2f_tab[tid];
+        __syncthreads();
+    }
+    // decode mode with more candidates than the shared-memory sort holds: top-K window first
+    bool window = cand != nullptr && M > kSortSmem;
+  pass_again: ;
     // ---- 0. boxes + sort keys, one thread per candidate -----------------------------
+    int n_in = M;                                   // candidates taking part in this pass
+    if (window)
+        n_in = select_top_window(cand, M, s_key, s_val, reinterpret_cast<int*>(s_val), s_scan,
+                                 &s_sel_n, &s_sel_bin);
     int mpad = 2;
-    while (mpad < M) mpad <<= 1;
+    while (mpad < n_in) mpad <<= 1;
     unsigned long long* key = s_key;
     unsigned long long* val = s_val;
     if (mpad > kSortSmem) {
         key = a.sort_scratch + (size_t)b * 2 * a.sort_scratch_stride;
         val = key + a.sort_scratch_stride;
     }
-    if (cand) {
-        __shared__ uint64_t s_tab[MGD_EXP2F_N];
-        if (tid < MGD_EXP2F_N) s_tab[tid] = mgd_exp2f_tab[tid];
-        __syncthreads();
-        const HeadGeom& g = a.g;
-        const int ih = a.image_hw ? a.image_hw[2 * b] : a.in_h;
-        const int iw = a.image_hw ? a.image_hw[2 * b + 1] : a.in_w;
-        const Letterbox lb = letterbox_consts(g.in_h, g.in_w, ih, iw);
-        BoxD* out = a.boxes + (size_t)b * a.cap;
-        for (int i = tid; i < M; i += kThreads) {
-            const Cand cd = cand[i];
-            int layer = 0;
-            while (layer + 1 < g.L && cd.index >= g.cell_off[layer + 1]) ++layer;
-            const int cell = cd.index - g.cell_off[layer];
-            const int rr = cell / g.gw[layer], cc = cell - rr * g.gw[layer];
-            BoxD bx;
-            decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 0, s_tab, bx.x, bx.w);
-            decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 1, s_tab, bx.y, bx.h);
-            out[i] = bx;
-        }
-    }
-    for (int i = tid; i < mpad; i += kThreads) {
-        if (i < M) {
+    if (!window) {
+        for (int i = tid; i < n_in; i += kThreads) {
             const double sc = cand ? (double)cand[i].score : a.in_scores[i];
             const unsigned idx = cand ? (unsigned)cand[i].index : (unsigned)i;
             key[i] = score_key(sc);
             val[i] = ((unsigned long long)idx << 32) | (unsigned)i;
-        } else {
-            key[i] = ~0ull; val[i] = ~0ull;
         }
     }
-    // ---- 1. sort ---------------------------------------------------------------
+    for (int i = n_in + tid; i < mpad; i += kThreads) { key[i] = ~0ull; val[i] = ~0ull; }
     if (tid == 0) { s_kept = 0; s_new = 0; s_scale = 0u; }
     __syncthreads();
     {
-        // coordinate scale of this image's boxes, for the float32 level of the pair test
+        // boxes of the participating candidates (rebuilt from the raw logits in decode mode)
+        // and the coordinate scale for the float32 level of the pair test
+        const HeadGeom& g = a.g;
+        const int ih = a.image_hw ? a.image_hw[2 * b] : a.in_h;
+        const int iw = a.image_hw ? a.image_hw[2 * b + 1] : a.in_w;
+        Letterbox lb;
+        if (cand) lb = letterbox_consts(g.in_h, g.in_w, ih, iw);
+        BoxD* out = cand ? a.boxes + (size_t)b * a.cap : nullptr;
         float sc = 0.f;
-        for (int i = tid; i < M; i += kThreads) {
-            const float4 o = outer_box(boxes[i]);
+        for (int i = tid; i < n_in; i += kThreads) {
+            const int pos = (int)(val[i] & 0xffffffffu);
+            BoxD bx;
+            if (cand) {
+                const Cand cd = cand[pos];
+                int layer = 0;
+                while (layer + 1 < g.L && cd.index >= g.cell_off[layer + 1]) ++layer;
+                const int cell = cd.index - g.cell_off[layer];
+                const int rr = cell / g.gw[layer], cc = cell - rr * g.gw[layer];
+                decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 0, s_tab, bx.x, bx.w);
+                decode_axis_of(g, cd.t, layer, cd.anchor, rr, cc, &lb, 1, s_tab, bx.y, bx.h);
+                out[pos] = bx;
+            } else {
+                bx = boxes[pos];
+            }
+            const float4 o = outer_box(bx);
             sc = fmaxf(sc, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
         }
         // non-negative floats order like their bit patterns; NaN (0x7fc00000) and inf sort on top
         atomicMax(&s_scale, __float_as_uint(sc));
     }
+    // ---- 1. sort ---------------------------------------------------------------
+    __syncthreads();
     for (int k = 2; k <= mpad; k <<= 1) {
         for (int jj = k >> 1; jj > 0; jj >>= 1) {
             for (int i = tid; i < mpad; i += kThreads) {
@@ -212,10 +279,10 @@ nms_kernel(const __grid_constant__ NmsArgs a)
     const float scale_f = __uint_as_float(s_scale);
     const float tmin = scale_f < 3.0e38f ? 1e-3f * scale_f : __int_as_float(0x7f800000);
     const float thr_f = (float)a.thr;
-    for (int c0 = 0; c0 < M; c0 += kChunk) {
+    for (int c0 = 0; c0 < n_in; c0 += kChunk) {
         const int kept = s_kept;
         if (kept >= a.max_boxes) break;
-        const int n = min(kChunk, M - c0);
+        const int n = min(kChunk, n_in - c0);
         if (tid < kChunk) {
             c_mask[tid] = 0ull;
             c_alive[tid] = tid < n;
@@ -315,6 +382,13 @@ nms_kernel(const __grid_constant__ NmsArgs a)
             if (a.out_index) a.out_index[o] = cand ? cand[pos].index : pos;
         }
         __syncthreads();
+    }
+
+    // the window ran out before max_boxes were kept: the answer needs candidates outside it
+    if (window && s_kept < a.max_boxes && n_in < M) {
+        __syncthreads();
+        window = false;
+        goto pass_again;
     }
 
     // ---- padding + counts ----------------------------------------------------------

@@ -633,3 +633,25 @@ def test_bench_sized_batch_and_internal_chunk_boundaries(c_oracle):
             assert np.array_equal(got2[k].cpu().numpy(), got[k][:500]), k
     finally:
         del os.environ["MGD_ENCODE_CHUNK_IMAGES"], os.environ["MGD_DECODE_CHUNK_IMAGES"]
+
+
+def test_nms_top_window_and_its_fallback(c_oracle):
+    """Images with more candidates than the shared-memory sort holds (2 048) first run NMS on
+    a top-of-the-order window; when that window cannot fill max_boxes the kernel repeats with
+    every candidate.  Dense random heads (every cell a candidate) hit both outcomes:
+    max_boxes = 100 is filled inside the window, max_boxes = 3 000 is not; a high NMS overlap
+    tolerance (threshold 1.0: nothing is ever suppressed... except identical boxes) and a
+    very low one stress the early exit."""
+    S, C, B = 608, 80, 3
+    anchors = synth.coco_anchors(np.float32)
+    rng = np.random.default_rng(8)
+    preds = [rng.normal(0, 1, (B, g, g, 88)).astype(np.float32) for g in (19, 38, 76)]
+    shapes = synth.image_shapes(5, B, mixed=True)
+    for max_boxes, thr, method in ((100, 0.45, "diou"), (3000, 0.45, "diou"), (2500, 1.0, "standard"),
+                                   (300, 0.05, "standard"), (7581, 0.3, "diou")):
+        kw = dict(max_boxes=max_boxes, confidence=0.001, nms_threshold=thr, nms_method=method)
+        ref = c_oracle.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+        got = engine.decode_nms(preds, shapes, (S, S), anchors, C, return_stats=True, **kw)
+        assert got["stats"]["n_candidates"] > 2048 * B
+        same, bits_off = _compare_detections(got, ref, B)
+        assert same == B and bits_off == 0, (max_boxes, thr, method)
