@@ -647,11 +647,14 @@ def test_nms_top_window_and_its_fallback(c_oracle):
     rng = np.random.default_rng(8)
     preds = [rng.normal(0, 1, (B, g, g, 88)).astype(np.float32) for g in (19, 38, 76)]
     shapes = synth.image_shapes(5, B, mixed=True)
-    for max_boxes, thr, method in ((100, 0.45, "diou"), (3000, 0.45, "diou"), (2500, 1.0, "standard"),
-                                   (300, 0.05, "standard"), (7581, 0.3, "diou")):
-        kw = dict(max_boxes=max_boxes, confidence=0.001, nms_threshold=thr, nms_method=method)
+    for max_boxes, thr, method, per_class in ((100, 0.45, "diou", False), (3000, 0.45, "diou", False),
+                                              (2500, 1.0, "standard", False), (300, 0.05, "standard", False),
+                                              (7581, 0.3, "diou", False), (100, 0.3, "diou", True),
+                                              (4000, 0.2, "standard", True)):
+        kw = dict(max_boxes=max_boxes, confidence=0.001, nms_threshold=thr, nms_method=method,
+                  per_class=per_class)
         ref = c_oracle.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
         got = engine.decode_nms(preds, shapes, (S, S), anchors, C, return_stats=True, **kw)
         assert got["stats"]["n_candidates"] > 2048 * B
         same, bits_off = _compare_detections(got, ref, B)
-        assert same == B and bits_off == 0, (max_boxes, thr, method)
+        assert same == B and bits_off == 0, (max_boxes, thr, method, per_class)
