@@ -415,7 +415,15 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
         // counts[nb], counts[nb+1]: the work counters of the two warp-per-image NMS launches
         CUDA_TRY(al.get(&d.counts, (size_t)(nb + 2) * sizeof(int)));
         CUDA_TRY(cudaMemsetAsync(d.counts, 0, (size_t)(nb + 2) * sizeof(int), stream));
-        CUDA_TRY(launch_decode(d, num_sms, stream));
+        {
+            const cudaError_t e = launch_decode(d, num_sms, stream);
+            if (e == cudaErrorInvalidConfiguration) {
+                cudaGetLastError();
+                return fail(MGD_ERR_UNSUPPORTED, "head too wide for the decode kernel: %d channels per "
+                            "cell (at most ~1750 are supported)", g.D[0]);
+            }
+            CUDA_TRY(e);
+        }
 
         NmsArgs n;
         memset(&n, 0, sizeof(n));

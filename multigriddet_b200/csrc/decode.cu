@@ -177,7 +177,7 @@ __device__ __noinline__ void flush_pool(const DecodeArgs& a, const WarpPool& poo
 // kFast: every layer has A == 3 anchors, D % 4 == 0 and 16-byte aligned tensors:
 // 16-byte loads for level 1, TMA bulk copies into the pool, float4 pool reads.
 template <bool kFast, int kPoolRows>
-__global__ void __launch_bounds__(kThreads, kPoolRows >= 32 ? 2 : (kPoolRows >= 24 ? 3 : 4))
+__global__ void __launch_bounds__(kThreads, kPoolRows >= 32 ? 2 : (kPoolRows >= 24 ? 3 : (kPoolRows >= 16 ? 4 : 2)))
 decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -404,11 +404,13 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
     static int env_pool = -1;
     if (env_pool < 0) { const char* e = getenv("MGD_DECODE_POOL_ROWS"); env_pool = e ? atoi(e) : 0; }
     int pool_rows = env_pool == 32 || env_pool == 24 || env_pool == 16 ? env_pool : 32;
+    // wide heads (hundreds of classes): smaller pools, down to 4 rows per warp (D <= ~1750)
     while (pool_rows > 16 && (size_t)kWarpsPerCta * pool_rows * stride * sizeof(float) > 200 * 1024) pool_rows -= 8;
+    while (pool_rows > 4 && (size_t)kWarpsPerCta * pool_rows * stride * sizeof(float) > 200 * 1024) pool_rows /= 2;
     const size_t smem = (size_t)kWarpsPerCta * pool_rows * stride * sizeof(float);
-    if (smem > 220 * 1024) return cudaErrorInvalidValue;
+    if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;     // reported as MGD_ERR_UNSUPPORTED
     int ctas_per_sm = (int)((224 * 1024) / (smem + 2048));
-    const int reg_limit = pool_rows >= 32 ? 2 : (pool_rows >= 24 ? 3 : 4);
+    const int reg_limit = pool_rows >= 32 ? 2 : (pool_rows >= 24 ? 3 : (pool_rows >= 16 ? 4 : 2));
     if (ctas_per_sm > reg_limit) ctas_per_sm = reg_limit;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     long long blocks = 0;
@@ -428,11 +430,15 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
     if (fast) {
         if (pool_rows == 32) err = run(decode_compact_kernel<true, 32>);
         else if (pool_rows == 24) err = run(decode_compact_kernel<true, 24>);
-        else err = run(decode_compact_kernel<true, 16>);
+        else if (pool_rows == 16) err = run(decode_compact_kernel<true, 16>);
+        else if (pool_rows == 8) err = run(decode_compact_kernel<true, 8>);
+        else err = run(decode_compact_kernel<true, 4>);
     } else {
         if (pool_rows == 32) err = run(decode_compact_kernel<false, 32>);
         else if (pool_rows == 24) err = run(decode_compact_kernel<false, 24>);
-        else err = run(decode_compact_kernel<false, 16>);
+        else if (pool_rows == 16) err = run(decode_compact_kernel<false, 16>);
+        else if (pool_rows == 8) err = run(decode_compact_kernel<false, 8>);
+        else err = run(decode_compact_kernel<false, 4>);
     }
     if (err != cudaSuccess) return err;
     prof_mark_end(PROF_DECODE_COMPACT, stream);

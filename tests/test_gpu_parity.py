@@ -658,3 +658,28 @@ def test_nms_top_window_and_its_fallback(c_oracle):
         assert got["stats"]["n_candidates"] > 2048 * B
         same, bits_off = _compare_detections(got, ref, B)
         assert same == B and bits_off == 0, (max_boxes, thr, method, per_class)
+
+
+@pytest.mark.parametrize("C,ok", [(365, True), (1203, True), (4000, False)])
+def test_wide_heads(c_oracle, C, ok):
+    """Hundreds / thousands of classes (Objects365, LVIS): the decode kernel shrinks its
+    row pools; beyond ~1 750 channels it reports MGD_ERR_UNSUPPORTED instead of a CUDA error.
+    The encoder has no such limit."""
+    S, B, N = 160, 3, 12
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(12, B, N, S, C)
+    got = engine.encode_targets(boxes, (S, S), anchors, C)
+    ref = c_oracle.encode_targets(boxes, (S, S), anchors, C)
+    _assert_encode_equal(got, ref)
+    import torch
+    preds = [p.numpy() for p in synth.planted_head_outputs([torch.from_numpy(y) for y in ref], 3, 12)]
+    kw = dict(max_boxes=50, confidence=0.01, nms_threshold=0.45, nms_method="diou")
+    if not ok:
+        with pytest.raises(NotImplementedError):
+            engine.decode_nms(preds, (S, S), (S, S), anchors, C, **kw)
+        return
+    r = c_oracle.decode_nms(preds, [(S, S)], (S, S), anchors, C, **kw)
+    g = engine.decode_nms(preds, (S, S), (S, S), anchors, C, **kw)
+    assert int(r["counts"].sum()) > 0
+    same, bits_off = _compare_detections(g, r, B)
+    assert same == B and bits_off == 0
