@@ -31,7 +31,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "encode+decode/NMS images/sec, COCO 608x608"
+def _baseline_metric():
+    """The metric string of BASELINE.json, verbatim (the driver matches lines on it)."""
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json"), encoding="utf-8") as fh:
+            return str(json.load(fh)["metric"])
+    except Exception:
+        return "encode+decode/NMS images/sec, COCO 608\u00d7608, 1\u20138 B200; % HBM peak"
+
+
+METRIC = _baseline_metric()
 UNIT = "images/s"
 S, C, A, NBOX = 608, 80, 3, 100
 CELLS = 19 * 19 + 38 * 38 + 76 * 76                    # 7581
