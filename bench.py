@@ -48,6 +48,8 @@ D = 5 + A + C                                           # 88
 BYTES_ENCODE = CELLS * D * 4 + NBOX * 5 * 4             # y_true written + boxes read
 BYTES_DECODE = CELLS * D * 4 + 100 * (32 + 16 + 8 + 4 + 4) + 4
 POST = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method="diou")
+WORKLOAD = ("COCO 80c 608x608 (grids 19/38/76, 88 ch): encode <=100 boxes/img + decode/DIoU-NMS "
+            "(conf 0.001, thr 0.45, max 100), planted head outputs, mixed letterbox shapes")
 
 
 def parse():
@@ -173,7 +175,7 @@ def _cpu_worker(args):
     t0 = time.perf_counter()
     O.encode_targets(boxes, (S, S), anchors, C)
     t1 = time.perf_counter()
-    O.postprocess_batch(preds, np.tile(np.array([[S, S]]), (boxes.shape[0], 1)), (S, S),
+    O.postprocess_batch(preds, synth.image_shapes(0, boxes.shape[0], mixed=True), (S, S),
                         anchors, C, **POST)
     t2 = time.perf_counter()
     return t1 - t0, t2 - t1
@@ -215,9 +217,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "COCO 80c 608x608 encode (<=100 boxes/img) + decode/DIoU-NMS "
-                               "(conf 0.001, thr 0.45, max 100), planted head outputs",
-                   "images_per_step": n_images},
+        "config": {"workload": WORKLOAD, "images_per_step": n_images},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n_images} images/step sharded over {cores} processes "
                                    "(oracle/mgd_oracle.py: NumPy port of the reference path; the "
@@ -531,10 +531,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "COCO 80c 608x608 (grids 19/38/76, 88 ch): encode <=100 boxes/img "
-                                   "+ decode/DIoU-NMS (conf 0.001, thr 0.45, max 100), planted head "
-                                   "outputs, mixed letterbox shapes",
-                       "images_per_rank_per_step": B, "sharding": f"image-sharded x{world}, no collective",
+            "config": {"workload": WORKLOAD, "images_per_rank_per_step": B, "sharding": f"image-sharded x{world}, no collective",
                        "streams": 1, "cpus_bound_to_rank": numa,
                        "l2": "inputs larger than L2 (2 x 2.67 MB/image x batch), no flush needed"},
             "roofline": roofline, "kernels": kernels, "two_stream": overlap,
