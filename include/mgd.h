@@ -316,7 +316,9 @@ MGD_API int mgd_iou_matrix(const double *boxes1, int n, const double *boxes2, in
 
 /*
  * Deferred device-side status of asynchronous calls issued by this thread on
- * `device` (class-range errors found by the encode kernel).  Synchronises `stream`.
+ * `device` (class-range errors found by the encode kernel).  Synchronises `stream`, then
+ * reads and clears the thread's status word (asynchronous calls OR their bits into one
+ * persistent device word per thread and device; nothing accumulates if it is never polled).
  */
 MGD_API int mgd_poll_status(int device, void *stream);
 

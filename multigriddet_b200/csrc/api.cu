@@ -316,16 +316,28 @@ int decode_chunk_images(const HeadGeom& g, int batch)
 }
 
 // ---- deferred device-side status of asynchronous encode calls ---------------------
-struct Pending { int* host; int device; };
-thread_local std::vector<Pending> t_pending;
-thread_local std::vector<int*> t_free_slots;
+// One persistent device word per (host thread, device): every asynchronous call ORs its
+// status bits into it (atomicOr in the assign kernel), mgd_poll_status reads it back and
+// clears it.  Nothing is allocated per call and nothing accumulates if the caller never
+// polls.
+struct DeferredStatus {
+    int* word[64] = {};
+    ~DeferredStatus()
+    {
+        for (int d = 0; d < 64; ++d) if (word[d]) cudaFree(word[d]);
+        cudaGetLastError();
+    }
+};
+thread_local DeferredStatus t_deferred;
 
-int* take_status_slot()
+int deferred_status_word(int device, int** out)
 {
-    if (!t_free_slots.empty()) { int* p = t_free_slots.back(); t_free_slots.pop_back(); return p; }
-    int* p = nullptr;
-    if (cudaMallocHost(&p, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return p;
+    if (!t_deferred.word[device]) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&t_deferred.word[device]), 256));
+        CUDA_TRY(cudaMemset(t_deferred.word[device], 0, 256));
+    }
+    *out = t_deferred.word[device];
+    return MGD_OK;
 }
 
 int status_to_error(int st)
@@ -722,12 +734,10 @@ int mgd_poll_status(int device, void* stream)
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     int st = 0;
-    std::vector<Pending> keep;
-    for (Pending& p : t_pending) {
-        if (p.device == device) { st |= *p.host; t_free_slots.push_back(p.host); }
-        else keep.push_back(p);
+    if (t_deferred.word[device]) {
+        CUDA_TRY(cudaMemcpy(&st, t_deferred.word[device], sizeof(int), cudaMemcpyDeviceToHost));
+        if (st) CUDA_TRY(cudaMemset(t_deferred.word[device], 0, sizeof(int)));
     }
-    t_pending.swap(keep);
     return status_to_error(st);
 }
 
@@ -755,6 +765,14 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
     if (stats) memset(stats, 0, 4 * sizeof(long long));
     if (batch == 0) return MGD_OK;
 
+    if (memory == MGD_MEM_DEVICE && !(flags & MGD_FLAG_SYNC)) {
+        // asynchronous: status bits go to the thread's persistent word (mgd_poll_status)
+        cudaStream_t st = (cudaStream_t)stream;
+        int* d_flag;
+        if ((rc = deferred_status_word(device, &d_flag))) return rc;
+        return encode_device(g, boxes, batch, max_boxes, y_true, num_sms, st, d_flag, nullptr,
+                             Alloc{nullptr, st}, (flags & MGD_FLAG_TF_COMPAT) != 0);
+    }
     if (memory == MGD_MEM_DEVICE) {
         cudaStream_t st = (cudaStream_t)stream;
         int* d_status;
@@ -775,12 +793,6 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
             CUDA_TRY(cudaStreamSynchronize(st));
             if (stats) for (int i = 0; i < 4; ++i) stats[i] = (long long)h[i];
             return status_to_error((int)(h[4] & 0xffffffffu));
-        }
-        int* slot = take_status_slot();
-        if (slot) {
-            *slot = 0;
-            CUDA_TRY(cudaMemcpyAsync(slot, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-            t_pending.push_back({slot, device});
         }
         CUDA_TRY(cudaFreeAsync(d_status, st));
         return MGD_OK;
