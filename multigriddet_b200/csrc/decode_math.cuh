@@ -52,7 +52,10 @@ static __device__ void octet_probs(float* x, int n, int j, unsigned m, bool use_
         int near_one = INT_MAX;                 // first own index whose exponential is ~1
         #pragma unroll 2
         for (int i = j; i < n; i += 8) {
-            const float e = mgd_expf_core(fmaxf(__fsub_rn(x[i], mx), -104.0f), tab);
+            // (a select, not fmaxf: NaN -- from a NaN or +inf logit -- must reach the sum like
+            //  it does in the reference, which then drops the row: NaN >= confidence is false)
+            const float d = __fsub_rn(x[i], mx);
+            const float e = mgd_expf_core(d < -104.0f ? -104.0f : d, tab);
             x[i] = e;
             if (e >= 0.99999f && near_one == INT_MAX) near_one = i;
         }

@@ -125,3 +125,32 @@ def test_decode_extreme_image_shapes(c_oracle, force):
         k = int(ref["counts"][b])
         assert np.array_equal(got["index"][b, :k], ref["index"][b, :k]), (b, shapes[b])
         np.testing.assert_allclose(got["boxes_xywh"][b, :k], ref["boxes_xywh"][b, :k], rtol=1e-5, atol=1e-4)
+
+
+def test_decode_non_finite_logits_are_dropped_like_the_reference(c_oracle):
+    """NaN / +-inf in the objectness, anchor or class logits of a cell: the reference's
+    softmax turns the score into NaN (or 0) and `score >= confidence` drops the cell."""
+    import torch
+    S, C, B = 416, 20, 4
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(78, B, 30, S, C)
+    y = c_oracle.encode_targets(boxes, (S, S), anchors, C)
+    preds = [p.numpy().copy() for p in synth.planted_head_outputs([torch.from_numpy(t) for t in y], 3, 78)]
+    rng = np.random.default_rng(3)
+    poisoned = 0
+    for l, p in enumerate(preds):
+        pos = np.argwhere(y[l][..., 4] > 0)
+        for n, (b, i, j) in enumerate(pos[rng.permutation(len(pos))[:12]]):
+            ch = [4, 5 + int(rng.integers(0, 3)), 8 + int(rng.integers(0, C))][n % 3]
+            p[b, i, j, ch] = [np.nan, np.inf, -np.inf][(n // 3) % 3]
+            poisoned += 1
+    assert poisoned >= 24
+    kw = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method="diou")
+    with np.errstate(all="ignore"):
+        ref = c_oracle.decode_nms(preds, [(S, S)], (S, S), anchors, C, **kw)
+    got = engine.decode_nms(preds, (S, S), (S, S), anchors, C, **kw)
+    assert np.array_equal(got["counts"], ref["counts"])
+    for b in range(B):
+        k = int(ref["counts"][b])
+        assert np.array_equal(got["index"][b, :k], ref["index"][b, :k]), b
+        assert np.array_equal(got["scores"][b, :k], ref["scores"][b, :k])
