@@ -322,7 +322,7 @@ decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
 }
 
 // ---- dense decode (decode_predictions API), one octet per row, not a hot path --
-__global__ void __launch_bounds__(kDenseThreads)
+__global__ void __launch_bounds__(kDenseThreads, 3)
 decode_dense_kernel(const __grid_constant__ DecodeArgs a, const int* image_hw, double* out,
                     int row_floats)
 {
