@@ -771,7 +771,7 @@ __device__ void cta_bitonic(unsigned long long* key, unsigned long long* val, in
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 soft_nms_kernel(const __grid_constant__ NmsArgs a)
 {
     __shared__ unsigned long long s_key[kSortSmem];
