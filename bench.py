@@ -181,7 +181,7 @@ def _cpu_worker(args):
     return t1 - t0, t2 - t1
 
 
-def cpu_baseline_single(n_images=192):
+def cpu_baseline_single(n_images=960):
     """Oracle port (NumPy restatement of the reference), one core."""
     _, boxes, preds = _cpu_inputs(n_images)
     te, td = _cpu_worker((boxes, preds))
