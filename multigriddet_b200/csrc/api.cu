@@ -187,7 +187,17 @@ int device_count_quiet()
     return n;
 }
 
-int prepare_device(int device, int* num_sms)
+// Entry points run on `device` and put the caller's current device back on exit: the
+// library must not change the application's (or torch's) notion of the current device.
+struct DeviceScope {
+    int prev = -1;
+    ~DeviceScope()
+    {
+        if (prev >= 0 && cudaSetDevice(prev) != cudaSuccess) cudaGetLastError();
+    }
+};
+
+int prepare_device(int device, int* num_sms, DeviceScope* scope)
 {
     const int n = device_count_quiet();
     if (n == 0)
@@ -195,7 +205,12 @@ int prepare_device(int device, int* num_sms)
                     "no CUDA device available: libmgd has no CPU fallback (sm_100a kernels only)");
     if (device < 0 || device >= n || device >= 64)
         return fail(MGD_ERR_INVALID_ARGUMENT, "device %d out of range (have %d)", device, n);
-    CUDA_TRY(cudaSetDevice(device));
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = -1; }
+    if (cur != device) {
+        CUDA_TRY(cudaSetDevice(device));
+        if (scope && scope->prev < 0) scope->prev = cur;
+    }
     std::lock_guard<std::mutex> lock(g_mutex);
     DeviceInfo& d = g_dev[device];
     if (!d.ready) {
@@ -465,12 +480,8 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
             n.soft_thr = 0.0;                              // skip_box_thr default
             CUDA_TRY(al.get(&n.soft_scratch, (size_t)nb * g.cells * 5 * sizeof(double)));
             CUDA_TRY(al.get(&n.wbf_ints, (size_t)nb * g.cells * 4 * sizeof(int)));
-            if (!n.sort_scratch) {
-                n.sort_scratch_stride = pow2;
-                CUDA_TRY(al.get(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long)));
-            }
         }
-        if (big_sort) {
+        if (n.wbf || big_sort) {                         // one allocation serves both users
             n.sort_scratch_stride = pow2;
             CUDA_TRY(al.get(&n.sort_scratch, (size_t)nb * 2 * pow2 * sizeof(unsigned long long)));
         }
@@ -730,7 +741,8 @@ int mgd_profile_end(double* ms, long long* launches)
 int mgd_poll_status(int device, void* stream)
 {
     int num_sms;
-    int rc = prepare_device(device, &num_sms);
+    DeviceScope dev_scope;
+    int rc = prepare_device(device, &num_sms, &dev_scope);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     int st = 0;
@@ -761,7 +773,8 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
     if ((long long)chunk_images(g, batch > 0 ? batch : 1) * max_boxes >= (1ll << 27))
         return fail(MGD_ERR_UNSUPPORTED, "batch chunk x max_boxes too large");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     if (stats) memset(stats, 0, 4 * sizeof(long long));
     if (batch == 0) return MGD_OK;
 
@@ -916,7 +929,8 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
         if (!preds[l] && batch > 0) return fail(MGD_ERR_INVALID_ARGUMENT, "preds[%d] is NULL", l);
     if (!counts && batch > 0) return fail(MGD_ERR_INVALID_ARGUMENT, "counts is NULL");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     if (stats) memset(stats, 0, 4 * sizeof(long long));
     if (batch == 0) return MGD_OK;
     const int M = post->max_boxes;
@@ -1071,7 +1085,8 @@ int mgd_decode_dense(const mgd_head_config* cfg, const mgd_post_config* post,
     if (batch < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "batch must be >= 0");
     if (batch > 0 && (!preds || !out)) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     if (batch == 0) return MGD_OK;
     DecodeArgs d;
     memset(&d, 0, sizeof(d));
@@ -1136,7 +1151,8 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
     if (n > 0 && (!boxes || !scores || !keep)) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
     if (max_keep <= 0 || max_keep > n) max_keep = n;
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     const bool host = memory == MGD_MEM_HOST;
     cudaStream_t st = (cudaStream_t)stream;
     if (host) {
@@ -1214,7 +1230,8 @@ int mgd_wbf(const double* boxes, const double* scores, const int* classes,
         return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
     if (conf_type < 0 || conf_type > 2) return fail(MGD_ERR_INVALID_ARGUMENT, "bad conf_type");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     const bool host = memory == MGD_MEM_HOST;
     cudaStream_t st = (cudaStream_t)stream;
     if (host) {
@@ -1285,8 +1302,11 @@ int mgd_soft_nms(const double* boxes, const double* scores, int n, double sigma,
     if (n > 0 && (!boxes || !scores || !keep || !soft_scores))
         return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
     if (!(sigma > 0.0)) return fail(MGD_ERR_INVALID_ARGUMENT, "sigma must be positive");
+    if (score_threshold != score_threshold)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "score_threshold is NaN");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     const bool host = memory == MGD_MEM_HOST;
     cudaStream_t st = (cudaStream_t)stream;
     if (host) {
@@ -1363,7 +1383,8 @@ int mgd_match_detections(const double* det_boxes, const double* det_scores, cons
     if ((long long)batch * max_gt > 0 && (!gt_boxes || !gt_classes))
         return fail(MGD_ERR_INVALID_ARGUMENT, "NULL ground-truth tensor");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     if (batch == 0) return MGD_OK;
     const bool host = memory == MGD_MEM_HOST;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1440,7 +1461,8 @@ int mgd_ignore_mask(const mgd_head_config* cfg, const float* const* y_pred,
         if (!y_pred[l] || !y_true[l] || !ignore_mask[l] || !assigned_anchor_iou[l] || !max_iou_map[l])
             return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor for layer %d", l);
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     if (batch == 0) return MGD_OK;
     const bool host = memory == MGD_MEM_HOST;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1512,7 +1534,8 @@ int mgd_reshape_boxes(const void* boxes, int boxes_dtype, const int* counts, con
     if (batch > 0 && !params) return fail(MGD_ERR_INVALID_ARGUMENT, "params is NULL");
     if (n > 0 && (!boxes || !out)) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     if (batch == 0) return MGD_OK;
     const size_t esz = boxes_dtype == MGD_BOXES_I32 ? 4 : 8;
     BoxOpArgs a;
@@ -1563,7 +1586,8 @@ int mgd_mosaic_merge_boxes(const double* boxes, int num_sources, int max_boxes, 
     if (batch > 0 && !params) return fail(MGD_ERR_INVALID_ARGUMENT, "params is NULL");
     if (n > 0 && (!out || (n_in > 0 && !boxes))) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     if (batch == 0) return MGD_OK;
     BoxOpArgs a;
     memset(&a, 0, sizeof(a));
@@ -1604,7 +1628,8 @@ int mgd_iou_matrix(const double* boxes1, int n, const double* boxes2, int m, dou
     if (n < 0 || m < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n and m must be >= 0");
     if ((long long)n * m > 0 && (!boxes1 || !boxes2 || !out)) return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
     int num_sms;
-    if ((rc = prepare_device(device, &num_sms))) return rc;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
     if ((long long)n * m == 0) return MGD_OK;
     const bool host = memory == MGD_MEM_HOST;
     cudaStream_t st = (cudaStream_t)stream;

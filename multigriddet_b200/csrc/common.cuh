@@ -68,6 +68,7 @@ struct DecodeArgs {
     float obj_logit_min;              // conservative prefilter on the raw objectness logit
     float score_lo;                   // confidence * (1 - 1e-3): bound for the fast prefilters
     long long rows_in_layer[MGD_MAX_LAYERS];    // B * gh * gw
+    unsigned long long cells_magic[MGD_MAX_LAYERS];   // floor(2^64 / (gh*gw)) + 1 (0 when gh*gw == 1): row -> image
     Cand* cand;                       // (B, cells)
     int* counts;                      // (B,)
 };

@@ -6,6 +6,22 @@
 // float64 tensor.  Box reconstruction of the few candidates (:151-163, 185-235)
 // happens in the NMS kernel, one thread per candidate.
 //
+// decode_ws_kernel (the hot path: 3 anchors per layer, C <= 128) -- the three filter
+// levels described below, split over WARP-SPECIALISED roles.  A CTA holds groups of one
+// producer warp and three consumer warps around a ring of shared-memory slots of 32 rows:
+//   producer  scans the head tensor (level 1, a 16-byte load per row, several blocks in
+//             flight), and has the TMA copy each surviving 352-byte row into the slot it
+//             is filling (cp.async.bulk -> the slot's `full` mbarrier); a full slot is
+//             published with one arrive;
+//   consumers take published slots in order (shared counter), run level 2 (lane per
+//             row) and level 3 (eight lanes per row, exact) straight from shared memory
+//             without ever writing to it, and hand the slot back through its `empty`
+//             mbarrier.
+// The scan's DRAM latency and the exact evaluation's arithmetic latency thus overlap
+// instead of alternating inside one warp (round 1: 46% issue utilisation, 23% of the
+// warp slots).  decode_compact_kernel below is the generic fallback (any anchor count,
+// any channel count) with the same three levels inside every warp.
+//
 // decode_compact_kernel -- persistent CTAs of independent warps.  A warp walks the
 // head tensor in blocks of 32 cell rows and filters them in three levels; only the
 // bytes a level needs are ever requested from HBM:
@@ -30,6 +46,8 @@
 // traffic of this kernel is lower and data-dependent.  No CTA barrier, no
 // inter-warp dependency.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "decode_math.cuh"
 
@@ -115,19 +133,19 @@ __device__ __noinline__ void flush_pool(const DecodeArgs& a, const WarpPool& poo
             for (int i = 0; i < C / 4; ++i) {
                 const float4 v = c4[i];
                 mc = fmaxf(fmaxf(mc, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-                if (softmax) sum += (__expf(v.x) + __expf(v.y)) + (__expf(v.z) + __expf(v.w));
+                if (softmax) sum += (fast_exp(v.x) + fast_exp(v.y)) + (fast_exp(v.z) + fast_exp(v.w));
             }
         } else {
             for (int i = 0; i < C; ++i) {
                 mc = fmaxf(mc, c[i]);
-                if (softmax) sum += __expf(c[i]);
+                if (softmax) sum += fast_exp(c[i]);
             }
         }
         float ub;
         if (softmax) {
             // max softmax = exp(mc) / sum; no max subtraction in the fast bound: if it
             // overflows (logits > 88) the row is simply kept for the exact evaluation
-            ub = __fdividef(pool.bound[lane] * __expf(mc), sum);
+            ub = __fdividef(pool.bound[lane] * fast_exp(mc), sum);
             if (!(sum < 3.0e38f) || !(ub == ub)) ub = 3.0e38f;
         } else {
             ub = pool.bound[lane] * fast_sigmoid(mc);
@@ -243,7 +261,7 @@ decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
                     if (kFast) {
                         const float ma = fmaxf(q.y, fmaxf(q.z, q.w));
                         if (softmax)
-                            bound = __fdividef(bound, (__expf(q.y - ma) + __expf(q.z - ma)) + __expf(q.w - ma));
+                            bound = __fdividef(bound, (fast_exp(q.y - ma) + fast_exp(q.z - ma)) + fast_exp(q.w - ma));
                         else
                             bound *= fast_sigmoid(ma);
                     } else {
@@ -252,7 +270,7 @@ decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
                         for (int i = 1; i < A; ++i) ma = fmaxf(ma, __ldg(an + i));
                         if (softmax) {
                             float sa = 0.f;
-                            for (int i = 0; i < A; ++i) sa += __expf(__ldg(an + i) - ma);
+                            for (int i = 0; i < A; ++i) sa += fast_exp(__ldg(an + i) - ma);
                             bound = __fdividef(bound, sa);
                         } else {
                             bound *= fast_sigmoid(ma);
@@ -321,12 +339,438 @@ decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
     }
 }
 
+// =================================================================================
+// Warp-specialised decoder
+// =================================================================================
+namespace ws {
+
+// Shape of a CTA: kGroups groups of (1 producer + kConsumers consumer warps), each around
+// its own ring of kSlots slots.  Measured instruction budget per COCO image (planted head):
+// producer ~43 k warp-instructions (scan + one TMA issue per surviving row), consumers ~80 k,
+// hence two consumers per producer; three groups x three slots fill the shared memory of an
+// SM with two CTAs (18 warps).
+template <int kConsumers_, int kGroups_, int kSlots_>
+struct Shape {
+    static constexpr int kConsumers = kConsumers_;
+    static constexpr int kGroupWarps = 1 + kConsumers_;
+    static constexpr int kGroups = kGroups_;
+    static constexpr int kThreads = kGroups_ * (1 + kConsumers_) * 32;
+    static constexpr int kSlots = kSlots_;
+};
+constexpr int kSlotRows = 32;
+constexpr int kPrefetch = 4;                  // level-1 loads in flight per producer lane
+
+struct SlotMeta {
+    int row[kSlotRows];                       // row index within the layer (b * cells_l + cell)
+    float bound[kSlotRows];                   // level-1 bound sigmoid(obj) * max anchor prob
+    int count;                                // rows in the slot; < 0: no more work
+    int layer;
+    int pad[2];
+};
+
+// exp2f-style kernel of libm_emul.h with the table split into two 32-entry 4-byte arrays
+// (low words at tab[0..31], high words at tab[32..63]; one entry per bank: any lane pattern
+// is conflict-free) and the 64-bit exponent add done
+// on the high word only (ki << 47 has no low half).  Same double operations, same bits.
+__device__ __forceinline__ float expf_core2(float x, const uint32_t* tab)
+{
+    const double inv_ln2_n = 0x1.71547652b82fep+0 * MGD_EXP2F_N;
+    const double shift = 0x1.8p+52;
+    const double c0 = 0x1.c6af84b912394p-5 / MGD_EXP2F_N / MGD_EXP2F_N / MGD_EXP2F_N;
+    const double c1 = 0x1.ebfce50fac4f3p-3 / MGD_EXP2F_N / MGD_EXP2F_N;
+    const double c2 = 0x1.62e42ff0c52d6p-1 / MGD_EXP2F_N;
+    const double z = __dmul_rn(inv_ln2_n, (double)x);
+    double kd = __dadd_rn(z, shift);
+    const int ki = __double2loint(kd);
+    kd = __dsub_rn(kd, shift);
+    const double r = __dsub_rn(z, kd);
+    const int idx = ki & (MGD_EXP2F_N - 1);
+    const int hi = (int)tab[idx + MGD_EXP2F_N] + (ki << 15);
+    const double sc = __hiloint2double(hi, (int)tab[idx]);
+    const double q = __fma_rn(c0, r, c1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(c2, r, 1.0);
+    y = __fma_rn(q, r2, y);
+    y = __dmul_rn(y, sc);
+    return __double2float_rn(y);
+}
+
+// full-range version (glibc's special-case block in front, libm_emul.h: mgd_expf_tab)
+__device__ __forceinline__ float expf_full2(float x, const uint32_t* tab)
+{
+    float special = 0.f;
+    bool is_special = false;
+    if (!(x < 88.0f && x > -88.0f)) {
+        if (x != x) { special = x + x; is_special = true; }
+        else if (x > 88.72283172607421875f) { special = __builtin_huge_valf(); is_special = true; }
+        else if (x < -103.972076416015625f) { special = 0.0f; is_special = true; }
+    }
+    const float v = expf_core2(is_special ? 0.f : x, tab);
+    return is_special ? special : v;
+}
+
+// if (d >= thr) { first = min(first, i); ++cnt; } as one compare and two predicated ops
+__device__ __forceinline__ void near_track(float d, float thr, int i, int& first, int& cnt)
+{
+    asm("{\n .reg .pred p;\n setp.ge.f32 p, %2, %3;\n @p min.s32 %0, %0, %4;\n @p add.s32 %1, %1, 1;\n}"
+        : "+r"(first), "+r"(cnt) : "f"(d), "f"(thr), "r"(i));
+}
+
+struct GroupShared {
+    float* rows;              // [kSlots][kSlotRows][stride]
+    SlotMeta* meta;           // [kSlots]
+    uint64_t* full;           // [kSlots]
+    uint64_t* empty;          // [kSlots]
+    int* next_seq;            // consumers' shared slot counter
+    int stride;
+};
+
+template <class Sh>
+__device__ __forceinline__ void producer(const DecodeArgs& a, const GroupShared& gs, int p, int P)
+{
+    constexpr int kSlots = Sh::kSlots;
+    constexpr int kConsumers = Sh::kConsumers;
+    const HeadGeom& g = a.g;
+    const int lane = threadIdx.x & 31;
+    const bool softmax = a.use_softmax != 0;
+    const bool rescore = a.rescore != 0;
+    int seq = 0, slot = 0, count = 0;
+    bool have_slot = false;
+
+    auto acquire = [&]() {
+        slot = seq % kSlots;
+        mbar_wait(&gs.empty[slot], (((unsigned)(seq / kSlots)) & 1u) ^ 1u);
+        have_slot = true;
+    };
+    auto publish = [&](int cnt, int layer) {
+        if (lane == 0) { gs.meta[slot].count = cnt; gs.meta[slot].layer = layer; }
+        __syncwarp();                                   // metadata of all lanes before the arrive
+        if (lane == 0) mbar_arrive(&gs.full[slot]);
+        ++seq;
+        have_slot = false;
+        count = 0;
+    };
+
+    for (int layer = 0; layer < g.L; ++layer) {
+        const int D = g.D[layer];
+        const int n_rows = (int)a.rows_in_layer[layer];
+        const int n_blocks = (n_rows + 31) >> 5;
+        const float* base = a.pred[layer];
+        auto load_head = [&](int blk, float4& q) {
+            const int row = blk * 32 + lane;
+            q = make_float4(NAN, 0.f, 0.f, 0.f);          // NaN never passes a >= test
+            if (blk < n_blocks && row < n_rows)
+                q = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * D + 4));
+        };
+        float4 q[kPrefetch];
+        #pragma unroll
+        for (int k = 0; k < kPrefetch; ++k) load_head(p + k * P, q[k]);
+        for (int blk0 = p; blk0 < n_blocks; blk0 += kPrefetch * P) {
+            #pragma unroll
+            for (int k = 0; k < kPrefetch; ++k) {
+                const int blk = blk0 + k * P;
+                if (blk >= n_blocks) break;
+                const float4 h = q[k];
+                load_head(blk + kPrefetch * P, q[k]);
+                const int row = blk * 32 + lane;
+
+                // ---- level 1: lane per row -----------------------------------------------
+                float bound = 0.f;
+                bool pass = false;
+                if (h.x >= a.obj_logit_min) {           // rows beyond the layer carry NaN
+                    bound = fast_sigmoid(h.x);
+                    if (rescore) {
+                        const float ma = fmaxf(h.y, fmaxf(h.z, h.w));
+                        if (softmax)
+                            bound = __fdividef(bound, (fast_exp(h.y - ma) + fast_exp(h.z - ma)) + fast_exp(h.w - ma));
+                        else
+                            bound *= fast_sigmoid(ma);
+                    }
+                    pass = bound >= a.score_lo;
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, pass);
+
+                // ---- survivors: TMA copy into the slot being filled ----------------------
+                while (todo) {
+                    if (!have_slot) acquire();
+                    const int free_slots = kSlotRows - count;
+                    const int rank = __popc(todo & ((1u << lane) - 1u));
+                    const bool take = ((todo >> lane) & 1u) && rank < free_slots;
+                    const unsigned taken = __ballot_sync(0xffffffffu, take);
+                    const int n_new = __popc(taken);
+                    if (take) {
+                        gs.meta[slot].row[count + rank] = row;
+                        gs.meta[slot].bound[count + rank] = bound;
+                    }
+                    if (lane == 0) mbar_expect_tx(&gs.full[slot], (uint32_t)n_new * D * sizeof(float));
+                    __syncwarp();
+                    if (take)
+                        bulk_g2s(gs.rows + ((size_t)slot * kSlotRows + count + rank) * gs.stride,
+                                 base + (size_t)row * D, (uint32_t)D * sizeof(float), &gs.full[slot]);
+                    count += n_new;
+                    todo &= ~taken;
+                    if (count == kSlotRows) publish(count, layer);
+                }
+            }
+        }
+        if (count) publish(count, layer);              // slots never mix layers
+    }
+    for (int c = 0; c < kConsumers; ++c) {             // one terminal slot per consumer
+        acquire();
+        publish(-1, 0);
+    }
+}
+
+template <class Sh>
+__device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared& gs,
+                                         const uint32_t* tab)
+{
+    constexpr int kSlots = Sh::kSlots;
+    const HeadGeom& g = a.g;
+    const int lane = threadIdx.x & 31;
+    const int j = lane & 7;
+    const int oct = lane >> 3;
+    const bool softmax = a.use_softmax != 0;
+    const bool rescore = a.rescore != 0;
+    const int C = g.C;
+    const int body = C >= 8 ? (C & ~7) : 0;             // NumPy: 8 accumulators over the body,
+    const int tail = C - body;                          // then the tail one by one (n < 8: all tail)
+    constexpr float kNear = 0.99999f;
+    constexpr float kNearD = -1.1e-5f;                  // exp(d) >= kNear implies d > kNearD
+
+    for (;;) {
+        int seq = 0;
+        if (lane == 0) seq = atomicAdd(gs.next_seq, 1);
+        seq = __shfl_sync(0xffffffffu, seq, 0);
+        const int slot = seq % kSlots;
+        mbar_wait(&gs.full[slot], ((unsigned)(seq / kSlots)) & 1u);
+        const SlotMeta& meta = gs.meta[slot];
+        const int count = meta.count;
+        if (count < 0) break;
+        const int layer = meta.layer;
+        const float* rows = gs.rows + (size_t)slot * kSlotRows * gs.stride;
+
+        // ---- level 2: lane per row, bound including the class maximum ------------------
+        bool pass = lane < count;
+        float mc = -INFINITY;
+        if (pass) {
+            const float4* c4 = reinterpret_cast<const float4*>(rows + (size_t)lane * gs.stride + 8);
+            float sum = 0.f;
+            if (softmax && rescore) {
+                #pragma unroll 4
+                for (int i = 0; i < C / 4; ++i) {
+                    const float4 v = c4[i];
+                    mc = fmaxf(fmaxf(mc, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                    sum += (fast_exp(v.x) + fast_exp(v.y)) + (fast_exp(v.z) + fast_exp(v.w));
+                }
+                // max softmax = exp(mc) / sum; no max subtraction in the fast bound: if it
+                // overflows (logits > 88) the row is simply kept for the exact evaluation
+                float ub = __fdividef(meta.bound[lane] * fast_exp(mc), sum);
+                if (!(sum < 3.0e38f) || !(ub == ub)) ub = 3.0e38f;
+                pass = ub >= a.score_lo;
+            } else {
+                #pragma unroll 4
+                for (int i = 0; i < C / 4; ++i) {
+                    const float4 v = c4[i];
+                    mc = fmaxf(fmaxf(mc, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                }
+                if (rescore) pass = meta.bound[lane] * fast_sigmoid(mc) >= a.score_lo;
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, pass);
+
+        // ---- level 3: exact evaluation, octet per row, nothing written to the slot ------
+        while (todo) {
+            const unsigned pos = nth_set_bit(todo, oct);
+            const bool live = pos < 32u;
+            const unsigned posr = live ? pos : (unsigned)__ffs((int)todo) - 1u;   // idle octets shadow a live row
+            const float* x = rows + (size_t)posr * gs.stride;
+            const float mx = __shfl_sync(0xffffffffu, mc, (int)posr);
+            const float4 head = *reinterpret_cast<const float4*>(x + 4);         // obj, 3 anchor logits
+            const int l0 = oct * 8;
+            float pa, pc, obj;
+            int ka, kc;
+            if (softmax) {
+                // -- classes: exp(x - max) accumulated in NumPy's order as it is produced --
+                const float* cx = x + 8;
+                float r = 0.f, e_tail = 0.f;
+                int near_cnt = 0, near_first = INT_MAX;
+                if (body) {
+                    {
+                        const float d = __fsub_rn(cx[j], mx);
+                        r = expf_core2(d < -104.0f ? -104.0f : d, tab);
+                        if (d >= kNearD) { near_cnt = 1; near_first = j; }
+                    }
+                    #pragma unroll 3
+                    for (int i = 8 + j; i < body; i += 8) {
+                        // (a select, not fmaxf: NaN -- from a NaN or +inf logit -- must reach the
+                        //  sum like it does in the reference, which then drops the row)
+                        const float d = __fsub_rn(cx[i], mx);
+                        const float e = expf_core2(d < -104.0f ? -104.0f : d, tab);
+                        r = __fadd_rn(r, e);
+                        near_track(d, kNearD, i, near_first, near_cnt);
+                    }
+                    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));   // (r0+r1) (r2+r3) ...
+                    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+                    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+                }
+                if (tail) {
+                    if (j < tail) {
+                        const float d = __fsub_rn(cx[body + j], mx);
+                        e_tail = expf_core2(d < -104.0f ? -104.0f : d, tab);
+                        near_track(d, kNearD, body + j, near_first, near_cnt);
+                    }
+                    for (int k = 0; k < tail; ++k)
+                        r = __fadd_rn(r, __shfl_sync(0xffffffffu, e_tail, l0 + k));
+                }
+                pc = __frcp_rn(r);                      // 1 / sum: the maximum's exponential is exactly 1
+                // argmax on the probabilities e/s like the reference: first index whose quotient
+                // equals the maximum quotient; only exponentials within 1e-5 of 1 can tie.  A row
+                // with a single logit within kNearD of the maximum (the maximum itself: a superset
+                // test, exp(-1.1e-5) < 0.99999) needs no division; anything else is settled exactly
+                const unsigned has = (__ballot_sync(0xffffffffu, near_cnt > 0) >> l0) & 0xffu;
+                const unsigned many = (__ballot_sync(0xffffffffu, near_cnt > 1) >> l0) & 0xffu;
+                const bool simple = !many && __popc(has) == 1;
+                kc = __shfl_sync(0xffffffffu, near_first, l0 + (has ? __ffs((int)has) - 1 : 0));
+                if (__any_sync(0xffffffffu, !simple)) {                     // rare
+                    int first = INT_MAX;
+                    for (int i = j; i < C; i += 8) {
+                        const float d = __fsub_rn(cx[i], mx);
+                        const float e = expf_core2(d < -104.0f ? -104.0f : d, tab);
+                        if (e >= kNear && __fdiv_rn(e, r) == pc) { first = i; break; }
+                    }
+                    first = min(first, __shfl_xor_sync(0xffffffffu, first, 1));
+                    first = min(first, __shfl_xor_sync(0xffffffffu, first, 2));
+                    first = min(first, __shfl_xor_sync(0xffffffffu, first, 4));
+                    if (!simple) kc = first;
+                }
+
+                // -- anchors (lanes 0-2 of the octet) and objectness (lane 3) in one expf round --
+                const float ma = fmaxf(head.y, fmaxf(head.z, head.w));
+                const float logit = x[5 + (j < 2 ? j : 2)];
+                const float da = __fsub_rn(logit, ma);
+                const float arg = j < 3 ? (da < -104.0f ? -104.0f : da) : (j == 3 ? -head.x : 0.f);
+                const float e = expf_full2(arg, tab);
+                const float e0 = __shfl_sync(0xffffffffu, e, l0);
+                const float e1 = __shfl_sync(0xffffffffu, e, l0 + 1);
+                const float e2 = __shfl_sync(0xffffffffu, e, l0 + 2);
+                const float eo = __shfl_sync(0xffffffffu, e, l0 + 3);
+                const float sa = __fadd_rn(__fadd_rn(__fadd_rn(0.f, e0), e1), e2);  // n < 8: sequential
+                pa = __frcp_rn(sa);
+                const int n0 = e0 >= kNear, n1 = e1 >= kNear, n2 = e2 >= kNear;
+                if (n0 + n1 + n2 == 1) {
+                    ka = n0 ? 0 : (n1 ? 1 : 2);
+                } else {
+                    ka = INT_MAX;
+                    if (n2 && __fdiv_rn(e2, sa) == pa) ka = 2;
+                    if (n1 && __fdiv_rn(e1, sa) == pa) ka = 1;
+                    if (n0 && __fdiv_rn(e0, sa) == pa) ka = 0;
+                }
+                obj = __frcp_rn(__fadd_rn(1.0f, eo));                            // :147
+            } else {
+                // element-wise expit; maximum and its first index
+                float best = -INFINITY;
+                int first = INT_MAX;
+                for (int i = j; i < C; i += 8) {
+                    const float qv = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_full2(-x[8 + i], tab)));
+                    if (qv > best) { best = qv; first = i; }
+                }
+                #pragma unroll
+                for (int d = 1; d <= 4; d <<= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, d);
+                    const int oi = __shfl_xor_sync(0xffffffffu, first, d);
+                    if (ob > best || (ob == best && oi < first)) { best = ob; first = oi; }
+                }
+                pc = best; kc = first;
+                const float logit = j == 0 ? head.x : (j == 1 ? head.y : (j == 2 ? head.z : head.w));
+                const float qv = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_full2(-logit, tab)));
+                obj = __shfl_sync(0xffffffffu, qv, l0);
+                const float q0 = __shfl_sync(0xffffffffu, qv, l0 + 1);
+                const float q1 = __shfl_sync(0xffffffffu, qv, l0 + 2);
+                const float q2 = __shfl_sync(0xffffffffu, qv, l0 + 3);
+                pa = -INFINITY; ka = INT_MAX;
+                if (q0 > pa) { pa = q0; ka = 0; }
+                if (q1 > pa) { pa = q1; ka = 1; }
+                if (q2 > pa) { pa = q2; ka = 2; }
+            }
+            float score = obj;
+            if (rescore) score = __fmul_rn(__fmul_rn(score, pa), pc);            // :170
+            if (live && j == 0 && (double)score >= a.confidence) {               // :271
+                const unsigned grow = (unsigned)meta.row[pos];
+                const unsigned long long magic = a.cells_magic[layer];
+                const unsigned b = magic ? (unsigned)__umul64hi((unsigned long long)grow, magic) : grow;
+                const int cell = (int)(grow - b * (unsigned)(g.gh[layer] * g.gw[layer]));
+                Cand cd;
+                cd.score = score;
+                cd.index = g.cell_off[layer] + cell;
+                const float4 t = *reinterpret_cast<const float4*>(x);
+                cd.t[0] = t.x; cd.t[1] = t.y; cd.t[2] = t.z; cd.t[3] = t.w;
+                cd.cls = kc;
+                cd.anchor = g.anchor_first[layer] + ka;
+                const int at = atomicAdd(a.counts + b, 1);
+                a.cand[(size_t)b * g.cells + at] = cd;
+            }
+            #pragma unroll
+            for (int q = 0; q < 4; ++q) todo &= todo - 1;
+        }
+        __syncwarp();                                   // every lane is done reading the slot
+        if (lane == 0) mbar_arrive(&gs.empty[slot]);
+    }
+}
+
+template <class Sh>
+__global__ void __launch_bounds__(Sh::kThreads, 2)
+decode_ws_kernel(const __grid_constant__ DecodeArgs a, int stride)
+{
+    constexpr int kGroups = Sh::kGroups, kSlots = Sh::kSlots, kGroupWarps = Sh::kGroupWarps;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t s_full[kGroups][kSlots];
+    __shared__ uint64_t s_empty[kGroups][kSlots];
+    __shared__ SlotMeta s_meta[kGroups][kSlots];
+    __shared__ uint32_t s_tab[2 * MGD_EXP2F_N];
+    __shared__ int s_next[kGroups];
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int grp = warp / kGroupWarps;
+    const int role = warp - grp * kGroupWarps;
+    if (tid < MGD_EXP2F_N) {
+        s_tab[tid] = (uint32_t)mgd_exp2f_tab[tid];
+        s_tab[tid + MGD_EXP2F_N] = (uint32_t)(mgd_exp2f_tab[tid] >> 32);
+    }
+    if (tid == 0) {
+        for (int gq = 0; gq < kGroups; ++gq) {
+            for (int sl = 0; sl < kSlots; ++sl) {
+                mbar_init(&s_full[gq][sl], 1);
+                mbar_init(&s_empty[gq][sl], 1);
+            }
+            s_next[gq] = 0;
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    GroupShared gs;
+    gs.rows = reinterpret_cast<float*>(smem_raw) + (size_t)grp * kSlots * kSlotRows * stride;
+    gs.meta = s_meta[grp];
+    gs.full = s_full[grp];
+    gs.empty = s_empty[grp];
+    gs.next_seq = &s_next[grp];
+    gs.stride = stride;
+    if (role == 0)
+        producer<Sh>(a, gs, blockIdx.x * kGroups + grp, gridDim.x * kGroups);
+    else
+        consumer<Sh>(a, gs, s_tab);
+}
+
+}  // namespace ws
+
 // ---- dense decode (decode_predictions API), one octet per row, not a hot path --
 __global__ void __launch_bounds__(kDenseThreads, 3)
 decode_dense_kernel(const __grid_constant__ DecodeArgs a, const int* image_hw, double* out,
                     int row_floats)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_tab[MGD_EXP2F_N];
     const HeadGeom& g = a.g;
     const int tid = threadIdx.x, j = tid & 7;
@@ -396,11 +840,54 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
                ((reinterpret_cast<uintptr_t>(a.pred[l]) & 15) == 0);
         a.rows_in_layer[l] = (long long)a.B * g.gh[l] * g.gw[l];
         if (a.rows_in_layer[l] >= 0x7fffffffll - 64) return cudaErrorInvalidValue;
+        const unsigned long long cells_l = (unsigned long long)g.gh[l] * g.gw[l];
+        a.cells_magic[l] = cells_l > 1 ? ~0ull / cells_l + 1ull : 0ull;
     }
     // pool row stride: an odd number of float4 (fast path) / an odd number of floats
     // (generic path) so that lane-per-row reads hit distinct banks
     int stride = fast ? (dmax / 4 | 1) * 4 : (dmax | 1);
     if (fast && stride < dmax) stride += 8;
+
+    // ---- warp-specialised kernel: 3 anchors per layer, up to 128 classes ----------------
+    static int env_impl = -1;      // MGD_DECODE_IMPL=legacy: the round-1 kernel (A/B measurements)
+    static int env_shape = 0;      // MGD_DECODE_SHAPE=1|2: alternative CTA shapes (measurements)
+    if (env_impl < 0) {
+        const char* e = getenv("MGD_DECODE_IMPL");
+        env_impl = e && !strcmp(e, "legacy") ? 1 : 0;
+        const char* sh = getenv("MGD_DECODE_SHAPE");
+        env_shape = sh ? atoi(sh) : 0;
+    }
+    if (fast && g.C <= 128 && !env_impl) {
+        long long blocks = 0;
+        for (int l = 0; l < g.L; ++l) blocks += (a.rows_in_layer[l] + 31) / 32;
+        auto run = [&](auto shape) -> cudaError_t {
+            using Sh = decltype(shape);
+            const size_t smem = (size_t)Sh::kGroups * Sh::kSlots * ws::kSlotRows * stride * sizeof(float);
+            int ctas_per_sm = (int)((227 * 1024) / (smem + 4096 + 1024));
+            if (ctas_per_sm > 2) ctas_per_sm = 2;
+            if (ctas_per_sm < 1) return cudaErrorInvalidConfiguration;
+            long long grid = (long long)num_sms * ctas_per_sm;
+            // a producer should have a few blocks of every layer to walk
+            const long long needed = (blocks + Sh::kGroups * 4 - 1) / (Sh::kGroups * 4);
+            if (grid > needed) grid = needed;
+            if (grid < 1) grid = 1;
+            auto kernel = ws::decode_ws_kernel<Sh>;
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            prof_mark_begin(PROF_DECODE_COMPACT, stream);
+            kernel<<<(unsigned)grid, Sh::kThreads, smem, stream>>>(a, stride);
+            prof_mark_end(PROF_DECODE_COMPACT, stream);
+            return cudaGetLastError();
+        };
+        // wide rows (more than ~96 channels): the three-group shape no longer fits twice per SM
+        const bool wide = (size_t)3 * 3 * ws::kSlotRows * stride * sizeof(float) + 5120 > (227 * 1024) / 2;
+        cudaError_t err;
+        if (env_shape == 1) err = run(ws::Shape<3, 2, 4>());
+        else if (env_shape == 2 || wide) err = run(ws::Shape<2, 2, 4>());
+        else err = run(ws::Shape<2, 3, 3>());
+        if (err != cudaErrorInvalidConfiguration) return err;
+        cudaGetLastError();                 // too wide even for one CTA per SM: generic kernel
+    }
     static int env_pool = -1;
     if (env_pool < 0) { const char* e = getenv("MGD_DECODE_POOL_ROWS"); env_pool = e ? atoi(e) : 0; }
     int pool_rows = env_pool == 32 || env_pool == 24 || env_pool == 16 ? env_pool : 32;

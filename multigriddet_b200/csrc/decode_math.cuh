@@ -93,9 +93,19 @@ static __device__ void octet_probs(float* x, int n, int j, unsigned m, bool use_
     }
 }
 
+// e^x by one MUFU.EX2 (flush-to-zero: no range fix-up code).  Only for the conservative
+// bounds of the filter levels: a flushed term makes a softmax denominator smaller, i.e. the
+// bound larger.
+__device__ __forceinline__ float fast_exp(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 __device__ __forceinline__ float fast_sigmoid(float x)
 {
-    return __fdividef(1.0f, 1.0f + __expf(-x));
+    return __fdividef(1.0f, 1.0f + fast_exp(-x));
 }
 
 // One coordinate pair of a cell's box in float64: multigrid_decode.py:151-163 then

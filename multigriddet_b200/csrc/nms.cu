@@ -832,7 +832,10 @@ soft_nms_kernel(const __grid_constant__ NmsArgs a)
     // ---- sequential decay in the original score order ------------------------------------
     for (int i = 0; i < M; ++i) {
         const int cur = (int)(val[i] & 0xffffffffu);
-        const double sc = soft[cur];                       // uniform across the CTA
+        // every thread reads soft[cur] BEFORE the barrier and thread 0 zeroes it only after:
+        // the branch below is then uniform for any threshold (also <= 0) and any score
+        const double sc = soft[cur];
+        __syncthreads();
         if (sc < a.soft_thr) {                             // nms.py:265-267
             if (tid == 0) soft[cur] = 0.0;
             continue;
@@ -1043,11 +1046,13 @@ wbf_kernel(const __grid_constant__ NmsArgs a)
 
     // ---- clustering: leader loop (wbf.py:159-183) -------------------------------------------
     for (int i = 0; i < V; ++i) {
-        if (leader_of[i] >= 0) continue;                       // already absorbed (uniform)
+        // leader_of[i] is only ever written in an earlier, non-skipped iteration, and each of
+        // those ends in a barrier: the test is uniform.  Leaders keep -1 inside the loop (a
+        // store here would race with slower warps still reading the flag) and are marked after.
+        if (leader_of[i] >= 0) continue;
         const int pi = order[i];
         const BoxD lbx = boxes[pi];
         const int lcls = class_of(pi);
-        if (tid == 0) leader_of[i] = i;
         for (int j = i + 1 + tid; j < V; j += kThreads) {
             if (leader_of[j] >= 0) continue;
             const int pj = order[j];
@@ -1056,6 +1061,9 @@ wbf_kernel(const __grid_constant__ NmsArgs a)
         }
         __syncthreads();
     }
+    for (int i = tid; i < V; i += kThreads)
+        if (leader_of[i] < 0) leader_of[i] = i;
+    __syncthreads();
 
     // ---- fusion: one thread per leader, members in sorted order (wbf.py:189-213) ---------------
     for (int i = tid; i < V; i += kThreads) {

@@ -128,6 +128,12 @@ class MultiGridDecoder:
                           per_class: bool = False, return_xyxy: bool = True):
         """B independent ``postprocess`` calls in one launch; returns a list of B
         ``(boxes, classes, scores)`` triples."""
+        # the reference normalises wh by self.input_shape (:163) and un-letterboxes with
+        # model_image_size (:205-216); the kernel has one model size, so they must agree
+        if tuple(int(v) for v in model_image_size) != tuple(int(v) for v in self.input_shape):
+            raise ValueError(f"model_image_size {tuple(model_image_size)} differs from the decoder's "
+                             f"input_shape {tuple(self.input_shape)}: construct the decoder with "
+                             "input_shape=model_image_size")
         want = ("boxes_xyxy" if return_xyxy else "boxes_xywh", "scores", "classes")
         det = engine.decode_nms(multigriddet_outputs, image_shapes, model_image_size,
                                 self.anchors, self.num_classes, max_boxes, confidence,

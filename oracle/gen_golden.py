@@ -174,6 +174,104 @@ def nms_cases():
     print("nms cases written")
 
 
+def reference_per_class(post, dec, boxes, classes, scores, thr, nms_cls, max_boxes):
+    """Per-class NMS out of reference code only: partition by class, the
+    reference's greedy NMS per partition (nms.py:83-187), concatenate, ``_filter_boxes``
+    top-k (multigrid_decode.py:322-345).  Returned in descending-score order."""
+    kb, kc, ks = [], [], []
+    for c in np.unique(classes):
+        m = classes == c
+        b, cl, sc = nms_cls().apply_nms(boxes[m], classes[m], scores[m], thr, 0.0)
+        if b:
+            kb.append(b[0]); kc.append(cl[0]); ks.append(sc[0])
+    if not kb:
+        return np.zeros((0, 4)), np.zeros((0,), np.int64), np.zeros((0,))
+    b, c, sc = dec._filter_boxes(np.concatenate(kb), np.concatenate(kc), np.concatenate(ks), max_boxes)
+    order = np.argsort(-sc, kind="stable")
+    return b[order], c[order], sc[order]
+
+
+def perclass_cases():
+    """tests/golden/perclass_cases.npz: per-class NMS composed of reference code, on the
+    explicit boxes of nms_cases.npz and on a COCO-608 head (the north star's own wording)."""
+    post = ref_loader.load_postprocess()
+    enc = ref_loader.load_encoder()
+    z = np.load(os.path.join(OUT, "nms_cases.npz"))
+    dec = post.MultiGridDecoder(synth.coco_anchors(np.float32), 80)
+    store = {}
+    i = 0
+    while f"n{i}_boxes" in z:
+        boxes, scores, classes = z[f"n{i}_boxes"], z[f"n{i}_scores"], z[f"n{i}_classes"]
+        for name, cls in (("diou", post.DIoUNMS), ("standard", post.StandardNMS)):
+            for thr in (0.3, 0.5):
+                for mx in (1000, 20):
+                    b, c, sc = reference_per_class(post, dec, boxes, classes, scores, thr, cls, mx)
+                    store[f"n{i}_{name}_{thr}_{mx}_boxes"] = b
+                    store[f"n{i}_{name}_{thr}_{mx}_classes"] = c
+                    store[f"n{i}_{name}_{thr}_{mx}_scores"] = sc
+        i += 1
+    np.savez_compressed(os.path.join(OUT, "perclass_cases.npz"), **store)
+    print("per-class NMS cases written:", i)
+
+
+def coco608_inputs(B=2, N=100, seed=400):
+    """Deterministic COCO-608 head outputs (regenerated bit-identically by the tests from the
+    same seeds: nothing of the 2.67 MB / image tensor is stored)."""
+    S, C = 608, 80
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(seed, B, N, S, C, anchors=anchors)
+    return S, C, anchors, boxes
+
+
+def coco608_case():
+    """tests/golden/coco608_detections.npz: the reference's detections on a full-size COCO head
+    (class-agnostic DIoU and per-class mode), plus sampled rows of its dense decode tensor.
+    Inputs are regenerated from seeds; a SHA-256 of the head tensor guards that."""
+    import hashlib
+    post = ref_loader.load_postprocess()
+    enc = ref_loader.load_encoder()
+    S, C, anchors, boxes = coco608_inputs()
+    y = enc(boxes.copy(), (S, S), anchors, C, False)
+    preds = [p.numpy() for p in synth.planted_head_outputs([torch.from_numpy(a) for a in y], 3, seed=401)]
+    h = hashlib.sha256()
+    for p in preds:
+        h.update(np.ascontiguousarray(p).tobytes())
+    dec = post.MultiGridDecoder(anchors, C, input_shape=(S, S))
+    store = {"sha256": np.array(h.hexdigest()), "S": S, "C": C, "B": len(boxes)}
+    dense = dec.decode_predictions([p.copy() for p in preds])
+    store["dense_sample_rows"] = np.arange(0, dense.shape[1], 97)
+    store["dense_sample"] = dense[:, ::97, :]
+    knobs = [dict(image_shape=(608, 608), confidence=0.001, nms_threshold=0.45, max_boxes=100),
+             dict(image_shape=(480, 640), confidence=0.1, nms_threshold=0.45, max_boxes=100),
+             dict(image_shape=(1080, 1920), confidence=0.001, nms_threshold=0.5, max_boxes=30)]
+    store["n_knobs"] = len(knobs)
+    for k, kn in enumerate(knobs):
+        for key, v in kn.items():
+            store[f"k{k}_{key}"] = np.array(v)
+        for b in range(len(boxes)):
+            one = [p[b:b + 1].copy() for p in preds]
+            bx, cl, sc = dec.postprocess(one, kn["image_shape"], (S, S), max_boxes=kn["max_boxes"],
+                                         confidence=kn["confidence"], nms_threshold=kn["nms_threshold"],
+                                         nms_method="diou")
+            store[f"k{k}_b{b}_xyxy"], store[f"k{k}_b{b}_classes"], store[f"k{k}_b{b}_scores"] = \
+                np.asarray(bx), np.asarray(cl), np.asarray(sc)
+            # per-class mode: reference decode + letterbox + threshold (:262-278), then the
+            # per-partition composition, then _convert_to_xyxy (:397-422)
+            corrected = dec.correct_boxes(dec.decode_predictions(one), kn["image_shape"], (S, S))
+            cls_all = np.argmax(corrected[..., 5:], axis=-1)
+            pos = np.where(corrected[..., 4] >= kn["confidence"])
+            cb, cc, cs = corrected[..., 0:4][pos], cls_all[pos], corrected[..., 4][pos]
+            pb, pc, ps = reference_per_class(post, dec, cb, cc, cs, kn["nms_threshold"], post.DIoUNMS,
+                                             kn["max_boxes"])
+            store[f"k{k}_b{b}_pc_xyxy"] = dec._convert_to_xyxy(pb, kn["image_shape"]) if len(pb) else np.zeros((0, 4), np.int32)
+            store[f"k{k}_b{b}_pc_classes"] = pc
+            store[f"k{k}_b{b}_pc_scores"] = ps
+            store[f"k{k}_b{b}_candidates"] = np.array(len(cs))
+        print("coco608 knob", k, "dets", [len(store[f"k{k}_b{b}_scores"]) for b in range(len(boxes))],
+              "per-class", [len(store[f"k{k}_b{b}_pc_scores"]) for b in range(len(boxes))])
+    np.savez_compressed(os.path.join(OUT, "coco608_detections.npz"), **store)
+
+
 def synth_eval_set(seed, B, M, N, C, ties=False):
     """Padded detections / ground truth shaped like an evaluation run: detections are
     jittered copies of ground-truth boxes (int32 xyxy like _convert_to_xyxy emits) with
@@ -286,7 +384,7 @@ if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found at " + ref_loader.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
-    only = sys.argv[1:] or ["encode", "decode", "nms", "metrics", "boxes"]
+    only = sys.argv[1:] or ["encode", "decode", "nms", "metrics", "boxes", "perclass", "coco608"]
     if "encode" in only:
         encode_cases()
     if "decode" in only:
@@ -297,5 +395,9 @@ if __name__ == "__main__":
         metrics_cases()
     if "boxes" in only:
         boxes_cases()
+    if "perclass" in only:
+        perclass_cases()
+    if "coco608" in only:
+        coco608_case()
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden fixtures: {total / 1e6:.2f} MB in {OUT}")

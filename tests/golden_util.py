@@ -59,3 +59,20 @@ def assert_encode_matches(got, ref, exact_floats):
             assert np.array_equal(g[..., 2:4], r[..., 2:4])
         else:
             np.testing.assert_allclose(g[..., 2:4], r[..., 2:4], rtol=1e-5, atol=1e-6)
+
+
+def coco608_inputs(c_oracle_encode):
+    """Regenerate the inputs of coco608_detections.npz from their seeds (oracle/gen_golden.py:
+    coco608_inputs / coco608_case) and check them against the stored SHA-256."""
+    import hashlib
+    import torch
+    from multigriddet_b200 import synth
+    S, C = 608, 80
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(400, 2, 100, S, C, anchors=anchors)
+    y = c_oracle_encode(boxes, (S, S), anchors, C)
+    preds = [p.numpy() for p in synth.planted_head_outputs([torch.from_numpy(a) for a in y], 3, seed=401)]
+    h = hashlib.sha256()
+    for p in preds:
+        h.update(np.ascontiguousarray(p).tobytes())
+    return S, C, anchors, preds, h.hexdigest()

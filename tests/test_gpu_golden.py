@@ -208,3 +208,49 @@ def test_threads_share_one_decoder():
                                                      nms_threshold=0.45), range(64)))
     for o in outs:
         assert all(np.array_equal(a, b) for a, b in zip(o, ref))
+
+
+def test_per_class_nms_against_reference_composition():
+    """a-9 through the C ABI: per_class keeps == the reference's per-partition composition."""
+    z = np.load(G.GOLDEN + "/nms_cases.npz")
+    pc = np.load(G.GOLDEN + "/perclass_cases.npz")
+    i = 0
+    while f"n{i}_boxes" in z:
+        boxes, scores, classes = z[f"n{i}_boxes"], z[f"n{i}_scores"], z[f"n{i}_classes"]
+        for name in ("diou", "standard"):
+            for thr in (0.3, 0.5):
+                keep = engine.nms(boxes, scores, classes, thr, name, True)
+                for mx in (1000, 20):
+                    k = keep[:mx]
+                    assert np.array_equal(scores[k], pc[f"n{i}_{name}_{thr}_{mx}_scores"])
+                    assert np.array_equal(boxes[k], pc[f"n{i}_{name}_{thr}_{mx}_boxes"])
+                    assert np.array_equal(classes[k], pc[f"n{i}_{name}_{thr}_{mx}_classes"])
+        i += 1
+
+
+def test_coco608_against_reference_golden(c_oracle, nms_kernel_choice):
+    """COCO 608 (configs[2] geometry) against detections of the reference itself, in the
+    class-agnostic and the per-class mode; inputs regenerated from seeds (SHA-256 checked)."""
+    z = np.load(G.GOLDEN + "/coco608_detections.npz")
+    S, C, anchors, preds, sha = G.coco608_inputs(c_oracle.encode_targets)
+    assert sha == str(z["sha256"]), "regenerated head outputs differ from the generator's"
+    B = len(preds[0])
+    for k in range(int(z["n_knobs"])):
+        kn = dict(max_boxes=int(z[f"k{k}_max_boxes"]), confidence=float(z[f"k{k}_confidence"]),
+                  nms_threshold=float(z[f"k{k}_nms_threshold"]), nms_method="diou")
+        ishape = tuple(int(v) for v in z[f"k{k}_image_shape"])
+        for per_class, tag in ((False, ""), (True, "pc_")):
+            got = engine.decode_nms(preds, ishape, (S, S), anchors, C, per_class=per_class,
+                                    return_stats=True, **kn)
+            if not per_class:
+                assert got["stats"]["n_candidates"] == sum(int(z[f"k{k}_b{b}_candidates"]) for b in range(B))
+            for b in range(B):
+                ref_s = z[f"k{k}_b{b}_{tag}scores"]
+                n = len(ref_s)
+                assert int(got["counts"][b]) == n
+                assert np.array_equal(got["scores"][b, :n], ref_s)          # bit-for-bit float32 scores
+                assert np.array_equal(got["classes"][b, :n], z[f"k{k}_b{b}_{tag}classes"])
+                diff = got["boxes_xyxy"][b, :n] != z[f"k{k}_b{b}_{tag}xyxy"].reshape(-1, 4)
+                if diff.any():                               # only at a .5 rounding boundary
+                    xy = got["boxes_xywh"][b, :n].copy(); xy[:, 2:] += xy[:, :2]
+                    assert np.all(np.abs((xy + 0.5) - np.round(xy + 0.5))[diff] < 1e-4)

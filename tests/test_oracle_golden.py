@@ -111,3 +111,48 @@ def test_nms_oracle_matches_reference_golden():
             assert np.array_equal(boxes[keep], z[f"n{i}_soft_{sigma}_boxes"])
         i += 1
     assert i == 4
+
+
+def test_per_class_nms_oracle_matches_reference_composition():
+    """per-class NMS := the reference's greedy NMS per class partition, merged
+    by score, top-k (perclass_cases.npz holds that composition run on reference code)."""
+    z = np.load(G.GOLDEN + "/nms_cases.npz")
+    pc = np.load(G.GOLDEN + "/perclass_cases.npz")
+    i = 0
+    while f"n{i}_boxes" in z:
+        boxes, scores, classes = z[f"n{i}_boxes"], z[f"n{i}_scores"], z[f"n{i}_classes"]
+        for name, diou in (("diou", True), ("standard", False)):
+            for thr in (0.3, 0.5):
+                keep = O.greedy_nms(boxes, scores, thr, diou, classes=classes, per_class=True)
+                for mx in (1000, 20):
+                    k = keep[:mx]
+                    assert np.array_equal(scores[k], pc[f"n{i}_{name}_{thr}_{mx}_scores"])
+                    assert np.array_equal(boxes[k], pc[f"n{i}_{name}_{thr}_{mx}_boxes"])
+                    assert np.array_equal(classes[k], pc[f"n{i}_{name}_{thr}_{mx}_classes"])
+        i += 1
+    assert i == 4
+
+
+def test_coco608_oracle_matches_reference_golden(c_oracle):
+    """Full-size COCO head: class-agnostic and per-class detections of the reference."""
+    z = np.load(G.GOLDEN + "/coco608_detections.npz")
+    S, C, anchors, preds, sha = G.coco608_inputs(c_oracle.encode_targets)
+    assert sha == str(z["sha256"]), "regenerated head outputs differ from the generator's"
+    dense = O.decode_predictions(preds, anchors, (S, S), C)
+    if G.numpy_pinned():
+        assert np.array_equal(dense[:, ::97, :], z["dense_sample"])
+    else:
+        np.testing.assert_allclose(dense[:, ::97, :], z["dense_sample"], rtol=1e-6, atol=1e-30)
+    for k in range(int(z["n_knobs"])):
+        kn = dict(max_boxes=int(z[f"k{k}_max_boxes"]), confidence=float(z[f"k{k}_confidence"]),
+                  nms_threshold=float(z[f"k{k}_nms_threshold"]), nms_method="diou")
+        ishape = tuple(int(v) for v in z[f"k{k}_image_shape"])
+        for per_class, tag in ((False, ""), (True, "pc_")):
+            cc = c_oracle.decode_nms(preds, [ishape], (S, S), anchors, C, per_class=per_class, **kn)
+            for b in range(len(preds[0])):
+                ref_s = z[f"k{k}_b{b}_{tag}scores"]
+                n = len(ref_s)
+                assert int(cc["counts"][b]) == n
+                assert np.array_equal(cc["scores"][b, :n], ref_s)
+                assert np.array_equal(cc["classes"][b, :n], z[f"k{k}_b{b}_{tag}classes"])
+                assert np.array_equal(cc["boxes_xyxy"][b, :n], z[f"k{k}_b{b}_{tag}xyxy"].reshape(-1, 4))

@@ -78,3 +78,28 @@ def test_reference_error_conventions():
     assert post.DIoUNMS().apply_nms(np.zeros((0, 4)), np.zeros(0), np.zeros(0), 0.5, 0.1) == ([], [], [])
     with pytest.raises(NotImplementedError):      # 'standard' is not wired in the reference
         dec.handle_predictions(np.ones((1, 3, 85)), (608, 608), nms_method="standard")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_per_class_nms_equals_reference_per_partition(seed):
+    """SURVEY 8a-9 / VERDICT r1 item 6a: O.greedy_nms(per_class=True) against the reference's
+    DIoUNMS / StandardNMS (nms.py:83-187) run per argmax-class partition, merged by score,
+    then the reference's top-k (multigrid_decode.py:336-345)."""
+    from oracle.gen_golden import reference_per_class
+    post = ref_loader.load_postprocess()
+    dec = post.MultiGridDecoder(synth.coco_anchors(np.float32), 80)
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(50, 700))
+    xy = rng.uniform(0, 300, size=(n, 2))
+    wh = rng.uniform(4, 150, size=(n, 2))
+    boxes = np.concatenate([xy, wh], 1)
+    scores = rng.uniform(0.01, 1, size=n)
+    classes = rng.integers(0, 5, size=n)
+    for cls, diou in ((post.DIoUNMS, True), (post.StandardNMS, False)):
+        for thr in (0.3, 0.45, 0.6):
+            keep = O.greedy_nms(boxes, scores, thr, diou, classes=classes, per_class=True)
+            for mx in (n, 30):
+                b, c, s = reference_per_class(post, dec, boxes, classes, scores, thr, cls, mx)
+                assert np.array_equal(scores[keep[:mx]], s)
+                assert np.array_equal(boxes[keep[:mx]], b)
+                assert np.array_equal(classes[keep[:mx]], c)
