@@ -71,6 +71,8 @@ struct DecodeArgs {
     unsigned long long cells_magic[MGD_MAX_LAYERS];   // floor(2^64 / (gh*gw)) + 1 (0 when gh*gw == 1): row -> image
     Cand* cand;                       // (B, cells)
     int* counts;                      // (B,)
+    int chunk_blocks;                 // consecutive 32-row blocks a producer warp takes at a time
+    int debug;                        // MGD_DECODE_DEBUG (measurements only): 1 scan only, 2 no level 3, 4 no level 2/3
 };
 
 struct NmsArgs {

@@ -14,9 +14,9 @@
 //             is filling (cp.async.bulk -> the slot's `full` mbarrier); a full slot is
 //             published with one arrive;
 //   consumers take published slots in order (shared counter), run level 2 (lane per
-//             row) and level 3 (eight lanes per row, exact) straight from shared memory
-//             without ever writing to it, and hand the slot back through its `empty`
-//             mbarrier.
+//             row) and level 3 (eight lanes per row, exact) straight from shared memory,
+//             append the slot's candidates to the per-image lists with one atomicAdd per
+//             image, and hand the slot back through its `empty` mbarrier.
 // The scan's DRAM latency and the exact evaluation's arithmetic latency thus overlap
 // instead of alternating inside one warp (round 1: 46% issue utilisation, 23% of the
 // warp slots).  decode_compact_kernel below is the generic fallback (any anchor count,
@@ -344,21 +344,25 @@ decode_compact_kernel(const __grid_constant__ DecodeArgs a, int pool_stride)
 // =================================================================================
 namespace ws {
 
-// Shape of a CTA: kGroups groups of (1 producer + kConsumers consumer warps), each around
-// its own ring of kSlots slots.  Measured instruction budget per COCO image (planted head):
-// producer ~43 k warp-instructions (scan + one TMA issue per surviving row), consumers ~80 k,
-// hence two consumers per producer; three groups x three slots fill the shared memory of an
-// SM with two CTAs (18 warps).
-template <int kConsumers_, int kGroups_, int kSlots_>
+// Shape of a CTA: kProducers producer warps and kConsumers consumer warps around ONE ring of
+// kSlots slots.  Slots are handed out by ticket: a producer takes the next sequence number when
+// it has a first row to store, a consumer takes the next sequence number when it is free; both
+// counters run through the same sequence, so the consumer of ticket s waits for the producer of
+// ticket s, whoever that is (slot = s mod kSlots, mbarrier phase = s div kSlots).
+// Measured per COCO image (planted head): producers ~43 k warp-instructions (scan + one TMA issue
+// per surviving row), consumers ~80 k, both bound by dependent-issue latency: about two
+// consumers per producer, and as many slots as shared memory holds (a slot is busy for the fill,
+// the DRAM latency of its last row, and the exact evaluation).
+template <int kProducers_, int kConsumers_, int kSlots_>
 struct Shape {
+    static constexpr int kProducers = kProducers_;
     static constexpr int kConsumers = kConsumers_;
-    static constexpr int kGroupWarps = 1 + kConsumers_;
-    static constexpr int kGroups = kGroups_;
-    static constexpr int kThreads = kGroups_ * (1 + kConsumers_) * 32;
+    static constexpr int kThreads = (kProducers_ + kConsumers_) * 32;
     static constexpr int kSlots = kSlots_;
+    static constexpr int kCtasPerSm = kSlots_ > 9 ? 1 : 2;      // by shared memory (11 KB per COCO slot)
 };
 constexpr int kSlotRows = 32;
-constexpr int kPrefetch = 4;                  // level-1 loads in flight per producer lane
+constexpr int kPrefetch = 16;                 // level-1 blocks in flight per producer (cp.async ring, 512 B each)
 
 struct SlotMeta {
     int row[kSlotRows];                       // row index within the layer (b * cells_l + cell)
@@ -416,12 +420,27 @@ __device__ __forceinline__ void near_track(float d, float thr, int i, int& first
         : "+r"(first), "+r"(cnt) : "f"(d), "f"(thr), "r"(i));
 }
 
+__device__ __forceinline__ int ld_acquire_smem(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_smem(int* p, int v)
+{
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
 struct GroupShared {
+    float4* stage;            // [kPrefetch][32]: level-1 inputs in flight (this producer's own)
     float* rows;              // [kSlots][kSlotRows][stride]
     SlotMeta* meta;           // [kSlots]
-    uint64_t* full;           // [kSlots]
-    uint64_t* empty;          // [kSlots]
-    int* next_seq;            // consumers' shared slot counter
+    uint64_t* full;           // [kSlots]: TMA bytes of the slot's current use have landed
+    int* published;           // [kSlots]: ticket most recently published in the slot
+    int* released;            // [kSlots]: completed uses of the slot
+    int* fill_seq;            // producers' ticket counter
+    int* next_seq;            // consumers' ticket counter
+    int* producers_done;
     int stride;
 };
 
@@ -430,6 +449,7 @@ __device__ __forceinline__ void producer(const DecodeArgs& a, const GroupShared&
 {
     constexpr int kSlots = Sh::kSlots;
     constexpr int kConsumers = Sh::kConsumers;
+    constexpr int kProducers = Sh::kProducers;
     const HeadGeom& g = a.g;
     const int lane = threadIdx.x & 31;
     const bool softmax = a.use_softmax != 0;
@@ -437,16 +457,28 @@ __device__ __forceinline__ void producer(const DecodeArgs& a, const GroupShared&
     int seq = 0, slot = 0, count = 0;
     bool have_slot = false;
 
+    // Tickets from different producers complete out of order, so a waiter can be several uses of
+    // a slot ahead of the slot's state; an mbarrier only distinguishes the parity of a phase.
+    // The hand-over therefore goes through per-slot sequence words (released / published, with
+    // release / acquire semantics); the mbarrier is only waited on for the TMA bytes, once the
+    // slot is known to be in the waiter's own use.
     auto acquire = [&]() {
+        if (lane == 0) {
+            seq = atomicAdd(gs.fill_seq, 1);
+            const int use = seq / kSlots;
+            while (ld_acquire_smem(&gs.released[seq % kSlots]) != use) __nanosleep(40);
+        }
+        seq = __shfl_sync(0xffffffffu, seq, 0);
         slot = seq % kSlots;
-        mbar_wait(&gs.empty[slot], (((unsigned)(seq / kSlots)) & 1u) ^ 1u);
         have_slot = true;
     };
     auto publish = [&](int cnt, int layer) {
         if (lane == 0) { gs.meta[slot].count = cnt; gs.meta[slot].layer = layer; }
-        __syncwarp();                                   // metadata of all lanes before the arrive
-        if (lane == 0) mbar_arrive(&gs.full[slot]);
-        ++seq;
+        __syncwarp();                                   // metadata of all lanes before the release
+        if (lane == 0) {
+            mbar_arrive(&gs.full[slot]);
+            st_release_smem(&gs.published[slot], seq);
+        }
         have_slot = false;
         count = 0;
     };
@@ -456,23 +488,57 @@ __device__ __forceinline__ void producer(const DecodeArgs& a, const GroupShared&
         const int n_rows = (int)a.rows_in_layer[layer];
         const int n_blocks = (n_rows + 31) >> 5;
         const float* base = a.pred[layer];
-        auto load_head = [&](int blk, float4& q) {
+        // Level-1 inputs ([obj, 3 anchor logits] = 16 bytes of every row) arrive through a ring
+        // of cp.async copies, kPrefetch blocks ahead: the scan is DRAM-bound (the memory system
+        // moves a 128-byte line per row whatever the request size) and needs far more loads in
+        // flight than registers could hold.  Every lane reads back only what it copied itself.
+        auto issue_head = [&](int blk, int st) {
             const int row = blk * 32 + lane;
-            q = make_float4(NAN, 0.f, 0.f, 0.f);          // NaN never passes a >= test
             if (blk < n_blocks && row < n_rows)
-                q = __ldg(reinterpret_cast<const float4*>(base + (size_t)row * D + 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                             ::"r"(smem_u32(gs.stage + st * 32 + lane)), "l"(base + (size_t)row * D + 4) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        float4 q[kPrefetch];
+        // a producer walks chunks of kChunk consecutive blocks (DRAM page locality; the rows of
+        // a slot then belong to one or two images), the chunks strided over the producers;
+        // kPrefetch is a multiple of the chunk, so the block kPrefetch steps ahead is kPrefetch*P on
+        const int kChunk = a.chunk_blocks;              // 1, 2, 4, 8 or 16 (divides kPrefetch)
         #pragma unroll
-        for (int k = 0; k < kPrefetch; ++k) load_head(p + k * P, q[k]);
-        for (int blk0 = p; blk0 < n_blocks; blk0 += kPrefetch * P) {
-            #pragma unroll
-            for (int k = 0; k < kPrefetch; ++k) {
-                const int blk = blk0 + k * P;
-                if (blk >= n_blocks) break;
-                const float4 h = q[k];
-                load_head(blk + kPrefetch * P, q[k]);
+        for (int k = 0; k < kPrefetch; ++k) issue_head((p + (k / kChunk) * P) * kChunk + k % kChunk, k);
+        // survivors: one TMA copy per row into the slot being filled
+        auto stage_rows = [&](int blk, unsigned todo, float bound) {
+            const int row = blk * 32 + lane;
+            while (todo) {
+                if (!have_slot) acquire();
+                const int free_slots = kSlotRows - count;
+                const int rank = __popc(todo & ((1u << lane) - 1u));
+                const bool take = ((todo >> lane) & 1u) && rank < free_slots;
+                const unsigned taken = __ballot_sync(0xffffffffu, take);
+                const int n_new = __popc(taken);
+                if (take) {
+                    gs.meta[slot].row[count + rank] = row;
+                    gs.meta[slot].bound[count + rank] = bound;
+                }
+                if (lane == 0) mbar_expect_tx(&gs.full[slot], (uint32_t)n_new * D * sizeof(float));
+                __syncwarp();
+                if (take)
+                    bulk_g2s(gs.rows + ((size_t)slot * kSlotRows + count + rank) * gs.stride,
+                             base + (size_t)row * D, (uint32_t)D * sizeof(float), &gs.full[slot]);
+                count += n_new;
+                todo &= ~taken;
+                if (count == kSlotRows) publish(count, layer);
+            }
+        };
+        int st = 0;
+        for (int chunk = p; chunk * kChunk < n_blocks; chunk += P) {
+            for (int u = 0; u < kChunk; ++u) {
+                const int blk = chunk * kChunk + u;
+                asm volatile("cp.async.wait_group %0;" ::"n"(kPrefetch - 1) : "memory");
                 const int row = blk * 32 + lane;
+                float4 h = gs.stage[st * 32 + lane];
+                if (row >= n_rows) h.x = NAN;               // NaN never passes a >= test
+                issue_head(blk + kPrefetch * P, st);
+                st = st + 1 == kPrefetch ? 0 : st + 1;
 
                 // ---- level 1: lane per row -----------------------------------------------
                 float bound = 0.f;
@@ -489,39 +555,28 @@ __device__ __forceinline__ void producer(const DecodeArgs& a, const GroupShared&
                     pass = bound >= a.score_lo;
                 }
                 unsigned todo = __ballot_sync(0xffffffffu, pass);
-
-                // ---- survivors: TMA copy into the slot being filled ----------------------
-                while (todo) {
-                    if (!have_slot) acquire();
-                    const int free_slots = kSlotRows - count;
-                    const int rank = __popc(todo & ((1u << lane) - 1u));
-                    const bool take = ((todo >> lane) & 1u) && rank < free_slots;
-                    const unsigned taken = __ballot_sync(0xffffffffu, take);
-                    const int n_new = __popc(taken);
-                    if (take) {
-                        gs.meta[slot].row[count + rank] = row;
-                        gs.meta[slot].bound[count + rank] = bound;
-                    }
-                    if (lane == 0) mbar_expect_tx(&gs.full[slot], (uint32_t)n_new * D * sizeof(float));
-                    __syncwarp();
-                    if (take)
-                        bulk_g2s(gs.rows + ((size_t)slot * kSlotRows + count + rank) * gs.stride,
-                                 base + (size_t)row * D, (uint32_t)D * sizeof(float), &gs.full[slot]);
-                    count += n_new;
-                    todo &= ~taken;
-                    if (count == kSlotRows) publish(count, layer);
-                }
+                if (a.debug & 1) todo = 0;
+                stage_rows(blk, todo, bound);
             }
         }
         if (count) publish(count, layer);              // slots never mix layers
     }
-    for (int c = 0; c < kConsumers; ++c) {             // one terminal slot per consumer
-        acquire();
-        publish(-1, 0);
-    }
+    // the last producer to finish hands every consumer a terminal slot
+    int done = 0;
+    if (lane == 0) done = atomicAdd(gs.producers_done, 1) + 1;
+    done = __shfl_sync(0xffffffffu, done, 0);
+    if (done == kProducers)
+        for (int c = 0; c < kConsumers; ++c) {
+            acquire();
+            publish(-1, 0);
+        }
 }
 
-template <class Sh>
+// kC: the class count when it is known at compile time (80: COCO, the benchmark), else 0.
+// With a constant trip count the whole exact evaluation of a round -- ten class chains, the
+// anchor / objectness chain and the three reciprocals -- is one basic block the scheduler can
+// interleave; the consumers are bound by dependent-issue latency, not by issue slots.
+template <class Sh, int kC>
 __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared& gs,
                                          const uint32_t* tab)
 {
@@ -532,7 +587,7 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
     const int oct = lane >> 3;
     const bool softmax = a.use_softmax != 0;
     const bool rescore = a.rescore != 0;
-    const int C = g.C;
+    const int C = kC ? kC : g.C;
     const int body = C >= 8 ? (C & ~7) : 0;             // NumPy: 8 accumulators over the body,
     const int tail = C - body;                          // then the tail one by one (n < 8: all tail)
     constexpr float kNear = 0.99999f;
@@ -540,10 +595,13 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
 
     for (;;) {
         int seq = 0;
-        if (lane == 0) seq = atomicAdd(gs.next_seq, 1);
+        if (lane == 0) {
+            seq = atomicAdd(gs.next_seq, 1);
+            while (ld_acquire_smem(&gs.published[seq % kSlots]) != seq) __nanosleep(40);
+        }
         seq = __shfl_sync(0xffffffffu, seq, 0);
         const int slot = seq % kSlots;
-        mbar_wait(&gs.full[slot], ((unsigned)(seq / kSlots)) & 1u);
+        mbar_wait(&gs.full[slot], ((unsigned)(seq / kSlots)) & 1u);    // the TMA bytes of this use
         const SlotMeta& meta = gs.meta[slot];
         const int count = meta.count;
         if (count < 0) break;
@@ -551,7 +609,7 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
         const float* rows = gs.rows + (size_t)slot * kSlotRows * gs.stride;
 
         // ---- level 2: lane per row, bound including the class maximum ------------------
-        bool pass = lane < count;
+        bool pass = lane < count && !(a.debug & 4);
         float mc = -INFINITY;
         if (pass) {
             const float4* c4 = reinterpret_cast<const float4*>(rows + (size_t)lane * gs.stride + 8);
@@ -578,8 +636,10 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
             }
         }
         unsigned todo = __ballot_sync(0xffffffffu, pass);
+        if (a.debug & 2) todo = 0;
 
-        // ---- level 3: exact evaluation, octet per row, nothing written to the slot ------
+        // ---- level 3: exact evaluation, octet per row ----------------------------------------
+        unsigned cand_rows = 0;                         // rows of this slot that became candidates
         while (todo) {
             const unsigned pos = nth_set_bit(todo, oct);
             const bool live = pos < 32u;
@@ -591,18 +651,20 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
             float pa, pc, obj;
             int ka, kc;
             if (softmax) {
+                // -- anchors (lanes 0-2 of the octet) and objectness (lane 3) in one expf round --
+                const float ma = fmaxf(head.y, fmaxf(head.z, head.w));
+                const float logit = x[5 + (j < 2 ? j : 2)];
+                const float da = __fsub_rn(logit, ma);
+                const float arg = j < 3 ? (da < -104.0f ? -104.0f : da) : (j == 3 ? -head.x : 0.f);
+                const float ea = expf_full2(arg, tab);
+
                 // -- classes: exp(x - max) accumulated in NumPy's order as it is produced --
                 const float* cx = x + 8;
-                float r = 0.f, e_tail = 0.f;
+                float r = 0.f, e_tail = 0.f;            // (0 + e == e exactly: e >= 0 or NaN)
                 int near_cnt = 0, near_first = INT_MAX;
                 if (body) {
-                    {
-                        const float d = __fsub_rn(cx[j], mx);
-                        r = expf_core2(d < -104.0f ? -104.0f : d, tab);
-                        if (d >= kNearD) { near_cnt = 1; near_first = j; }
-                    }
-                    #pragma unroll 3
-                    for (int i = 8 + j; i < body; i += 8) {
+                    #pragma unroll 10
+                    for (int i = j; i < body; i += 8) {
                         // (a select, not fmaxf: NaN -- from a NaN or +inf logit -- must reach the
                         //  sum like it does in the reference, which then drops the row)
                         const float d = __fsub_rn(cx[i], mx);
@@ -624,6 +686,13 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
                         r = __fadd_rn(r, __shfl_sync(0xffffffffu, e_tail, l0 + k));
                 }
                 pc = __frcp_rn(r);                      // 1 / sum: the maximum's exponential is exactly 1
+                const float e0 = __shfl_sync(0xffffffffu, ea, l0);
+                const float e1 = __shfl_sync(0xffffffffu, ea, l0 + 1);
+                const float e2 = __shfl_sync(0xffffffffu, ea, l0 + 2);
+                const float eo = __shfl_sync(0xffffffffu, ea, l0 + 3);
+                const float sa = __fadd_rn(__fadd_rn(__fadd_rn(0.f, e0), e1), e2);  // n < 8: sequential
+                pa = __frcp_rn(sa);
+                obj = __frcp_rn(__fadd_rn(1.0f, eo));                            // :147
                 // argmax on the probabilities e/s like the reference: first index whose quotient
                 // equals the maximum quotient; only exponentials within 1e-5 of 1 can tie.  A row
                 // with a single logit within kNearD of the maximum (the maximum itself: a superset
@@ -632,7 +701,9 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
                 const unsigned many = (__ballot_sync(0xffffffffu, near_cnt > 1) >> l0) & 0xffu;
                 const bool simple = !many && __popc(has) == 1;
                 kc = __shfl_sync(0xffffffffu, near_first, l0 + (has ? __ffs((int)has) - 1 : 0));
-                if (__any_sync(0xffffffffu, !simple)) {                     // rare
+                const int n0 = e0 >= kNear, n1 = e1 >= kNear, n2 = e2 >= kNear;
+                ka = n0 ? 0 : (n1 ? 1 : 2);
+                if (__any_sync(0xffffffffu, !simple || n0 + n1 + n2 != 1)) {  // rare
                     int first = INT_MAX;
                     for (int i = j; i < C; i += 8) {
                         const float d = __fsub_rn(cx[i], mx);
@@ -643,30 +714,13 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
                     first = min(first, __shfl_xor_sync(0xffffffffu, first, 2));
                     first = min(first, __shfl_xor_sync(0xffffffffu, first, 4));
                     if (!simple) kc = first;
+                    if (n0 + n1 + n2 != 1) {
+                        ka = INT_MAX;
+                        if (n2 && __fdiv_rn(e2, sa) == pa) ka = 2;
+                        if (n1 && __fdiv_rn(e1, sa) == pa) ka = 1;
+                        if (n0 && __fdiv_rn(e0, sa) == pa) ka = 0;
+                    }
                 }
-
-                // -- anchors (lanes 0-2 of the octet) and objectness (lane 3) in one expf round --
-                const float ma = fmaxf(head.y, fmaxf(head.z, head.w));
-                const float logit = x[5 + (j < 2 ? j : 2)];
-                const float da = __fsub_rn(logit, ma);
-                const float arg = j < 3 ? (da < -104.0f ? -104.0f : da) : (j == 3 ? -head.x : 0.f);
-                const float e = expf_full2(arg, tab);
-                const float e0 = __shfl_sync(0xffffffffu, e, l0);
-                const float e1 = __shfl_sync(0xffffffffu, e, l0 + 1);
-                const float e2 = __shfl_sync(0xffffffffu, e, l0 + 2);
-                const float eo = __shfl_sync(0xffffffffu, e, l0 + 3);
-                const float sa = __fadd_rn(__fadd_rn(__fadd_rn(0.f, e0), e1), e2);  // n < 8: sequential
-                pa = __frcp_rn(sa);
-                const int n0 = e0 >= kNear, n1 = e1 >= kNear, n2 = e2 >= kNear;
-                if (n0 + n1 + n2 == 1) {
-                    ka = n0 ? 0 : (n1 ? 1 : 2);
-                } else {
-                    ka = INT_MAX;
-                    if (n2 && __fdiv_rn(e2, sa) == pa) ka = 2;
-                    if (n1 && __fdiv_rn(e1, sa) == pa) ka = 1;
-                    if (n0 && __fdiv_rn(e0, sa) == pa) ka = 0;
-                }
-                obj = __frcp_rn(__fadd_rn(1.0f, eo));                            // :147
             } else {
                 // element-wise expit; maximum and its first index
                 float best = -INFINITY;
@@ -695,72 +749,109 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
             }
             float score = obj;
             if (rescore) score = __fmul_rn(__fmul_rn(score, pa), pc);            // :170
-            if (live && j == 0 && (double)score >= a.confidence) {               // :271
-                const unsigned grow = (unsigned)meta.row[pos];
-                const unsigned long long magic = a.cells_magic[layer];
-                const unsigned b = magic ? (unsigned)__umul64hi((unsigned long long)grow, magic) : grow;
-                const int cell = (int)(grow - b * (unsigned)(g.gh[layer] * g.gw[layer]));
-                Cand cd;
-                cd.score = score;
-                cd.index = g.cell_off[layer] + cell;
-                const float4 t = *reinterpret_cast<const float4*>(x);
-                cd.t[0] = t.x; cd.t[1] = t.y; cd.t[2] = t.z; cd.t[3] = t.w;
-                cd.cls = kc;
-                cd.anchor = g.anchor_first[layer] + ka;
-                const int at = atomicAdd(a.counts + b, 1);
-                a.cand[(size_t)b * g.cells + at] = cd;
+            // A candidate leaves its result in the row's own (now dead) objectness / anchor words;
+            // the records go out once per slot, below.
+            const bool is_cand = live && j == 0 && (double)score >= a.confidence;   // :271
+            __syncwarp();                               // shadow octets are done reading the row head
+            if (is_cand) {
+                float4 res;
+                res.x = score;
+                res.y = __int_as_float(kc);
+                res.z = __int_as_float(g.anchor_first[layer] + ka);
+                res.w = 0.f;
+                *reinterpret_cast<float4*>(const_cast<float*>(x) + 4) = res;
             }
+            cand_rows |= __reduce_or_sync(0xffffffffu, is_cand ? (1u << pos) : 0u);
             #pragma unroll
             for (int q = 0; q < 4; ++q) todo &= todo - 1;
         }
-        __syncwarp();                                   // every lane is done reading the slot
-        if (lane == 0) mbar_arrive(&gs.empty[slot]);
+        // ---- records out: lane per row; one atomicAdd per image present in the slot ----------
+        // (a per-candidate atomicAdd serialises in L2: every warp of the grid works on the same
+        //  few images at any time, i.e. on the same few counters)
+        __syncwarp();
+        const bool mine = (cand_rows >> lane) & 1u;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f), res = t;
+        unsigned grow = 0;
+        if (mine) {
+            const float* x = rows + (size_t)lane * gs.stride;
+            t = *reinterpret_cast<const float4*>(x);
+            res = *reinterpret_cast<const float4*>(x + 4);
+            grow = (unsigned)meta.row[lane];
+        }
+        if (cand_rows) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes before the next TMA fill
+        __syncwarp();                                   // every lane is done with the slot
+        if (lane == 0) st_release_smem(&gs.released[slot], seq / kSlots + 1);
+        if (cand_rows) {
+            const unsigned long long magic = a.cells_magic[layer];
+            const unsigned b = magic ? (unsigned)__umul64hi((unsigned long long)grow, magic) : grow;
+            const unsigned same = __match_any_sync(0xffffffffu, mine ? b : (0x80000000u | (unsigned)lane));
+            const int leader = __ffs((int)same) - 1;
+            int base = 0;
+            if (mine && lane == leader) base = atomicAdd(a.counts + b, __popc(same));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (mine) {
+                Cand cd;
+                cd.score = res.x;
+                cd.index = g.cell_off[layer] + (int)(grow - b * (unsigned)(g.gh[layer] * g.gw[layer]));
+                cd.t[0] = t.x; cd.t[1] = t.y; cd.t[2] = t.z; cd.t[3] = t.w;
+                cd.cls = __float_as_int(res.y);
+                cd.anchor = __float_as_int(res.z);
+                a.cand[(size_t)b * g.cells + base + __popc(same & ((1u << lane) - 1u))] = cd;
+            }
+        }
     }
 }
 
-template <class Sh>
-__global__ void __launch_bounds__(Sh::kThreads, 2)
+template <class Sh, int kC>
+__global__ void __launch_bounds__(Sh::kThreads, Sh::kCtasPerSm)
 decode_ws_kernel(const __grid_constant__ DecodeArgs a, int stride)
 {
-    constexpr int kGroups = Sh::kGroups, kSlots = Sh::kSlots, kGroupWarps = Sh::kGroupWarps;
+    constexpr int kSlots = Sh::kSlots, kProducers = Sh::kProducers;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint64_t s_full[kGroups][kSlots];
-    __shared__ uint64_t s_empty[kGroups][kSlots];
-    __shared__ SlotMeta s_meta[kGroups][kSlots];
+    __shared__ uint64_t s_full[kSlots];
+    __shared__ int s_published[kSlots], s_released[kSlots];
+    __shared__ SlotMeta s_meta[kSlots];
     __shared__ uint32_t s_tab[2 * MGD_EXP2F_N];
-    __shared__ int s_next[kGroups];
+    __shared__ int s_counters[3];
+
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
-    const int grp = warp / kGroupWarps;
-    const int role = warp - grp * kGroupWarps;
     if (tid < MGD_EXP2F_N) {
         s_tab[tid] = (uint32_t)mgd_exp2f_tab[tid];
         s_tab[tid + MGD_EXP2F_N] = (uint32_t)(mgd_exp2f_tab[tid] >> 32);
     }
     if (tid == 0) {
-        for (int gq = 0; gq < kGroups; ++gq) {
-            for (int sl = 0; sl < kSlots; ++sl) {
-                mbar_init(&s_full[gq][sl], 1);
-                mbar_init(&s_empty[gq][sl], 1);
-            }
-            s_next[gq] = 0;
+        for (int sl = 0; sl < kSlots; ++sl) {
+            mbar_init(&s_full[sl], 1);
+            s_published[sl] = -1;
+            s_released[sl] = 0;
         }
+        s_counters[0] = s_counters[1] = s_counters[2] = 0;
         fence_mbar_init();
     }
     __syncthreads();
 
     GroupShared gs;
-    gs.rows = reinterpret_cast<float*>(smem_raw) + (size_t)grp * kSlots * kSlotRows * stride;
-    gs.meta = s_meta[grp];
-    gs.full = s_full[grp];
-    gs.empty = s_empty[grp];
-    gs.next_seq = &s_next[grp];
+    gs.rows = reinterpret_cast<float*>(smem_raw);
+    // producers take the HIGHEST warp ids: the issue arbiter favours them, and a producer is a
+    // serial instruction stream that everything else waits for
+    constexpr int kFirstProducer = Sh::kConsumers;
+    const int pw = warp - kFirstProducer;
+    gs.stage = reinterpret_cast<float4*>(gs.rows + (size_t)kSlots * kSlotRows * stride) +
+               (size_t)(pw >= 0 ? pw : 0) * kPrefetch * 32;
+    gs.meta = s_meta;
+    gs.full = s_full;
+    gs.published = s_published;
+    gs.released = s_released;
+    gs.fill_seq = &s_counters[0];
+    gs.next_seq = &s_counters[1];
+    gs.producers_done = &s_counters[2];
     gs.stride = stride;
-    if (role == 0)
-        producer<Sh>(a, gs, blockIdx.x * kGroups + grp, gridDim.x * kGroups);
+    if (pw >= 0)
+        producer<Sh>(a, gs, blockIdx.x * kProducers + pw, gridDim.x * kProducers);
     else
-        consumer<Sh>(a, gs, s_tab);
+        consumer<Sh, kC>(a, gs, s_tab);
 }
 
 }  // namespace ws
@@ -857,34 +948,49 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
         const char* sh = getenv("MGD_DECODE_SHAPE");
         env_shape = sh ? atoi(sh) : 0;
     }
+    static int env_debug = -1;
+    if (env_debug < 0) { const char* e = getenv("MGD_DECODE_DEBUG"); env_debug = e ? atoi(e) : 0; }
+    a.debug = env_debug;
     if (fast && g.C <= 128 && !env_impl) {
         long long blocks = 0;
         for (int l = 0; l < g.L; ++l) blocks += (a.rows_in_layer[l] + 31) / 32;
+        // slot rows are stored back to back (stride = D floats): level 3's octet reads are
+        // conflict-free at any stride, level 2's lane-per-row float4 reads take a 2-way conflict
+        // at 88 floats -- cheaper than the shared memory a padded stride costs (a fourth slot)
+        const int ws_stride = dmax;
         auto run = [&](auto shape) -> cudaError_t {
             using Sh = decltype(shape);
-            const size_t smem = (size_t)Sh::kGroups * Sh::kSlots * ws::kSlotRows * stride * sizeof(float);
-            int ctas_per_sm = (int)((227 * 1024) / (smem + 4096 + 1024));
-            if (ctas_per_sm > 2) ctas_per_sm = 2;
+            const size_t smem = (size_t)Sh::kSlots * ws::kSlotRows * ws_stride * sizeof(float) +
+                                (size_t)Sh::kProducers * ws::kPrefetch * 32 * sizeof(float4);
+            // (static shared memory: slot metadata, barriers, tables; 1 KB reserved per CTA)
+            const size_t fixed = 1024 + 1024 + (size_t)Sh::kSlots * 304;
+            int ctas_per_sm = (int)((227 * 1024) / (smem + fixed));
+            if (ctas_per_sm > Sh::kCtasPerSm) ctas_per_sm = Sh::kCtasPerSm;
             if (ctas_per_sm < 1) return cudaErrorInvalidConfiguration;
             long long grid = (long long)num_sms * ctas_per_sm;
             // a producer should have a few blocks of every layer to walk
-            const long long needed = (blocks + Sh::kGroups * 4 - 1) / (Sh::kGroups * 4);
+            const long long needed = (blocks + Sh::kProducers * 4 - 1) / (Sh::kProducers * 4);
             if (grid > needed) grid = needed;
             if (grid < 1) grid = 1;
-            auto kernel = ws::decode_ws_kernel<Sh>;
+            // big batches: chunks of 8 consecutive blocks per producer; small ones: single blocks
+            // (latency: every producer should get work)
+            a.chunk_blocks = blocks / (grid * Sh::kProducers) >= 64 ? 8 : 1;
+
+            auto kernel = g.C == 80 ? ws::decode_ws_kernel<Sh, 80> : ws::decode_ws_kernel<Sh, 0>;
             cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             prof_mark_begin(PROF_DECODE_COMPACT, stream);
-            kernel<<<(unsigned)grid, Sh::kThreads, smem, stream>>>(a, stride);
+            kernel<<<(unsigned)grid, Sh::kThreads, smem, stream>>>(a, ws_stride);
             prof_mark_end(PROF_DECODE_COMPACT, stream);
             return cudaGetLastError();
         };
-        // wide rows (more than ~96 channels): the three-group shape no longer fits twice per SM
-        const bool wide = (size_t)3 * 3 * ws::kSlotRows * stride * sizeof(float) + 5120 > (227 * 1024) / 2;
         cudaError_t err;
-        if (env_shape == 1) err = run(ws::Shape<3, 2, 4>());
-        else if (env_shape == 2 || wide) err = run(ws::Shape<2, 2, 4>());
-        else err = run(ws::Shape<2, 3, 3>());
+        if (env_shape == 1) err = run(ws::Shape<4, 12, 16>());       // one CTA per SM
+        else if (env_shape == 2) err = run(ws::Shape<4, 10, 16>());
+        else if (env_shape == 3) err = run(ws::Shape<2, 6, 7>());    // two CTAs per SM
+        else if (env_shape == 4) err = run(ws::Shape<3, 9, 17>());
+        else if (env_shape == 5) err = run(ws::Shape<4, 16, 16>());
+        else err = run(ws::Shape<2, 4, 8>());                        // two CTAs per SM
         if (err != cudaErrorInvalidConfiguration) return err;
         cudaGetLastError();                 // too wide even for one CTA per SM: generic kernel
     }

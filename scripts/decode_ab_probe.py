@@ -11,6 +11,13 @@ BD = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 S, C = 608, 80
 anchors = synth.coco_anchors(np.float32)
 torch.cuda.set_device(0)
+if os.environ.get("L2_FETCH"):
+    import ctypes, glob
+    torch.zeros(1, device="cuda")
+    rt = ctypes.CDLL(sorted(glob.glob("/usr/local/cuda/lib64/libcudart.so*"))[0])
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["L2_FETCH"])))   # cudaLimitMaxL2FetchGranularity
+    v = ctypes.c_size_t(0); rt.cudaDeviceGetLimit(ctypes.byref(v), 5)
+    print("MaxL2FetchGranularity rc", rc, "now", v.value, file=sys.stderr)
 kw = dict(max_boxes=100, confidence=0.001, nms_threshold=0.45, nms_method="diou")
 
 def timed(preds, shapes, n=5):
