@@ -173,6 +173,28 @@ MGD_API int mgd_decode_nms(const mgd_head_config *cfg, const mgd_post_config *po
                    long long *stats);
 
 /*
+ * Both halves of the grid path in ONE call on device tensors: mgd_encode_targets on
+ * (enc_batch, max_gt_boxes) ground-truth boxes and mgd_decode_nms on dec_batch images of
+ * head outputs (arguments as in the two functions above; device memory only).  The two
+ * halves are independent, so the library forks inside the call: the target encoder (an
+ * HBM-bound write stream) runs on an internal stream underneath the decoder and the
+ * latency-bound NMS, and the caller's stream joins both before the call's work counts as
+ * complete -- to the caller it behaves like one stream-ordered operation on `stream`.
+ * Class-range errors of the encoder are reported through mgd_poll_status (asynchronous
+ * semantics of mgd_encode_targets without MGD_FLAG_SYNC); MGD_FLAG_SYNC synchronises
+ * `stream` before returning.  The reference never runs the two halves together
+ * (generators.py:1756 is training-side, multigrid_decode.py:347 inference-side); this
+ * entry exists for pipelines that do -- and for the benchmark's combined step.
+ */
+MGD_API int mgd_encode_decode_nms(const mgd_head_config *cfg, const mgd_post_config *post,
+                          const float *gt_boxes, int enc_batch, int max_gt_boxes,
+                          float *const *y_true,
+                          const float *const *preds, int dec_batch, const int *image_hw,
+                          double *boxes_xywh, int *boxes_xyxy, double *scores,
+                          int *classes, int *index, int *counts,
+                          int device, void *stream, int flags);
+
+/*
  * Dense decode only.  Replaces MultiGridDecoder.decode_predictions
  * (multigrid_decode.py:48-98) and, when image_hw != NULL, correct_boxes
  * (:185-235) applied per image.

@@ -72,7 +72,7 @@ EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targ
            "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack", "mgd_profile_begin",
            "mgd_profile_end", "mgd_match_detections", "mgd_iou_matrix", "mgd_host_alloc",
            "mgd_host_free", "mgd_release_workspace", "mgd_reshape_boxes", "mgd_mosaic_merge_boxes",
-           "mgd_ignore_mask")
+           "mgd_ignore_mask", "mgd_encode_decode_nms")
 
 
 def load():
@@ -99,6 +99,13 @@ def load():
         ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, _LLP]
+    lib.mgd_encode_decode_nms.restype = ctypes.c_int
+    lib.mgd_encode_decode_nms.argtypes = [
+        ctypes.POINTER(HeadConfig), ctypes.POINTER(PostConfig),
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     lib.mgd_decode_dense.restype = ctypes.c_int
     lib.mgd_decode_dense.argtypes = [
         ctypes.POINTER(HeadConfig), ctypes.POINTER(PostConfig),

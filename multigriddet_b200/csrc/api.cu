@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -367,10 +368,73 @@ int status_to_error(int st)
 // ---- encode ------------------------------------------------------------------------
 struct EncodeScratch { int* table; BoxRec* recs; };
 
+// The fused entry (mgd_encode_decode_nms) runs the encoder in two phases.  The assign kernel
+// needs ~60 KB of shared memory per CTA and cannot share an SM with the decoder's persistent
+// CTAs, and the y_true writer and the decoder are both DRAM-bound (run together they take longer
+// than one after the other: 4.6 ms against 3.6 ms per 4 096 images); the NMS that follows the
+// decoder is latency-bound and leaves the memory system idle.  So: every chunk's assign kernel
+// first, then the decoder, then the writer on a second stream underneath the NMS.
+int encode_assign_all(const HeadGeom& g, const float* boxes, int batch, int N, float* const* y,
+                      cudaStream_t stream, int* d_status, int tf_compat, std::vector<EncodeArgs>* chunks)
+{
+    nvtx_range nv("mgd:encode assign (preprocess_true_boxes)");
+    const Alloc al{nullptr, stream};
+    const int step = chunk_images(g, batch);
+    for (int b0 = 0; b0 < batch; b0 += step) {
+        const int nb = batch - b0 < step ? batch - b0 : step;
+        EncodeArgs a;
+        a.g = g;
+        a.B = nb;
+        a.N = N;
+        a.boxes = boxes + (size_t)b0 * N * 5;
+        for (int l = 0; l < g.L; ++l)
+            a.y[l] = y[l] + (size_t)b0 * g.gh[l] * g.gw[l] * g.D[l];
+        a.tf_compat = tf_compat;
+        a.status = d_status;
+        a.stats = nullptr;
+        a.big_tables = nullptr;
+        a.table = nullptr;
+        a.recs = nullptr;
+        chunks->push_back(a);                    // (first, so that a failure below still frees it)
+        EncodeArgs& c = chunks->back();
+        if (encode_needs_big_tables(g, N))
+            CUDA_TRY(al.get(&c.big_tables, (size_t)nb * 2 * g.cells * sizeof(int)));
+        CUDA_TRY(al.get(&c.table, (size_t)nb * g.cells * sizeof(int)));
+        CUDA_TRY(al.get(&c.recs, (size_t)nb * (N > 0 ? N : 1) * sizeof(BoxRec)));
+        CUDA_TRY(launch_encode_assign(c, stream));
+    }
+    return MGD_OK;
+}
+
+// the writer of every chunk on `stream` (which must already be ordered behind the assigns)
+int encode_fill_all(std::vector<EncodeArgs>& chunks, int num_sms, cudaStream_t stream)
+{
+    nvtx_range nv("mgd:encode fill (preprocess_true_boxes)");
+    for (EncodeArgs& a : chunks) {
+        const cudaError_t e = launch_encode_fill(a, num_sms, stream);
+        if (e != cudaSuccess) return fail(MGD_ERR_CUDA, "y_true writer launch failed: %s", cudaGetErrorString(e));
+    }
+    return MGD_OK;
+}
+
+// Scratch goes back to the pool on the stream it was allocated on (once that stream is ordered
+// behind every user): a block freed on another stream is not reused by this stream's next
+// allocation -- the pool grew by the owner tables (125 MB per 4 096 images) every step.
+void encode_free_all(std::vector<EncodeArgs>& chunks, cudaStream_t stream)
+{
+    const Alloc al{nullptr, stream};
+    for (EncodeArgs& a : chunks) {
+        al.put(a.table); al.put(a.recs); al.put(a.big_tables);
+        a.table = nullptr; a.recs = nullptr; a.big_tables = nullptr;
+    }
+    cudaGetLastError();
+}
+
 int encode_device(const HeadGeom& g, const float* boxes, int batch, int N, float* const* y,
                   int num_sms, cudaStream_t stream, int* d_status, unsigned long long* d_stats,
                   const Alloc& al, int tf_compat)
 {
+    nvtx_range nv("mgd:encode (preprocess_true_boxes)");
     const int step = chunk_images(g, batch);
     for (int b0 = 0; b0 < batch; b0 += step) {
         const int nb = batch - b0 < step ? batch - b0 : step;
@@ -415,8 +479,10 @@ float objectness_prefilter(const mgd_post_config& post)
 int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const float* const* preds,
                       int batch, const int* image_hw, double* xywh, int* xyxy, double* scores,
                       int* classes, int* index, int* counts, int num_sms, cudaStream_t stream,
-                      unsigned long long* d_stats, const Alloc& al)
+                      unsigned long long* d_stats, const Alloc& al,
+                      const std::function<int()>* after_first_decode = nullptr)
 {
+    nvtx_range nv("mgd:decode+nms (MultiGridDecoder.postprocess)");
     const int step = decode_chunk_images(g, batch);
     const int M = post.max_boxes;
     int pow2 = 2;
@@ -450,6 +516,10 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
                             "cell (at most ~1750 are supported)", g.D[0]);
             }
             CUDA_TRY(e);
+        }
+        if (after_first_decode && b0 == 0) {
+            const int hook_rc = (*after_first_decode)();
+            if (hook_rc) return hook_rc;
         }
 
         NmsArgs n;
@@ -757,6 +827,7 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
                        float* const* y_true, int memory, int device, void* stream, int flags,
                        long long* stats)
 {
+    nvtx_range nv_api("mgd_encode_targets");
     HeadGeom g;
     int rc = build_geom(cfg, &g);
     if (rc) return rc;
@@ -918,6 +989,7 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
                    double* boxes_xywh, int* boxes_xyxy, double* scores, int* classes, int* index,
                    int* counts, int memory, int device, void* stream, int flags, long long* stats)
 {
+    nvtx_range nv_api("mgd_decode_nms");
     HeadGeom g;
     int rc = build_geom(cfg, &g);
     if (rc) return rc;
@@ -1073,10 +1145,108 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
     return MGD_OK;
 }
 
+// side stream + fork / join events of the fused entry, one set per (host thread, device)
+struct ForkStreams {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    ~ForkStreams()
+    {
+        if (fork) cudaEventDestroy(fork);
+        if (join) cudaEventDestroy(join);
+        if (side) cudaStreamDestroy(side);
+        cudaGetLastError();
+    }
+};
+thread_local ForkStreams t_fork[64];
+
+int mgd_encode_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
+                          const float* gt_boxes, int enc_batch, int max_gt_boxes,
+                          float* const* y_true,
+                          const float* const* preds, int dec_batch, const int* image_hw,
+                          double* boxes_xywh, int* boxes_xyxy, double* scores,
+                          int* classes, int* index, int* counts,
+                          int device, void* stream, int flags)
+{
+    nvtx_range nv_api("mgd_encode_decode_nms");
+    HeadGeom g;
+    int rc = build_geom(cfg, &g);
+    if (rc) return rc;
+    if ((rc = check_post(post))) return rc;
+    if (enc_batch < 0 || dec_batch < 0 || max_gt_boxes < 0)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "batch sizes and max_gt_boxes must be >= 0");
+    if (enc_batch > 0) {
+        if (!y_true) return fail(MGD_ERR_INVALID_ARGUMENT, "y_true is NULL");
+        for (int l = 0; l < g.L; ++l)
+            if (!y_true[l]) return fail(MGD_ERR_INVALID_ARGUMENT, "y_true[%d] is NULL", l);
+        if (!gt_boxes && max_gt_boxes > 0) return fail(MGD_ERR_INVALID_ARGUMENT, "gt_boxes is NULL");
+        if (max_gt_boxes > 65000)
+            return fail(MGD_ERR_UNSUPPORTED, "max_boxes per image must be <= 65000, got %d", max_gt_boxes);
+        if ((long long)chunk_images(g, enc_batch) * max_gt_boxes >= (1ll << 27))
+            return fail(MGD_ERR_UNSUPPORTED, "batch chunk x max_boxes too large");
+    }
+    if (dec_batch > 0) {
+        if (!preds) return fail(MGD_ERR_INVALID_ARGUMENT, "preds is NULL");
+        for (int l = 0; l < g.L; ++l)
+            if (!preds[l]) return fail(MGD_ERR_INVALID_ARGUMENT, "preds[%d] is NULL", l);
+        if (!counts) return fail(MGD_ERR_INVALID_ARGUMENT, "counts is NULL");
+    }
+    int num_sms;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ForkStreams& fk = t_fork[device];
+    if (!fk.side) {
+        // lowest priority: decode / NMS blocks are placed first, the writer takes what is left
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char* pe = getenv("MGD_STEP_PRIORITY");          // measurements: -1 low, 0 default, 1 high
+        const int want = pe ? atoi(pe) : -1;
+        CUDA_TRY(cudaStreamCreateWithPriority(&fk.side, cudaStreamNonBlocking, want < 0 ? lo : (want > 0 ? hi : 0)));
+        CUDA_TRY(cudaEventCreateWithFlags(&fk.fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&fk.join, cudaEventDisableTiming));
+    }
+    std::vector<EncodeArgs> chunks;
+    if (enc_batch > 0) {
+        int* d_flag;
+        if ((rc = deferred_status_word(device, &d_flag))) return rc;
+        rc = encode_assign_all(g, gt_boxes, enc_batch, max_gt_boxes, y_true, st, d_flag,
+                               (flags & MGD_FLAG_TF_COMPAT) != 0, &chunks);
+        if (rc) { encode_free_all(chunks, st); return rc; }
+    }
+    if (dec_batch == 0) {
+        rc = encode_fill_all(chunks, num_sms, st);
+        encode_free_all(chunks, st);
+        if (rc) return rc;
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    bool forked = false;
+    const std::function<int()> fork_writer = [&]() -> int {
+        if (chunks.empty()) return MGD_OK;
+        CUDA_TRY(cudaEventRecord(fk.fork, st));                  // behind the assigns and the decoder
+        CUDA_TRY(cudaStreamWaitEvent(fk.side, fk.fork, 0));
+        forked = true;
+        const int frc = encode_fill_all(chunks, num_sms, fk.side);
+        CUDA_TRY(cudaEventRecord(fk.join, fk.side));
+        return frc;
+    };
+    rc = decode_nms_device(g, *post, preds, dec_batch, image_hw, boxes_xywh, boxes_xyxy, scores,
+                           classes, index, counts, num_sms, st, nullptr, Alloc{nullptr, st}, &fork_writer);
+    if (forked) {
+        const cudaError_t e = cudaStreamWaitEvent(st, fk.join, 0);
+        if (e != cudaSuccess && rc == MGD_OK) rc = fail(MGD_ERR_CUDA, "join failed: %s", cudaGetErrorString(e));
+    }
+    encode_free_all(chunks, st);                                 // st is behind the writer now
+    if (rc) return rc;
+    if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+    return MGD_OK;
+}
+
 int mgd_decode_dense(const mgd_head_config* cfg, const mgd_post_config* post,
                      const float* const* preds, int batch, const int* image_hw, double* out,
                      int memory, int device, void* stream, int flags)
 {
+    nvtx_range nv_api("mgd_decode_dense");
     HeadGeom g;
     int rc = build_geom(cfg, &g);
     if (rc) return rc;
@@ -1142,6 +1312,7 @@ int mgd_nms(const double* boxes, const double* scores, const int* classes, int n
             double nms_threshold, int nms_method, int per_class, int max_keep, int* keep,
             int* n_keep, int memory, int device, void* stream, int flags)
 {
+    nvtx_range nv_api("mgd_nms");
     int rc;
     if ((rc = check_memory_arg(memory))) return rc;
     if (n < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n must be >= 0");
@@ -1222,6 +1393,7 @@ int mgd_wbf(const double* boxes, const double* scores, const int* classes,
             double* out_boxes, double* out_scores, int* out_classes, int* n_out, int memory,
             int device, void* stream, int flags)
 {
+    nvtx_range nv_api("mgd_wbf");
     int rc;
     if ((rc = check_memory_arg(memory))) return rc;
     if (n < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n must be >= 0");
@@ -1295,6 +1467,7 @@ int mgd_soft_nms(const double* boxes, const double* scores, int n, double sigma,
                  double score_threshold, int* keep, double* soft_scores, int* n_keep, int memory,
                  int device, void* stream, int flags)
 {
+    nvtx_range nv_api("mgd_soft_nms");
     int rc;
     if ((rc = check_memory_arg(memory))) return rc;
     if (n < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n must be >= 0");
@@ -1365,6 +1538,7 @@ int mgd_match_detections(const double* det_boxes, const double* det_scores, cons
                          unsigned char* tp, int* matched_gt, int memory, int device, void* stream,
                          int flags)
 {
+    nvtx_range nv_api("mgd_match_detections");
     int rc;
     if ((rc = check_memory_arg(memory))) return rc;
     if (batch < 0 || max_dets < 0 || max_gt < 0)
@@ -1450,6 +1624,7 @@ int mgd_ignore_mask(const mgd_head_config* cfg, const float* const* y_pred,
                     float* const* ignore_mask, float* const* assigned_anchor_iou,
                     float* const* max_iou_map, int memory, int device, void* stream, int flags)
 {
+    nvtx_range nv_api("mgd_ignore_mask");
     HeadGeom g;
     int rc = build_geom(cfg, &g);
     if (rc) return rc;
@@ -1525,6 +1700,7 @@ int mgd_reshape_boxes(const void* boxes, int boxes_dtype, const int* counts, con
                       int batch, int max_boxes, void* out, float* out_f32, int* out_counts,
                       int memory, int device, void* stream, int flags)
 {
+    nvtx_range nv_api("mgd_reshape_boxes");
     int rc;
     if ((rc = check_memory_arg(memory))) return rc;
     if (batch < 0 || max_boxes < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "batch and max_boxes must be >= 0");
@@ -1578,6 +1754,7 @@ int mgd_mosaic_merge_boxes(const double* boxes, int num_sources, int max_boxes, 
                            int batch, int height, int width, double* out, float* out_f32,
                            int* out_counts, int memory, int device, void* stream, int flags)
 {
+    nvtx_range nv_api("mgd_mosaic_merge_boxes");
     int rc;
     if ((rc = check_memory_arg(memory))) return rc;
     if (batch < 0 || max_boxes < 0 || num_sources < 0)
@@ -1623,6 +1800,7 @@ int mgd_mosaic_merge_boxes(const double* boxes, int num_sources, int max_boxes, 
 int mgd_iou_matrix(const double* boxes1, int n, const double* boxes2, int m, double* out, int memory,
                    int device, void* stream, int flags)
 {
+    nvtx_range nv_api("mgd_iou_matrix");
     int rc;
     if ((rc = check_memory_arg(memory))) return rc;
     if (n < 0 || m < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "n and m must be >= 0");

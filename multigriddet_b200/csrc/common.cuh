@@ -154,6 +154,17 @@ struct LossArgs {
     int* gt_count;                         // scratch: (B, L) unique ground-truth boxes
 };
 
+// NVTX ranges (header-only NVTX3: no link dependency; a no-op unless a profiler injects
+// itself) around every C-ABI entry point and every kernel launch group, so nsys / ncu
+// attribute GPU time to the reference function each kernel replaces.
+#include <nvtx3/nvToolsExt.h>
+struct nvtx_range {
+    explicit nvtx_range(const char* name) { nvtxRangePushA(name); }
+    ~nvtx_range() { nvtxRangePop(); }
+    nvtx_range(const nvtx_range&) = delete;
+    nvtx_range& operator=(const nvtx_range&) = delete;
+};
+
 // per-kernel CUDA-event timing (mgd_profile_begin / mgd_profile_end)
 enum ProfKind { PROF_ENCODE_ASSIGN = 0, PROF_ENCODE_FILL = 1, PROF_DECODE_COMPACT = 2,
                 PROF_NMS = 3, PROF_OTHER = 4, PROF_KINDS = 5 };
@@ -162,6 +173,8 @@ void prof_mark_end(int kind, cudaStream_t stream);
 
 // launchers (each enqueues on `stream` and returns the launch error, if any)
 cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream);
+cudaError_t launch_encode_assign(const EncodeArgs& a, cudaStream_t stream);      // owner tables + box records
+cudaError_t launch_encode_fill(const EncodeArgs& a, int num_sms, cudaStream_t stream);   // the y_true writer
 cudaError_t launch_decode(const DecodeArgs& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_nms(const NmsArgs& a, int num_sms, cudaStream_t stream);
 size_t encode_assign_smem_bytes(const HeadGeom& g, int N);

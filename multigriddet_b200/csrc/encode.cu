@@ -380,6 +380,13 @@ bool encode_needs_big_tables(const HeadGeom& g, int N)
 
 cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
 {
+    cudaError_t err = launch_encode_assign(a, stream);
+    if (err != cudaSuccess) return err;
+    return launch_encode_fill(a, num_sms, stream);
+}
+
+cudaError_t launch_encode_assign(const EncodeArgs& a, cudaStream_t stream)
+{
     const HeadGeom& g = a.g;
     const size_t smem = a.big_tables ? (size_t)a.N * sizeof(int) + 16 : encode_assign_smem_bytes(g, a.N);
     cudaError_t err = cudaFuncSetAttribute(encode_assign_kernel,
@@ -388,9 +395,12 @@ cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
     prof_mark_begin(PROF_ENCODE_ASSIGN, stream);
     encode_assign_kernel<<<a.B, kAssignThreads, smem, stream>>>(a);
     prof_mark_end(PROF_ENCODE_ASSIGN, stream);
-    err = cudaGetLastError();
-    if (err != cudaSuccess) return err;
+    return cudaGetLastError();
+}
 
+cudaError_t launch_encode_fill(const EncodeArgs& a, int num_sms, cudaStream_t stream)
+{
+    const HeadGeom& g = a.g;
     bool vec4 = true;
     for (int l = 0; l < g.L; ++l)
         vec4 = vec4 && (g.D[l] % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.y[l]) & 15) == 0);

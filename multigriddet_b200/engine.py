@@ -216,6 +216,59 @@ def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_
     return out
 
 
+def grid_step(true_boxes, y_true, preds, image_shapes, input_shape, anchors, num_classes,
+              max_boxes=100, confidence=0.1, nms_threshold=0.5, nms_method="diou", per_class=False,
+              use_softmax=True, rescore_confidence=True, sync=True,
+              want=("boxes_xywh", "boxes_xyxy", "scores", "classes", "index")):
+    """Both halves of the grid path in one library call on torch CUDA tensors
+    (``mgd_encode_decode_nms``): ``y_true`` (list of preallocated (Be, G, G, D) tensors) is
+    overwritten with the targets of ``true_boxes`` while ``preds`` are decoded and suppressed;
+    the library overlaps the two internally.  Returns the detection dict of ``decode_nms``."""
+    import torch
+    lib = _lib.load()
+    if len(preds) != len(anchors) or len(y_true) != len(anchors):
+        raise ValueError(f"Expected {len(anchors)} tensors per list")
+    grid_shapes = [(int(p.shape[1]), int(p.shape[2])) for p in preds]
+    cfg = _lib.make_head_config(anchors, num_classes, input_shape, grid_shapes)
+    pc = post_config(max_boxes, confidence, nms_threshold, nms_method, per_class, use_softmax,
+                     rescore_confidence)
+    B = int(preds[0].shape[0])
+    Be, N = int(true_boxes.shape[0]), int(true_boxes.shape[1])
+    dev = preds[0].device.index or 0
+    for l, (p, y) in enumerate(zip(preds, y_true)):
+        d = 5 + cfg.num_anchors[l] + cfg.num_classes
+        if tuple(p.shape) != (B, cfg.grid_h[l], cfg.grid_w[l], d) or \
+                tuple(y.shape) != (Be, cfg.grid_h[l], cfg.grid_w[l], d):
+            raise ValueError(f"layer {l}: unexpected tensor shape")
+        if not (p.is_cuda and y.is_cuda and p.is_contiguous() and y.is_contiguous()
+                and p.dtype == torch.float32 and y.dtype == torch.float32):
+            raise ValueError("grid_step takes contiguous float32 CUDA tensors")
+    tb = true_boxes.to(torch.float32).contiguous()
+    d_hw = None
+    if image_shapes is not None:
+        d_hw = image_shapes if _is_torch(image_shapes) else torch.from_numpy(
+            np.ascontiguousarray(np.broadcast_to(np.asarray(image_shapes, np.int32).reshape(-1, 2), (B, 2)))).to(preds[0].device)
+        d_hw = d_hw.to(torch.int32).contiguous()
+    M = int(max_boxes)
+    spec = {"boxes_xywh": ((B, M, 4), torch.float64), "boxes_xyxy": ((B, M, 4), torch.int32),
+            "scores": ((B, M), torch.float64), "classes": ((B, M), torch.int32),
+            "index": ((B, M), torch.int32)}
+    out = {k: torch.empty(spec[k][0], dtype=spec[k][1], device=preds[0].device) for k in want}
+    out["counts"] = torch.empty((B,), dtype=torch.int32, device=preds[0].device)
+    addr = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else None
+    rc = lib.mgd_encode_decode_nms(
+        ctypes.byref(cfg), ctypes.byref(pc), ctypes.c_void_p(tb.data_ptr()), Be, N,
+        _lib.ptr_array([y.data_ptr() for y in y_true]),
+        _lib.ptr_array([p.data_ptr() for p in preds]), B,
+        ctypes.c_void_p(d_hw.data_ptr()) if d_hw is not None else None,
+        addr("boxes_xywh"), addr("boxes_xyxy"), addr("scores"), addr("classes"), addr("index"),
+        addr("counts"), dev, ctypes.c_void_p(_torch_stream(dev)), _lib.FLAG_SYNC if sync else 0)
+    _lib.raise_for_status(rc)
+    if not sync:
+        out["_keepalive"] = (tb, d_hw)
+    return out
+
+
 def decode_dense(preds, anchors, num_classes, model_image_size, image_shapes=None,
                  use_softmax=True, rescore_confidence=True):
     """Dense decode (reference ``decode_predictions`` [+ ``correct_boxes``]):

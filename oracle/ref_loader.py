@@ -51,9 +51,37 @@ def numpy_is_pinned() -> bool:
     return os.environ.get("NPY_DISABLE_CPU_FEATURES", "") == NUMPY_PIN
 
 
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
 def available() -> bool:
     return os.path.isfile(os.path.join(
         REFERENCE_ROOT, "multigriddet", "data", "generators.py"))
+
+
+def staged() -> bool:
+    """True when ``oracle/build_ref.py`` has staged the reference's hot-path sources under
+    ``oracle/_ref/`` (they travel to the GPU box; ``/root/reference`` does not)."""
+    return os.path.isfile(os.path.join(STAGED_ROOT, "MANIFEST.json"))
+
+
+def load_staged_encoder():
+    """``preprocess_true_boxes`` from the staged verbatim source segments."""
+    if "enc_staged" in _cache:
+        return _cache["enc_staged"]
+    spec = importlib.util.spec_from_file_location(
+        "_mgd_ref_staged_encoder", os.path.join(STAGED_ROOT, "encoder_functions.py"))
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    raw = module.preprocess_true_boxes
+
+    def preprocess_true_boxes(*a, **k):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            return raw(*a, **k)
+
+    _cache["enc_staged"] = preprocess_true_boxes
+    return preprocess_true_boxes
 
 
 _ENCODER_NAMES = ("get_anchor_mask", "iol_common_center", "best_fit_and_layer",
@@ -89,13 +117,15 @@ def load_encoder():
     return preprocess_true_boxes
 
 
-def load_postprocess():
-    """Return a namespace with the reference ``MultiGridDecoder`` and NMS classes."""
-    if "post" in _cache:
-        return _cache["post"]
+def load_postprocess(staged_copy: bool = False):
+    """Return a namespace with the reference ``MultiGridDecoder`` and NMS classes
+    (``staged_copy``: from ``oracle/_ref`` instead of ``/root/reference``)."""
+    key = "post_staged" if staged_copy else "post"
+    if key in _cache:
+        return _cache[key]
     if "tensorflow" not in sys.modules:
         sys.modules["tensorflow"] = types.ModuleType("tensorflow")
-    pkg_root = os.path.join(REFERENCE_ROOT, "multigriddet")
+    pkg_root = os.path.join(STAGED_ROOT if staged_copy else REFERENCE_ROOT, "multigriddet")
     names = {}
     for pkg, sub in (("_mgd_ref", pkg_root),
                      ("_mgd_ref.postprocess", os.path.join(pkg_root, "postprocess"))):
@@ -117,7 +147,7 @@ def load_postprocess():
         ClusterNMS=names["nms"].ClusterNMS, nms_boxes=names["nms"].nms_boxes,
         fast_cluster_nms_boxes=names["nms"].fast_cluster_nms_boxes,
         WeightedBoxesFusion=names["wbf"].WeightedBoxesFusion)
-    _cache["post"] = ns
+    _cache[key] = ns
     return ns
 
 

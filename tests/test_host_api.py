@@ -28,6 +28,11 @@ def test_decoder_shim_conventions():
     b, c, s = dec.postprocess([np.zeros((0, g, g, 88), np.float32) for g in (19, 38, 76)],
                               (608, 608), (608, 608))
     assert b.size == c.size == s.size == 0
+    # the kernel has ONE model size: the reference's two (input_shape for wh, model_image_size
+    # for the letterbox) must agree, otherwise results would silently differ
+    with pytest.raises(ValueError, match="input_shape"):
+        dec.postprocess([np.zeros((1, g, g, 88), np.float32) for g in (13, 26, 52)],
+                        (416, 416), (416, 416))
     # nothing above the threshold needs no device either
     b, c, s = dec.handle_predictions(np.zeros((1, 10, 85)), (608, 608), confidence=0.5)
     assert b.size == 0
