@@ -397,7 +397,7 @@ def run_b200(args):
         det = fused(n)
         det = {k: v for k, v in det.items() if not k.startswith("_")}
         if gather == "device":
-            full = sharding.gather_detections_device(det)
+            full = sharding.gather_detections_device(det, Bs)
         else:
             full = sharding.gather_detections(det)
         out_keep[:] = [det, full]

@@ -294,6 +294,23 @@ MGD_API int mgd_ignore_mask(const mgd_head_config *cfg, const float *const *y_pr
                     float *const *max_iou_map, int memory, int device, void *stream, int flags);
 
 /*
+ * Target encoder and loss-side ignore mask in one call (SURVEY.md 8f-2 as specified): the
+ * ignore mask is fed by the encoder's owner table and box records, so the ground truth of the
+ * loss is never re-derived from the dense y_true tensor (4 bytes per cell are read instead of
+ * 352) and y_true itself is optional.  Replaces preprocess_true_boxes (generators.py:3393-3473)
+ * followed by MultiGridLoss._compute_ignore_mask (losses/multigrid_loss.py:494-703) on the same
+ * boxes; results are identical to mgd_encode_targets + mgd_ignore_mask.  Device memory only.
+ *   boxes (batch, max_boxes, 5) float32;  y_pred L x (batch, gh, gw, 5+A+C) float32;
+ *   y_true L pointers or NULL (skip writing the targets);  outputs as in mgd_ignore_mask.
+ * Class-range errors are reported through mgd_poll_status (MGD_FLAG_SYNC synchronises first).
+ */
+MGD_API int mgd_encode_ignore_mask(const mgd_head_config *cfg, const float *boxes, int batch,
+                           int max_boxes, const float *const *y_pred, float *const *y_true,
+                           double ignore_thresh, double eps, float *const *ignore_mask,
+                           float *const *assigned_anchor_iou, float *const *max_iou_map,
+                           int device, void *stream, int flags);
+
+/*
  * Box-side pre-step of the encoder, over a batch (so the (B, N, 5) tensor mgd_encode_targets
  * consumes can be produced on the device).
  *
@@ -328,6 +345,32 @@ MGD_API int mgd_mosaic_merge_boxes(const double *boxes, int num_sources, int max
                            const int *params, int batch, int height, int width, double *out,
                            float *out_f32, int *out_counts,
                            int memory, int device, void *stream, int flags);
+
+/*
+ * tf.data box pre-step: what happens to an image's boxes between the annotation parser and
+ * tf_preprocess_true_boxes on the reference's DEFAULT training path (build_tf_dataset,
+ * multigriddet/data/generators.py):
+ *   - the letterbox / multi-scale box transform of _preprocess_image_and_boxes (:1859-1916,
+ *     with tf_letterbox_resize :167-209): boxes * scale + padding offset, float32;
+ *   - the optional horizontal flip of tf_random_horizontal_flip (:227-256), the coin handed
+ *     in by the caller (hflip);
+ *   - padded_batch to max_boxes_per_image rows (:1963-1976) and _expand_box_capacity
+ *     (:1983-2034): zero rows up to max_boxes_per_image * expansion (1 / 2 / 4 / 8 for none /
+ *     MixUp / Mosaic / both).
+ * The crop / rotate / gridmask augmentations in between are image-space work and stay in the
+ * reference.
+ *   boxes   (batch, max_in, 5) float32 [x1, y1, x2, y2, class], original-image pixels
+ *   counts  (batch,) int32 valid rows per image, or NULL (= max_in)
+ *   params  (batch, 6) int32: src_h, src_w, scale_h, scale_w (the multi-scale shape sampled
+ *           for the image, 0 0 = no multi-scale), hflip, reserved
+ *   out     (batch, max_boxes_per_image * expansion, 5) float32 -- the tensor
+ *           mgd_encode_targets consumes; rows beyond min(count, max_boxes_per_image) are zero
+ *           (TensorFlow's padded_batch raises on a longer component; here it is truncated)
+ */
+MGD_API int mgd_letterbox_boxes(const float *boxes, const int *counts, const int *params,
+                        int batch, int max_in, int input_h, int input_w,
+                        int max_boxes_per_image, int expansion, float *out,
+                        int memory, int device, void *stream, int flags);
 
 /*
  * IoU matrix of two sets of xyxy boxes.  Replaces calculate_iou_matrix

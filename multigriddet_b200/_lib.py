@@ -72,7 +72,8 @@ EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targ
            "mgd_encode_targets_dlpack", "mgd_decode_nms_dlpack", "mgd_profile_begin",
            "mgd_profile_end", "mgd_match_detections", "mgd_iou_matrix", "mgd_host_alloc",
            "mgd_host_free", "mgd_release_workspace", "mgd_reshape_boxes", "mgd_mosaic_merge_boxes",
-           "mgd_ignore_mask", "mgd_encode_decode_nms")
+           "mgd_ignore_mask", "mgd_encode_decode_nms", "mgd_letterbox_boxes",
+           "mgd_encode_ignore_mask")
 
 
 def load():
@@ -157,6 +158,17 @@ def load():
     lib.mgd_mosaic_merge_boxes.argtypes = [
         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+        ctypes.c_void_p, ctypes.c_int]
+    lib.mgd_encode_ignore_mask.restype = ctypes.c_int
+    lib.mgd_encode_ignore_mask.argtypes = [
+        ctypes.POINTER(HeadConfig), ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.c_double, ctypes.c_double,
+        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+        ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.mgd_letterbox_boxes.restype = ctypes.c_int
+    lib.mgd_letterbox_boxes.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
         ctypes.c_void_p, ctypes.c_int]
     lib.mgd_ignore_mask.restype = ctypes.c_int
     lib.mgd_ignore_mask.argtypes = [

@@ -1750,6 +1750,134 @@ int mgd_reshape_boxes(const void* boxes, int boxes_dtype, const int* counts, con
     return MGD_OK;
 }
 
+int mgd_encode_ignore_mask(const mgd_head_config* cfg, const float* boxes, int batch, int max_boxes,
+                           const float* const* y_pred, float* const* y_true, double ignore_thresh,
+                           double eps, float* const* ignore_mask, float* const* assigned_anchor_iou,
+                           float* const* max_iou_map, int device, void* stream, int flags)
+{
+    nvtx_range nv_api("mgd_encode_ignore_mask");
+    HeadGeom g;
+    int rc = build_geom(cfg, &g);
+    if (rc) return rc;
+    if (batch < 0 || max_boxes < 0) return fail(MGD_ERR_INVALID_ARGUMENT, "batch and max_boxes must be >= 0");
+    if (!y_pred || !ignore_mask || !assigned_anchor_iou || !max_iou_map)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor list");
+    for (int l = 0; l < g.L && batch > 0; ++l)
+        if (!y_pred[l] || !ignore_mask[l] || !assigned_anchor_iou[l] || !max_iou_map[l] || (y_true && !y_true[l]))
+            return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor for layer %d", l);
+    if (!boxes && (long long)batch * max_boxes > 0) return fail(MGD_ERR_INVALID_ARGUMENT, "boxes is NULL");
+    if (max_boxes > 65000)
+        return fail(MGD_ERR_UNSUPPORTED, "max_boxes per image must be <= 65000, got %d", max_boxes);
+    if ((long long)chunk_images(g, batch > 0 ? batch : 1) * max_boxes >= (1ll << 27))
+        return fail(MGD_ERR_UNSUPPORTED, "batch chunk x max_boxes too large");
+    int num_sms;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
+    if (batch == 0) return MGD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int* d_flag;
+    if ((rc = deferred_status_word(device, &d_flag))) return rc;
+    const Alloc al{nullptr, st};
+    const int step = chunk_images(g, batch);
+    for (int b0 = 0; b0 < batch; b0 += step) {
+        const int nb = batch - b0 < step ? batch - b0 : step;
+        EncodeArgs e;
+        e.g = g; e.B = nb; e.N = max_boxes;
+        e.boxes = boxes + (size_t)b0 * max_boxes * 5;
+        for (int l = 0; l < g.L; ++l)
+            e.y[l] = y_true ? y_true[l] + (size_t)b0 * g.gh[l] * g.gw[l] * g.D[l] : nullptr;
+        e.tf_compat = (flags & MGD_FLAG_TF_COMPAT) != 0;
+        e.status = d_flag; e.stats = nullptr;
+        e.big_tables = nullptr; e.table = nullptr; e.recs = nullptr;
+        unsigned char* scratch = nullptr;
+        auto release = [&]() { al.put(e.table); al.put(e.recs); al.put(e.big_tables); al.put(scratch); };
+        cudaError_t ce = cudaSuccess;
+        if (encode_needs_big_tables(g, max_boxes))
+            ce = al.get(&e.big_tables, (size_t)nb * 2 * g.cells * sizeof(int));
+        if (ce == cudaSuccess) ce = al.get(&e.table, (size_t)nb * g.cells * sizeof(int));
+        if (ce == cudaSuccess) ce = al.get(&e.recs, (size_t)nb * (max_boxes > 0 ? max_boxes : 1) * sizeof(BoxRec));
+        const size_t n_gt = (size_t)nb * g.cells * 2;
+        const size_t off_area = n_gt * 16, off_cnt = off_area + n_gt * 4;
+        if (ce == cudaSuccess) ce = al.get(&scratch, off_cnt + (size_t)nb * g.L * 4);
+        if (ce == cudaSuccess) ce = launch_encode_assign(e, st);
+        if (ce == cudaSuccess && y_true) ce = launch_encode_fill(e, num_sms, st);
+        if (ce == cudaSuccess) {
+            LossArgs a;
+            memset(&a, 0, sizeof(a));
+            a.g = g; a.B = nb; a.ignore_thresh = (float)ignore_thresh; a.eps = (float)eps;
+            a.table = e.table; a.recs = e.recs;
+            a.gt_boxes = scratch;
+            a.gt_area = reinterpret_cast<float*>(scratch + off_area);
+            a.gt_count = reinterpret_cast<int*>(scratch + off_cnt);
+            for (int l = 0; l < g.L; ++l) {
+                const size_t cells_b0 = (size_t)b0 * g.gh[l] * g.gw[l];
+                a.y_pred[l] = y_pred[l] + cells_b0 * g.D[l];
+                a.ignore[l] = ignore_mask[l] + cells_b0;
+                a.assigned[l] = assigned_anchor_iou[l] + cells_b0;
+                a.max_iou[l] = max_iou_map[l] + cells_b0;
+            }
+            ce = launch_ignore_mask(a, st);
+        }
+        release();
+        CUDA_TRY(ce);
+    }
+    if (flags & MGD_FLAG_SYNC) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return mgd_poll_status(device, stream);
+    }
+    return MGD_OK;
+}
+
+int mgd_letterbox_boxes(const float* boxes, const int* counts, const int* params, int batch,
+                        int max_in, int input_h, int input_w, int max_boxes_per_image, int expansion,
+                        float* out, int memory, int device, void* stream, int flags)
+{
+    nvtx_range nv_api("mgd_letterbox_boxes");
+    int rc;
+    if ((rc = check_memory_arg(memory))) return rc;
+    if (batch < 0 || max_in < 0 || max_boxes_per_image < 1)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "batch, max_in >= 0 and max_boxes_per_image >= 1 required");
+    if (expansion != 1 && expansion != 2 && expansion != 4 && expansion != 8)
+        return fail(MGD_ERR_INVALID_ARGUMENT, "expansion must be 1, 2, 4 or 8 (generators.py:2008-2017)");
+    if (input_h < 1 || input_w < 1) return fail(MGD_ERR_INVALID_ARGUMENT, "input shape must be positive");
+    const long long cap = (long long)max_boxes_per_image * expansion;
+    if (cap > (1 << 20)) return fail(MGD_ERR_UNSUPPORTED, "capacity too large");
+    if (batch > 0 && (!params || !out || (max_in > 0 && !boxes)))
+        return fail(MGD_ERR_INVALID_ARGUMENT, "NULL tensor");
+    int num_sms;
+    DeviceScope dev_scope;
+    if ((rc = prepare_device(device, &num_sms, &dev_scope))) return rc;
+    if (batch == 0) return MGD_OK;
+    if (memory == MGD_MEM_DEVICE) {
+        cudaStream_t st = (cudaStream_t)stream;
+        CUDA_TRY(launch_letterbox_boxes(boxes, counts, params, batch, max_in, max_boxes_per_image,
+                                        (int)cap, input_h, input_w, out, st));
+        if (flags & MGD_FLAG_SYNC) CUDA_TRY(cudaStreamSynchronize(st));
+        return MGD_OK;
+    }
+    cudaStream_t* ss;
+    if ((rc = host_streams(device, &ss, nullptr))) return rc;
+    cudaStream_t st = ss[0];
+    const size_t n_in = (size_t)batch * max_in * 5 * 4, n_out = (size_t)batch * cap * 5 * 4;
+    const size_t off_out = (n_in + 15) & ~(size_t)15, off_par = off_out + ((n_out + 15) & ~(size_t)15);
+    const size_t off_cnt = off_par + (size_t)batch * 24, total = off_cnt + (size_t)batch * 4;
+    unsigned char* buf;
+    CUDA_TRY(pool_malloc(&buf, total, st));
+    if (n_in) CUDA_TRY(cudaMemcpyAsync(buf, boxes, n_in, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(buf + off_par, params, (size_t)batch * 24, cudaMemcpyHostToDevice, st));
+    if (counts) CUDA_TRY(cudaMemcpyAsync(buf + off_cnt, counts, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+    cudaError_t e = launch_letterbox_boxes(reinterpret_cast<const float*>(buf),
+                                           counts ? reinterpret_cast<const int*>(buf + off_cnt) : nullptr,
+                                           reinterpret_cast<const int*>(buf + off_par), batch, max_in,
+                                           max_boxes_per_image, (int)cap, input_h, input_w,
+                                           reinterpret_cast<float*>(buf + off_out), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaMemcpy(out, buf + off_out, n_out, cudaMemcpyDeviceToHost);
+    cudaFreeAsync(buf, st);
+    CUDA_TRY(e);
+    return MGD_OK;
+}
+
 int mgd_mosaic_merge_boxes(const double* boxes, int num_sources, int max_boxes, const int* params,
                            int batch, int height, int width, double* out, float* out_f32,
                            int* out_counts, int memory, int device, void* stream, int flags)

@@ -147,7 +147,79 @@ mosaic_merge_kernel(const __grid_constant__ BoxOpArgs a)
     if (lane == 0 && a.out_counts) a.out_counts[b] = kept;
 }
 
+// tf.data box pre-step (reference multigriddet/data/generators.py:1859-1916 letterbox / multi-scale
+// transform, :227-256 horizontal flip, :1963-1976 padded_batch to max_boxes_per_image,
+// :1983-2034 _expand_box_capacity): one warp per image, float32 arithmetic in the order of the
+// TensorFlow ops (every op is an IEEE float32 multiply / divide / add; tf.cast(float -> int32)
+// truncates).  Output rows beyond the image's count are zero, up to the expanded capacity.
+//   params (B, 6) int32: src_h, src_w, scale_h, scale_w (multi-scale target shape, 0 = none),
+//                        hflip, reserved
+__global__ void __launch_bounds__(kBoxWarps * 32)
+letterbox_boxes_kernel(const float* __restrict__ in, const int* __restrict__ counts,
+                       const int* __restrict__ params, int B, int n_in, int n_keep, int capacity,
+                       int input_h, int input_w, float* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kBoxWarps + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int* p = params + (size_t)b * 6;
+    const float src_h = (float)p[0], src_w = (float)p[1];
+    const float th = (float)input_h, tw = (float)input_w;
+    float sx, sy, pad_left, pad_top;
+    if (p[2] > 0 && p[3] > 0) {                                   // multi-scale branch, :1866-1897
+        const float scale_h = __fdiv_rn((float)p[2], th), scale_w = __fdiv_rn((float)p[3], tw);
+        const int scaled_h = (int)__fmul_rn(src_h, scale_h), scaled_w = (int)__fmul_rn(src_w, scale_w);
+        const float fh = (float)scaled_h, fw = (float)scaled_w;
+        const float ls0 = fminf(__fdiv_rn(tw, fw), __fdiv_rn(th, fh));       // tf_letterbox_resize :186
+        const int new_w = (int)__fmul_rn(fw, ls0), new_h = (int)__fmul_rn(fh, ls0);
+        const float ls = fminf(__fdiv_rn((float)new_w, fw), __fdiv_rn((float)new_h, fh));   // :1887-1890
+        sx = __fmul_rn(scale_w, ls);
+        sy = __fmul_rn(scale_h, ls);
+        pad_left = (float)((input_w - new_w) / 2);                // // on non-negative ints
+        pad_top = (float)((input_h - new_h) / 2);
+    } else {                                                      // :1898-1916
+        const float s0 = fminf(__fdiv_rn(tw, src_w), __fdiv_rn(th, src_h));
+        const int new_w = (int)__fmul_rn(src_w, s0), new_h = (int)__fmul_rn(src_h, s0);
+        const float sc = fminf(__fdiv_rn((float)new_w, src_w), __fdiv_rn((float)new_h, src_h));
+        sx = sy = sc;
+        pad_left = (float)((input_w - new_w) / 2);
+        pad_top = (float)((input_h - new_h) / 2);
+    }
+    const bool flip = p[4] != 0;
+    int n = counts ? counts[b] : n_in;
+    n = min(max(n, 0), min(n_in, n_keep));
+    const float* src = in + (size_t)b * n_in * 5;
+    float* dst = out + (size_t)b * capacity * 5;
+    for (int i = lane; i < capacity; i += 32) {
+        float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (i < n) {
+            float x1 = __fadd_rn(__fmul_rn(src[i * 5 + 0], sx), pad_left);
+            const float y1 = __fadd_rn(__fmul_rn(src[i * 5 + 1], sy), pad_top);
+            float x2 = __fadd_rn(__fmul_rn(src[i * 5 + 2], sx), pad_left);
+            const float y2 = __fadd_rn(__fmul_rn(src[i * 5 + 3], sy), pad_top);
+            if (flip) { const float t = __fsub_rn(tw, x2); x2 = __fsub_rn(tw, x1); x1 = t; }   // :248-251
+            v[0] = x1; v[1] = y1; v[2] = x2; v[3] = y2;
+            v[4] = __fadd_rn(__fmul_rn(src[i * 5 + 4], 1.0f), 0.0f);
+        }
+        #pragma unroll
+        for (int e = 0; e < 5; ++e) dst[i * 5 + e] = v[e];
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_letterbox_boxes(const float* in, const int* counts, const int* params, int B,
+                                   int n_in, int n_keep, int capacity, int input_h, int input_w,
+                                   float* out, cudaStream_t stream)
+{
+    if (B <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((B + kBoxWarps - 1) / kBoxWarps);
+    prof_mark_begin(PROF_OTHER, stream);
+    letterbox_boxes_kernel<<<grid, kBoxWarps * 32, 0, stream>>>(in, counts, params, B, n_in, n_keep,
+                                                                capacity, input_h, input_w, out);
+    prof_mark_end(PROF_OTHER, stream);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_reshape_boxes(const BoxOpArgs& a, int boxes_i32, cudaStream_t stream)
 {

@@ -152,6 +152,11 @@ struct LossArgs {
     void* gt_boxes;                        // scratch: (B, cells, 2) x 16 B corner boxes (raw | unique)
     float* gt_area;                        // scratch: (B, cells, 2)
     int* gt_count;                         // scratch: (B, L) unique ground-truth boxes
+    // fed by the target encoder instead of a dense y_true (mgd_encode_ignore_mask): the assign
+    // kernel's owner table (layer-major, [l][b][cell]: -1 or box record * 16 + neighbour id) and
+    // its box records; y_true[] is then unused
+    const int* table;
+    const BoxRec* recs;
 };
 
 // NVTX ranges (header-only NVTX3: no link dependency; a no-op unless a profiler injects
@@ -188,6 +193,9 @@ cudaError_t launch_iou_matrix(const double* b1, int n, const double* b2, int m, 
                               cudaStream_t stream);
 cudaError_t launch_reshape_boxes(const BoxOpArgs& a, int boxes_i32, cudaStream_t stream);
 cudaError_t launch_mosaic_merge(const BoxOpArgs& a, cudaStream_t stream);
+cudaError_t launch_letterbox_boxes(const float* in, const int* counts, const int* params, int B,
+                                   int n_in, int n_keep, int capacity, int input_h, int input_w,
+                                   float* out, cudaStream_t stream);
 cudaError_t launch_ignore_mask(const LossArgs& a, cudaStream_t stream);
 cudaError_t launch_keep_from_index(const int* index, const int* counts, int max_keep, int* keep,
                                    int* n_keep, cudaStream_t stream);

@@ -8,6 +8,8 @@
 // stop_gradient / cast-from-bool in the reference, so this is a forward-only op.
 //
 // TensorFlow materialises a (G*G*A) x (positives) IoU matrix per image.  Here:
+//   (mgd_encode_ignore_mask feeds both kernels from the encoder's owner table and box records
+//   instead of a dense y_true: 4 bytes per cell instead of 352, and y_true need not exist.)
 //   gt_gather_kernel    one CTA per (image, layer): decode the positive cells into corner
 //       boxes, drop exact duplicates (the nine cells of one object decode to the same box
 //       when the encoder's fractions are dyadic), write a compact list.  The maximum over the
@@ -37,7 +39,7 @@ gt_gather_kernel(const __grid_constant__ LossArgs a)
     const int b = blockIdx.x, layer = blockIdx.y;
     const int gh = g.gh[layer], gw = g.gw[layer], D = g.D[layer], A = g.na[layer];
     const int cells = gh * gw;
-    const float* yt = a.y_true[layer] + (size_t)b * cells * D;
+    const float* yt = a.table ? nullptr : a.y_true[layer] + (size_t)b * cells * D;
     // scratch of this (image, layer): raw list, then the de-duplicated one
     GtBox* raw = reinterpret_cast<GtBox*>(a.gt_boxes) + ((size_t)b * g.cells + g.cell_off[layer]) * 2;
     float* raw_area = a.gt_area + ((size_t)b * g.cells + g.cell_off[layer]) * 2;
@@ -46,13 +48,29 @@ gt_gather_kernel(const __grid_constant__ LossArgs a)
     const float scale_w = __fdiv_rn((float)g.in_w, (float)gw), scale_h = __fdiv_rn((float)g.in_h, (float)gh);
     if (threadIdx.x == 0) { s_n = 0; s_kept = 0; }
     __syncthreads();
+    const int* codes = a.table ? a.table + (size_t)a.B * g.cell_off[layer] + (size_t)b * cells : nullptr;
     for (int c = threadIdx.x; c < cells; c += kGatherThreads) {
-        const float* row = yt + (size_t)c * D;
-        if (!(row[4] > 0.5f)) continue;                                   // :305 object_mask
+        float row[4];
+        int k = 0;
+        if (codes) {
+            // the y_true row the writer would store for this cell (encode.cu: encode_fill_kernel)
+            const int code = codes[c];
+            if (code < 0) continue;
+            const BoxRec* rec = a.recs + (code >> 4);
+            const int nb = code & 15;
+            row[0] = (float)__dadd_rn((double)(1 - nb / 3), rec->fx);
+            row[1] = (float)__dadd_rn((double)(1 - nb % 3), rec->fy);
+            row[2] = rec->tw;
+            row[3] = rec->th;
+            k = rec->hot_anchor - 5;
+        } else {
+            const float* r = yt + (size_t)c * D;
+            if (!(r[4] > 0.5f)) continue;                                 // :305 object_mask
+            row[0] = r[0]; row[1] = r[1]; row[2] = r[2]; row[3] = r[3];
+            float best = r[5];                                              // :562 argmax, first maximum
+            for (int q = 1; q < A; ++q) if (r[5 + q] > best) { best = r[5 + q]; k = q; }
+        }
         const int i = c / gw, j = c - i * gw;                              // tensor position [row i, col j]
-        int k = 0;                                                          // :562 argmax, first maximum
-        float best = row[5];
-        for (int q = 1; q < A; ++q) if (row[5 + q] > best) { best = row[5 + q]; k = q; }
         const int ga = g.anchor_first[layer] + k;
         const float cx = __fmul_rn(__fadd_rn(row[0], (float)i), scale_w);   // :558 with the 'ij' grid
         const float cy = __fmul_rn(__fadd_rn(row[1], (float)j), scale_h);
@@ -104,7 +122,6 @@ ignore_mask_kernel(const __grid_constant__ LossArgs a, int layer)
     int assigned = 0;
     if (live) {
         const float* yp = a.y_pred[layer] + ((size_t)b * cells + c) * D;
-        const float* yt = a.y_true[layer] + ((size_t)b * cells + c) * D;
         const int i = c / gw, j = c - i * gw;
         const float ux = __fmul_rn(0.15f, yp[0]), uy = __fmul_rn(0.15f, yp[1]);
         const float ax = __fadd_rn(tanhf(ux), __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-ux))));   // :582
@@ -112,9 +129,16 @@ ignore_mask_kernel(const __grid_constant__ LossArgs a, int layer)
         cx = __fmul_rn(__fadd_rn(ax, (float)i), scale_w);                                       // :585
         cy = __fmul_rn(__fadd_rn(ay, (float)j), scale_h);
         ew = expf(yp[2]); eh = expf(yp[3]);
-        obj = yt[4] > 0.5f ? 1.0f : 0.0f;
-        float best = yt[5];
-        for (int q = 1; q < A; ++q) if (yt[5 + q] > best) { best = yt[5 + q]; assigned = q; }
+        if (a.table) {
+            const int code = a.table[(size_t)a.B * g.cell_off[layer] + (size_t)b * cells + c];
+            obj = code >= 0 ? 1.0f : 0.0f;
+            assigned = code >= 0 ? a.recs[code >> 4].hot_anchor - 5 : 0;   // all-zero row: argmax 0
+        } else {
+            const float* yt = a.y_true[layer] + ((size_t)b * cells + c) * D;
+            obj = yt[4] > 0.5f ? 1.0f : 0.0f;
+            float best = yt[5];
+            for (int q = 1; q < A; ++q) if (yt[5 + q] > best) { best = yt[5 + q]; assigned = q; }
+        }
     }
     float iou_max = 0.f, iou_assigned = 0.f;
     for (int an = 0; an < A; ++an) {

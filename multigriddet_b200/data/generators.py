@@ -86,3 +86,32 @@ def tf_preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, mult
         return [tf.convert_to_tensor(t) for t in y]
     return engine.encode_targets(true_boxes, shape, anchors, int(num_classes), grid_shapes,
                                  semantics=semantics)
+
+
+def expand_box_capacity(boxes_dense, mosaic_enabled=False, mixup_enabled=False):
+    """``_expand_box_capacity`` of the reference's tf.data path (generators.py:1983-2034): pad the
+    (B, N, 5) box tensor with zero rows to N x {1, 2, 4, 8} for none / MixUp / Mosaic / both.
+    Shape glue (no arithmetic): NumPy in -> NumPy out, torch in -> torch out."""
+    factor = 8 if (mosaic_enabled and mixup_enabled) else 4 if mosaic_enabled else 2 if mixup_enabled else 1
+    if factor == 1:
+        return boxes_dense
+    B, N = int(boxes_dense.shape[0]), int(boxes_dense.shape[1])
+    if engine._is_torch(boxes_dense):
+        import torch
+        pad = torch.zeros((B, N * (factor - 1), 5), dtype=boxes_dense.dtype, device=boxes_dense.device)
+        return torch.cat([boxes_dense, pad], dim=1)
+    return np.concatenate([np.asarray(boxes_dense),
+                           np.zeros((B, N * (factor - 1), 5), dtype=np.asarray(boxes_dense).dtype)], axis=1)
+
+
+def letterbox_boxes(boxes, src_shapes, input_shape, max_boxes_per_image, counts=None,
+                    mosaic_enabled=False, mixup_enabled=False, multiscale_shapes=None, hflip=None):
+    """Box side of ``build_tf_dataset`` up to the encoder's input, for a batch: the letterbox /
+    multi-scale transform of ``_preprocess_image_and_boxes`` (generators.py:1859-1916), the
+    flip of ``tf_random_horizontal_flip`` (:227-256, coin supplied by the caller), ``padded_batch``
+    to ``max_boxes_per_image`` (:1963-1976) and ``_expand_box_capacity`` (:1983-2034), in one
+    kernel (``mgd_letterbox_boxes``).  Parity against TensorFlow itself is UNPINNED (TF is not
+    installed here); the oracle restates the float32 ops in their graph order."""
+    factor = 8 if (mosaic_enabled and mixup_enabled) else 4 if mosaic_enabled else 2 if mixup_enabled else 1
+    return engine.letterbox_boxes_batch(boxes, src_shapes, input_shape, max_boxes_per_image, counts,
+                                        factor, multiscale_shapes, hflip)

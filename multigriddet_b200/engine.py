@@ -517,6 +517,49 @@ def reshape_boxes_batch(boxes, params, counts=None, want_f32=True, sync=True):
     return out, o32, ocn
 
 
+def letterbox_boxes_batch(boxes, src_shapes, input_shape, max_boxes_per_image, counts=None,
+                          expansion=1, multiscale_shapes=None, hflip=None, sync=True):
+    """The tf.data box pre-step of the reference's default training path
+    (``mgd_letterbox_boxes``; generators.py:1859-1916 letterbox / multi-scale transform,
+    :227-256 flip, :1963-1976 padded_batch, :1983-2034 ``_expand_box_capacity``).
+
+    boxes (B, N, 5) float32 NumPy or torch CUDA, original-image pixels; src_shapes (B, 2)
+    (h, w); multiscale_shapes (B, 2) or None; hflip (B,) bool or None.  Returns the
+    (B, max_boxes_per_image * expansion, 5) float32 tensor ``encode_targets`` consumes."""
+    lib = _lib.load()
+    B, N = int(boxes.shape[0]), int(boxes.shape[1])
+    par = np.zeros((B, 6), dtype=np.int32)
+    par[:, 0:2] = np.asarray(src_shapes, dtype=np.int64).reshape(B, 2)
+    if multiscale_shapes is not None:
+        par[:, 2:4] = np.asarray(multiscale_shapes, dtype=np.int64).reshape(B, 2)
+    if hflip is not None:
+        par[:, 4] = np.asarray(hflip).astype(np.int32).reshape(B)
+    cap = int(max_boxes_per_image) * int(expansion)
+    ih, iw = int(input_shape[0]), int(input_shape[1])
+    if _is_torch(boxes):
+        import torch
+        dev = boxes.device
+        b = boxes.to(torch.float32).contiguous()
+        d_par = torch.from_numpy(par).to(dev)
+        cnt = None if counts is None else torch.as_tensor(counts).to(device=dev, dtype=torch.int32).contiguous()
+        out = torch.empty((B, cap, 5), dtype=torch.float32, device=dev)
+        p = lambda x: ctypes.c_void_p(x.data_ptr()) if x is not None and x.numel() else None
+        idx = dev.index or 0
+        rc = lib.mgd_letterbox_boxes(p(b), p(cnt), p(d_par), B, N, ih, iw, int(max_boxes_per_image),
+                                     int(expansion), p(out), _lib.MEM_DEVICE, idx,
+                                     ctypes.c_void_p(_torch_stream(idx)), _lib.FLAG_SYNC if sync else 0)
+    else:
+        b = np.ascontiguousarray(np.asarray(boxes), dtype=np.float32)
+        cnt = None if counts is None else np.ascontiguousarray(np.asarray(counts), dtype=np.int32)
+        out = np.zeros((B, cap, 5), dtype=np.float32)
+        p = lambda x: ctypes.c_void_p(x.ctypes.data) if x is not None and x.size else None
+        rc = lib.mgd_letterbox_boxes(p(b), p(cnt), p(par), B, N, ih, iw, int(max_boxes_per_image),
+                                     int(expansion), p(out), _lib.MEM_HOST, _current_device(), None,
+                                     _lib.FLAG_SYNC)
+    _lib.raise_for_status(rc)
+    return out
+
+
 def mosaic_merge_boxes_batch(boxes, sample_index, crop_xy, image_size, want_f32=True, sync=True):
     """``merge_mosaic_bboxes`` for a batch of mosaics (``mgd_mosaic_merge_boxes``).
 
@@ -597,3 +640,32 @@ def ignore_masks(y_preds, y_trues, anchors, input_shape, num_classes, ignore_thr
                                  _lib.MEM_HOST, _current_device(), None, _lib.FLAG_SYNC)
     _lib.raise_for_status(rc)
     return outs
+
+
+def encode_ignore_masks(true_boxes, y_preds, anchors, input_shape, num_classes, ignore_thresh=0.5,
+                        eps=1e-7, want_y_true=True, sync=True, semantics="numpy"):
+    """Target encoding and loss-side ignore mask in one call on torch CUDA tensors
+    (``mgd_encode_ignore_mask``): the mask kernels read the encoder's owner table instead of a
+    dense ``y_true``.  Returns ``(y_true list or None, [(ignore, assigned_iou, max_iou)] per layer)``;
+    identical to ``encode_targets`` followed by ``ignore_masks``."""
+    import torch
+    lib = _lib.load()
+    grids = [(int(p.shape[1]), int(p.shape[2])) for p in y_preds]
+    cfg = _lib.make_head_config([np.asarray(a, dtype=np.float32) for a in anchors], num_classes,
+                                input_shape, grids)
+    dev = y_preds[0].device
+    B, N = int(true_boxes.shape[0]), int(true_boxes.shape[1])
+    tb = true_boxes.to(device=dev, dtype=torch.float32).contiguous()
+    yp = [t.to(torch.float32).contiguous() for t in y_preds]
+    yt = [torch.empty_like(t) for t in yp] if want_y_true else None
+    outs = [tuple(torch.empty((B, gh, gw, 1), dtype=torch.float32, device=dev) for _ in range(3))
+            for gh, gw in grids]
+    ptr = lambda ts: _lib.ptr_array([t.data_ptr() for t in ts])
+    idx = dev.index or 0
+    flags = (_lib.FLAG_SYNC if sync else 0) | (_lib.FLAG_TF_COMPAT if semantics == "tf_compat" else 0)
+    rc = lib.mgd_encode_ignore_mask(ctypes.byref(cfg), ctypes.c_void_p(tb.data_ptr()), B, N, ptr(yp),
+                                    ptr(yt) if yt is not None else None, float(ignore_thresh), float(eps),
+                                    ptr([o[0] for o in outs]), ptr([o[1] for o in outs]),
+                                    ptr([o[2] for o in outs]), idx, ctypes.c_void_p(_torch_stream(idx)), flags)
+    _lib.raise_for_status(rc)
+    return yt, outs

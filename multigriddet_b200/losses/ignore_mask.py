@@ -29,3 +29,12 @@ def compute_ignore_mask(y_pred_layer, y_true_layer, anchors_layer, input_shape, 
     C = int(y_pred_layer.shape[-1]) - 5 - A
     return compute_ignore_masks([y_pred_layer], [y_true_layer], [np.asarray(anchors_layer)],
                                 input_shape, C, ignore_thresh, eps)[0]
+
+
+def encode_and_ignore_masks(true_boxes, y_preds, anchors, input_shape, num_classes, ignore_thresh=0.5,
+                            eps=1e-7, want_y_true=True):
+    """``preprocess_true_boxes`` + ``_compute_ignore_mask`` of all layers in one library call on
+    device tensors: the mask is fed by the encoder's owner table, the dense ``y_true`` is never
+    re-read (and not even written with ``want_y_true=False``).  Returns ``(y_true, masks)``."""
+    return engine.encode_ignore_masks(true_boxes, y_preds, anchors, input_shape, num_classes,
+                                      ignore_thresh, eps, want_y_true)

@@ -85,33 +85,54 @@ def gather_detections(local: Dict, dst: Optional[int] = None) -> Optional[Dict[s
     return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
 
 
-def gather_detections_device(local: Dict) -> Dict:
+def gather_detections_device(local: Dict, n_total: Optional[int] = None) -> Dict:
     """Device-side gather: every rank ends with the whole batch's padded detection
-    tensors in ITS OWN device memory (one all-gather of <= 2.8 KB per image
-    over NVLink with the NCCL backend; CPU tensors with gloo).  ``local`` holds torch
-    tensors of this rank's shard; shards may differ by one image, so they are padded to
-    the largest shard for the collective and trimmed afterwards."""
+    tensors in ITS OWN device memory (the path's one exchange step, <= 2.8 KB
+    per image over NVLink with the NCCL backend; CPU tensors with gloo).
+
+    ONE collective per call: the rows of all tensors of an image are packed into one byte
+    row, the packed shards are all-gathered (``all_gather_into_tensor``) and the result is
+    viewed back -- nothing synchronises with the host.  ``local`` holds torch tensors of this
+    rank's shard; shards follow ``shard_bounds`` (they differ by at most one image and are
+    padded to the largest for the collective).  ``n_total``: images in the global batch;
+    default ``world_size`` equal shards of the local size."""
     import torch
     d = _dist()
     keys = [k for k, v in local.items() if hasattr(v, "detach") and not k.startswith("_")]
     if d is None or d.get_world_size() == 1:
         return {k: local[k] for k in keys}
-    ws = d.get_world_size()
+    ws, rank = d.get_world_size(), d.get_rank()
     n_local = int(local["counts"].shape[0])
-    sizes = torch.zeros(ws, dtype=torch.int64, device=local["counts"].device)
-    sizes[d.get_rank()] = n_local
-    d.all_reduce(sizes)
-    sizes = [int(v) for v in sizes.tolist()]
+    if n_total is None:
+        n_total = n_local * ws
+    sizes = [shard_bounds(n_total, r, ws)[1] - shard_bounds(n_total, r, ws)[0] for r in range(ws)]
+    if sizes[rank] != n_local:
+        raise ValueError(f"rank {rank} holds {n_local} images, shard_bounds({n_total}) says {sizes[rank]}")
     n_max = max(sizes)
-    out = {}
+    # byte layout of one image's row: the tensors in key order, each padded to 8 bytes
+    spans, off = [], 0
     for k in keys:
-        t = local[k].contiguous()
-        if n_local < n_max:
-            pad = torch.zeros((n_max - n_local,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            t = torch.cat([t, pad], 0)
-        parts = [torch.empty_like(t) for _ in range(ws)]
-        d.all_gather(parts, t)
-        out[k] = torch.cat([p[:n] for p, n in zip(parts, sizes)], 0)
+        t = local[k]
+        nbytes = t.element_size() * int(np.prod(t.shape[1:], dtype=np.int64))
+        spans.append((k, off, nbytes))
+        off += (nbytes + 7) & ~7
+    row = off
+    dev = local["counts"].device
+    send = torch.zeros((n_max, row), dtype=torch.uint8, device=dev)
+    for k, o, nb in spans:
+        if n_local:
+            send[:n_local, o:o + nb] = local[k].contiguous().view(torch.uint8).reshape(n_local, nb)
+    recv = torch.empty((ws * n_max, row), dtype=torch.uint8, device=dev)
+    d.all_gather_into_tensor(recv, send)
+    recv = recv.view(ws, n_max, row)
+    if all(sz == n_max for sz in sizes):
+        full = recv.reshape(ws * n_max, row)
+    else:
+        full = torch.cat([recv[r, :sizes[r]] for r in range(ws)], 0)
+    out = {}
+    for k, o, nb in spans:
+        t = local[k]
+        out[k] = full[:, o:o + nb].contiguous().view(t.dtype).reshape((full.shape[0],) + tuple(t.shape[1:]))
     return out
 
 
@@ -152,5 +173,5 @@ class ShardedGridPath:
         det = self.compute.decode_nms([p[sl] for p in global_preds], shapes, self.input_shape,
                                       self.anchors, self.num_classes, **kw)
         if gather == "device":
-            return gather_detections_device(det)
+            return gather_detections_device({k: v for k, v in det.items() if k != "stats"}, n)
         return gather_detections(det, dst) if gather else det

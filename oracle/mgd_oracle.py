@@ -701,3 +701,58 @@ def merge_mosaic_bboxes(bboxes, crop_x, crop_y, image_size):
     if merged:
         out[:len(merged)] = merged
     return out
+
+
+# --------------------------------------------------------------------------
+# tf.data box pre-step (generators.py:1859-1916, 227-256, 1963-2034) -- PARITY UNPINNED:
+# TensorFlow is not installed; every op restated here is an IEEE float32 multiply / divide /
+# add or an int truncation, in the order the TF graph applies them.
+# --------------------------------------------------------------------------
+
+def tf_letterbox_params(src_h, src_w, input_shape, multiscale_shape=None):
+    """(sx, sy, pad_left, pad_top) as float32 scalars, following tf_letterbox_resize (:167-209)
+    and _preprocess_image_and_boxes (:1866-1916)."""
+    f = np.float32
+    th, tw = f(input_shape[0]), f(input_shape[1])
+    sh, sw = f(src_h), f(src_w)
+    if multiscale_shape is not None and multiscale_shape[0] > 0 and multiscale_shape[1] > 0:
+        scale_h = f(multiscale_shape[0]) / th                       # :1872-1873 (base = input_shape)
+        scale_w = f(multiscale_shape[1]) / tw
+        scaled_h = int(f(sh * scale_h))                             # tf.cast(..., tf.int32) :1879-1880
+        scaled_w = int(f(sw * scale_w))
+        fh, fw = f(scaled_h), f(scaled_w)
+        ls0 = min(tw / fw, th / fh)                                 # :186-187
+        new_w, new_h = int(f(fw * ls0)), int(f(fh * ls0))           # :190-191
+        ls = min(f(new_w) / fw, f(new_h) / fh)                      # :1887-1890
+        sx, sy = f(scale_w * ls), f(scale_h * ls)                   # :1891-1892
+    else:
+        s0 = min(tw / sw, th / sh)
+        new_w, new_h = int(f(sw * s0)), int(f(sh * s0))
+        sc = min(f(new_w) / sw, f(new_h) / sh)                      # :1906-1909
+        sx = sy = f(sc)
+    pad_left = (int(input_shape[1]) - new_w) // 2                   # :197-200
+    pad_top = (int(input_shape[0]) - new_h) // 2
+    return sx, sy, f(pad_left), f(pad_top)
+
+
+def tf_letterbox_boxes(boxes, counts, src_shapes, input_shape, max_boxes_per_image, expansion=1,
+                       multiscale_shapes=None, hflip=None):
+    """Batch form of the box side of build_tf_dataset up to the encoder's input:
+    transform (:1891-1916), flip (:248-251), padded_batch (:1963-1976),
+    _expand_box_capacity (:1983-2034).  (B, N, 5) float32 -> (B, max*expansion, 5) float32."""
+    f = np.float32
+    boxes = np.asarray(boxes, dtype=f)
+    B, N = boxes.shape[0], boxes.shape[1]
+    out = np.zeros((B, int(max_boxes_per_image) * int(expansion), 5), dtype=f)
+    for b in range(B):
+        ms = None if multiscale_shapes is None else multiscale_shapes[b]
+        sx, sy, pl, pt = tf_letterbox_params(src_shapes[b][0], src_shapes[b][1], input_shape, ms)
+        n = N if counts is None else int(counts[b])
+        n = max(0, min(n, N, int(max_boxes_per_image)))
+        bx = boxes[b, :n] * np.array([sx, sy, sx, sy, 1.0], dtype=f)
+        bx = bx + np.array([pl, pt, pl, pt, 0.0], dtype=f)
+        if hflip is not None and bool(hflip[b]):
+            w = f(input_shape[1])
+            bx = np.stack([w - bx[:, 2], bx[:, 1], w - bx[:, 0], bx[:, 3], bx[:, 4]], axis=1)
+        out[b, :n] = bx
+    return out

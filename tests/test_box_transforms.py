@@ -138,3 +138,67 @@ def test_device_pipeline_reshape_then_encode():
         g = g.cpu().numpy()
         assert np.array_equal(g[..., 4:], r[..., 4:]) and np.array_equal(g[..., :2], r[..., :2])
         np.testing.assert_allclose(g[..., 2:4], r[..., 2:4], rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------
+# tf.data box pre-step (generators.py:1859-1916, 1963-2034): oracle unpinned (no TensorFlow)
+# ------------------------------------------------------------------------------
+
+def _tfdata_case(seed, B=12, N=40):
+    rng = np.random.default_rng(seed)
+    src = np.stack([rng.integers(120, 1400, B), rng.integers(120, 1400, B)], 1)       # (h, w)
+    counts = rng.integers(0, N + 1, B).astype(np.int32)
+    boxes = np.zeros((B, N, 5), np.float32)
+    for b in range(B):
+        n = counts[b]
+        xy = rng.uniform(0, [src[b, 1], src[b, 0]], (n, 2))
+        wh = rng.uniform(2, [src[b, 1] / 2, src[b, 0] / 2], (n, 2))
+        boxes[b, :n] = np.concatenate([xy, np.minimum(xy + wh, [src[b, 1], src[b, 0]]),
+                                       rng.integers(0, 80, (n, 1))], 1)
+    ms = np.stack([rng.choice([320, 416, 512, 608], B), ] * 2, 1)
+    ms[::3] = 0                                                                      # some without
+    flip = rng.integers(0, 2, B).astype(bool)
+    return boxes, counts, src, ms, flip
+
+
+def test_tf_letterbox_oracle_known_values():
+    """Hand-derived: a 480x640 image into 608x608 -> scale 0.95, new size 608x456, pad_top 76."""
+    sx, sy, pl, pt = O.tf_letterbox_params(480, 640, (608, 608))
+    assert (float(sx), float(pl), float(pt)) == (np.float32(608) / np.float32(640), 0.0, 76.0) and sx == sy
+    out = O.tf_letterbox_boxes(np.array([[[100, 50, 300, 250, 7]]], np.float32), None, [(480, 640)],
+                               (608, 608), 100, expansion=4)
+    assert out.shape == (1, 400, 5) and not out[0, 1:].any()
+    np.testing.assert_allclose(out[0, 0], [95.0, 123.5, 285.0, 313.5, 7.0], rtol=1e-6)
+    flipped = O.tf_letterbox_boxes(np.array([[[100, 50, 300, 250, 7]]], np.float32), None, [(480, 640)],
+                                   (608, 608), 100, hflip=[True])
+    np.testing.assert_allclose(flipped[0, 0], [608 - 285.0, 123.5, 608 - 95.0, 313.5, 7.0], rtol=1e-6)
+    # multi-scale: sampled shape 320 -> image scaled by 320/608, then letterboxed back up
+    sx, sy, pl, pt = O.tf_letterbox_params(480, 640, (608, 608), (320, 320))
+    assert abs(float(sx) - 0.95) < 5e-3 and float(pl) in (0.0, 1.0)
+
+
+@pytest.mark.gpu
+def test_tf_letterbox_boxes_match_oracle_and_feed_the_encoder():
+    import torch
+    from multigriddet_b200 import engine, synth
+    from multigriddet_b200.data import expand_box_capacity, letterbox_boxes
+    for seed in (1, 2):
+        boxes, counts, src, ms, flip = _tfdata_case(seed)
+        for expansion, (mo, mi) in ((1, (False, False)), (2, (False, True)), (4, (True, False)), (8, (True, True))):
+            ref = O.tf_letterbox_boxes(boxes, counts, src, (608, 608), 30, expansion, ms, flip)
+            got = letterbox_boxes(boxes, src, (608, 608), 30, counts, mo, mi, ms, flip)
+            assert got.dtype == np.float32 and np.array_equal(got, ref)
+            dev = letterbox_boxes(torch.from_numpy(boxes).cuda(), src, (608, 608), 30, counts, mo, mi, ms, flip)
+            assert np.array_equal(dev.cpu().numpy(), ref)
+        # capacity expansion alone == what the fused kernel pads
+        plain = letterbox_boxes(boxes, src, (608, 608), 30, counts, multiscale_shapes=ms, hflip=flip)
+        assert np.array_equal(expand_box_capacity(plain, True, True),
+                              letterbox_boxes(boxes, src, (608, 608), 30, counts, True, True, ms, flip))
+    # device pipeline: raw annotation boxes -> letterbox kernel -> encoder, nothing on the host
+    boxes, counts, src, ms, flip = _tfdata_case(5, B=6)
+    d = letterbox_boxes(torch.from_numpy(boxes).cuda(), src, (608, 608), 40, counts, True, False)
+    anchors = synth.coco_anchors(np.float32)
+    y_dev = engine.encode_targets(d, (608, 608), anchors, 80)
+    y_ref = O.encode_targets(O.tf_letterbox_boxes(boxes, counts, src, (608, 608), 40, 4), (608, 608), anchors, 80)
+    for a, r in zip(y_dev, y_ref):
+        assert np.array_equal(a.cpu().numpy()[..., 4:], r[..., 4:])

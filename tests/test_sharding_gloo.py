@@ -65,7 +65,7 @@ def _worker(rank, world, port, out_dir):
     # tensor gather (NCCL over NVLink on the GPU box, gloo here): unequal shards 4 + 3
     local = path.decode_nms(preds, shapes, gather=False, **kw)
     dev = sharding.gather_detections_device({k: torch.from_numpy(np.ascontiguousarray(v))
-                                             for k, v in local.items()})
+                                             for k, v in local.items()}, n_total=boxes.shape[0])
     for k, v in everyone.items():
         assert np.array_equal(dev[k].numpy(), v), k
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), y0=y_local[0], lo=lo, hi=hi,
