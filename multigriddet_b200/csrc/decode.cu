@@ -352,17 +352,20 @@ namespace ws {
 // Measured per COCO image (planted head): producers ~43 k warp-instructions (scan + one TMA issue
 // per surviving row), consumers ~80 k, both bound by dependent-issue latency: about two
 // consumers per producer, and as many slots as shared memory holds (a slot is busy for the fill,
-// the DRAM latency of its last row, and the exact evaluation).
-template <int kProducers_, int kConsumers_, int kSlots_>
+// the DRAM latency of its last row, and the exact evaluation).  Slots of 16 rows instead of 32
+// halve what a slot holds while it is being filled or waiting for its last row (level 2 then
+// runs two lanes per row); rows arrive at ~1.3 slots of 32 per microsecond and SM.
+template <int kProducers_, int kConsumers_, int kSlots_, int kRows_ = 32, int kPrefetch_ = 16>
 struct Shape {
+    static constexpr int kPrefetch = kPrefetch_;                 // level-1 blocks in flight per producer (512 B each)
     static constexpr int kProducers = kProducers_;
     static constexpr int kConsumers = kConsumers_;
     static constexpr int kThreads = (kProducers_ + kConsumers_) * 32;
     static constexpr int kSlots = kSlots_;
-    static constexpr int kCtasPerSm = kSlots_ > 9 ? 1 : 2;      // by shared memory (11 KB per COCO slot)
+    static constexpr int kRows = kRows_;                         // rows per slot: 32 or 16
+    static constexpr int kCtasPerSm = kSlots_ * kRows_ > 9 * 32 ? 1 : 2;   // by shared memory (352 B per COCO row)
 };
-constexpr int kSlotRows = 32;
-constexpr int kPrefetch = 16;                 // level-1 blocks in flight per producer (cp.async ring, 512 B each)
+constexpr int kSlotRows = 32;                 // capacity of the per-slot metadata arrays
 
 struct SlotMeta {
     int row[kSlotRows];                       // row index within the layer (b * cells_l + cell)
@@ -448,6 +451,8 @@ template <class Sh>
 __device__ __forceinline__ void producer(const DecodeArgs& a, const GroupShared& gs, int p, int P)
 {
     constexpr int kSlots = Sh::kSlots;
+    constexpr int kRows = Sh::kRows;
+    constexpr int kPrefetch = Sh::kPrefetch;
     constexpr int kConsumers = Sh::kConsumers;
     constexpr int kProducers = Sh::kProducers;
     const HeadGeom& g = a.g;
@@ -510,7 +515,7 @@ __device__ __forceinline__ void producer(const DecodeArgs& a, const GroupShared&
             const int row = blk * 32 + lane;
             while (todo) {
                 if (!have_slot) acquire();
-                const int free_slots = kSlotRows - count;
+                const int free_slots = kRows - count;
                 const int rank = __popc(todo & ((1u << lane) - 1u));
                 const bool take = ((todo >> lane) & 1u) && rank < free_slots;
                 const unsigned taken = __ballot_sync(0xffffffffu, take);
@@ -522,11 +527,11 @@ __device__ __forceinline__ void producer(const DecodeArgs& a, const GroupShared&
                 if (lane == 0) mbar_expect_tx(&gs.full[slot], (uint32_t)n_new * D * sizeof(float));
                 __syncwarp();
                 if (take)
-                    bulk_g2s(gs.rows + ((size_t)slot * kSlotRows + count + rank) * gs.stride,
+                    bulk_g2s(gs.rows + ((size_t)slot * kRows + count + rank) * gs.stride,
                              base + (size_t)row * D, (uint32_t)D * sizeof(float), &gs.full[slot]);
                 count += n_new;
                 todo &= ~taken;
-                if (count == kSlotRows) publish(count, layer);
+                if (count == kRows) publish(count, layer);
             }
         };
         int st = 0;
@@ -581,6 +586,8 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
                                          const uint32_t* tab)
 {
     constexpr int kSlots = Sh::kSlots;
+    constexpr int kRows = Sh::kRows;
+    constexpr int kSplit = 32 / kRows;                  // lanes per row in level 2
     const HeadGeom& g = a.g;
     const int lane = threadIdx.x & 31;
     const int j = lane & 7;
@@ -606,36 +613,48 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
         const int count = meta.count;
         if (count < 0) break;
         const int layer = meta.layer;
-        const float* rows = gs.rows + (size_t)slot * kSlotRows * gs.stride;
+        const float* rows = gs.rows + (size_t)slot * kRows * gs.stride;
 
-        // ---- level 2: lane per row, bound including the class maximum ------------------
-        bool pass = lane < count && !(a.debug & 4);
-        float mc = -INFINITY;
+        // ---- level 2: lane per row (two lanes per row with 16-row slots), bound including the
+        // class maximum ------------------------------------------------------------------------
+        const int lrow = lane & (kRows - 1), part = lane / kRows;
+        bool pass = lrow < count && !(a.debug & 4);
+        float mc = -INFINITY, sum = 0.f;
         if (pass) {
-            const float4* c4 = reinterpret_cast<const float4*>(rows + (size_t)lane * gs.stride + 8);
-            float sum = 0.f;
+            const float4* c4 = reinterpret_cast<const float4*>(rows + (size_t)lrow * gs.stride + 8);
+            const int n4 = C / 4, per = (n4 + kSplit - 1) / kSplit;
+            const int i0 = part * per, i1 = min(n4, i0 + per);
             if (softmax && rescore) {
                 #pragma unroll 4
-                for (int i = 0; i < C / 4; ++i) {
+                for (int i = i0; i < i1; ++i) {
                     const float4 v = c4[i];
                     mc = fmaxf(fmaxf(mc, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
                     sum += (fast_exp(v.x) + fast_exp(v.y)) + (fast_exp(v.z) + fast_exp(v.w));
                 }
-                // max softmax = exp(mc) / sum; no max subtraction in the fast bound: if it
-                // overflows (logits > 88) the row is simply kept for the exact evaluation
-                float ub = __fdividef(meta.bound[lane] * fast_exp(mc), sum);
-                if (!(sum < 3.0e38f) || !(ub == ub)) ub = 3.0e38f;
-                pass = ub >= a.score_lo;
             } else {
                 #pragma unroll 4
-                for (int i = 0; i < C / 4; ++i) {
+                for (int i = i0; i < i1; ++i) {
                     const float4 v = c4[i];
                     mc = fmaxf(fmaxf(mc, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
                 }
-                if (rescore) pass = meta.bound[lane] * fast_sigmoid(mc) >= a.score_lo;
             }
         }
-        unsigned todo = __ballot_sync(0xffffffffu, pass);
+        if (kSplit == 2) {
+            mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, 16));
+            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+        }
+        if (pass && rescore) {
+            if (softmax) {
+                // max softmax = exp(mc) / sum; no max subtraction in the fast bound: if it
+                // overflows (logits > 88) the row is simply kept for the exact evaluation
+                float ub = __fdividef(meta.bound[lrow] * fast_exp(mc), sum);
+                if (!(sum < 3.0e38f) || !(ub == ub)) ub = 3.0e38f;
+                pass = ub >= a.score_lo;
+            } else {
+                pass = meta.bound[lrow] * fast_sigmoid(mc) >= a.score_lo;
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, pass) & (kRows == 32 ? 0xffffffffu : (1u << (kRows & 31)) - 1u);
         if (a.debug & 2) todo = 0;
 
         // ---- level 3: exact evaluation, octet per row ----------------------------------------
@@ -769,7 +788,7 @@ __device__ __forceinline__ void consumer(const DecodeArgs& a, const GroupShared&
         // (a per-candidate atomicAdd serialises in L2: every warp of the grid works on the same
         //  few images at any time, i.e. on the same few counters)
         __syncwarp();
-        const bool mine = (cand_rows >> lane) & 1u;
+        const bool mine = lane < kRows && ((cand_rows >> lane) & 1u);
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f), res = t;
         unsigned grow = 0;
         if (mine) {
@@ -838,8 +857,8 @@ decode_ws_kernel(const __grid_constant__ DecodeArgs a, int stride)
     // serial instruction stream that everything else waits for
     constexpr int kFirstProducer = Sh::kConsumers;
     const int pw = warp - kFirstProducer;
-    gs.stage = reinterpret_cast<float4*>(gs.rows + (size_t)kSlots * kSlotRows * stride) +
-               (size_t)(pw >= 0 ? pw : 0) * kPrefetch * 32;
+    gs.stage = reinterpret_cast<float4*>(gs.rows + (size_t)kSlots * Sh::kRows * stride) +
+               (size_t)(pw >= 0 ? pw : 0) * Sh::kPrefetch * 32;
     gs.meta = s_meta;
     gs.full = s_full;
     gs.published = s_published;
@@ -960,8 +979,8 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
         const int ws_stride = dmax;
         auto run = [&](auto shape) -> cudaError_t {
             using Sh = decltype(shape);
-            const size_t smem = (size_t)Sh::kSlots * ws::kSlotRows * ws_stride * sizeof(float) +
-                                (size_t)Sh::kProducers * ws::kPrefetch * 32 * sizeof(float4);
+            const size_t smem = (size_t)Sh::kSlots * Sh::kRows * ws_stride * sizeof(float) +
+                                (size_t)Sh::kProducers * Sh::kPrefetch * 32 * sizeof(float4);
             // (static shared memory: slot metadata, barriers, tables; 1 KB reserved per CTA)
             const size_t fixed = 1024 + 1024 + (size_t)Sh::kSlots * 304;
             int ctas_per_sm = (int)((227 * 1024) / (smem + fixed));
@@ -985,12 +1004,18 @@ cudaError_t launch_decode(const DecodeArgs& a_in, int num_sms, cudaStream_t stre
             return cudaGetLastError();
         };
         cudaError_t err;
-        if (env_shape == 1) err = run(ws::Shape<4, 12, 16>());       // one CTA per SM
-        else if (env_shape == 2) err = run(ws::Shape<4, 10, 16>());
-        else if (env_shape == 3) err = run(ws::Shape<2, 6, 7>());    // two CTAs per SM
-        else if (env_shape == 4) err = run(ws::Shape<3, 9, 17>());
-        else if (env_shape == 5) err = run(ws::Shape<4, 16, 16>());
-        else err = run(ws::Shape<2, 4, 8>());                        // two CTAs per SM
+        // Default: 3 producers + 7 consumers per CTA around 17 slots of 16 rows, 8 level-1 blocks
+        // in flight per producer, two CTAs (20 warps) per SM.  Measured per 4 096 planted COCO
+        // images / per 256 dense-random ones (MGD_DECODE_SHAPE selects the alternatives):
+        //   <2,4,8,32>     1.24 / 0.50 ms      <3,6,7,32>      1.16 ms
+        //   <3,6,15,16>    1.08 / 0.51 ms      <3,6,17,16,8>   1.08 / 0.50 ms
+        //   <3,7,17,16,8>  1.03 / 0.47 ms      <3,8,17,16,8>   1.06 / 0.46 ms (80 registers)
+        //   <4,6,14,16>    1.56 / 0.79 ms (a fourth producer starves the ring of slots)
+        if (env_shape == 1) err = run(ws::Shape<3, 6, 17, 16, 8>());
+        else if (env_shape == 3) err = run(ws::Shape<3, 8, 17, 16, 8>());
+        else if (env_shape == 4) err = run(ws::Shape<3, 6, 7, 32>());
+        else if (env_shape == 5) err = run(ws::Shape<2, 4, 8, 32>());
+        else err = run(ws::Shape<3, 7, 17, 16, 8>());
         if (err != cudaErrorInvalidConfiguration) return err;
         cudaGetLastError();                 // too wide even for one CTA per SM: generic kernel
     }
