@@ -390,7 +390,7 @@ __device__ __forceinline__ float expf_core2(float x, const uint32_t* tab)
     double kd = __dadd_rn(z, shift);
     const int ki = __double2loint(kd);
     kd = __dsub_rn(kd, shift);
-    const double r = __dsub_rn(z, kd);
+    const double r = __fma_rn(inv_ln2_n, (double)x, -kd);      // exact residual (libm_emul.h)
     const int idx = ki & (MGD_EXP2F_N - 1);
     const int hi = (int)tab[idx + MGD_EXP2F_N] + (ki << 15);
     const double sc = __hiloint2double(hi, (int)tab[idx]);

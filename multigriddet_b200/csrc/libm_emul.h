@@ -71,14 +71,19 @@ MGD_HD float mgd_expf_core(float x, const uint64_t *tab)
     double kd = z + shift;                       // round to nearest-even integer
     uint64_t ki = mgd_double_as_u64(kd);
     kd -= shift;
-    double r = z - kd;
+    // r is the exact residual: glibc's FMA build contracts `z - kd` with the product that
+    // made z (gcc fuses a multiply into every add that consumes it, also when the product
+    // has a second use), so r = fma(InvLn2N, x, -kd), not the difference of the rounded z
+    double r = fma(inv_ln2_n, (double)x, -kd);
     uint64_t t = tab[ki % MGD_EXP2F_N];
     t += ki << (52 - 5);
     double s = mgd_u64_as_double(t);
     // glibc selects its FMA build of this routine on every x86-64 CPU with FMA3
     // (sysdeps/x86_64/fpu/multiarch/e_expf.c), where the compiler contracts the three
-    // multiply-adds below; fused here as well (differs from the unfused evaluation
-    // for 2 of the 2^32 float inputs).
+    // multiply-adds below and the residual above; fused here as well.  With these four
+    // contractions the routine equals the host's expf on all 2^32 float inputs
+    // (tests/test_libm_emul.py sweeps every one); with the residual left unfused it differs
+    // for x = 0x1.04845ep+5 and x = -0x1.f8cbb2p+5.
     double q = fma(c0, r, c1);
     double r2 = r * r;
     double y = fma(c2, r, 1.0);

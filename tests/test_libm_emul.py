@@ -1,9 +1,11 @@
 """libm_emul.h (the device's float32 exp) against the host libm.
 
 The header is host-compilable; the same arithmetic runs on the GPU (FMA-for-FMA,
-compiled with -fmad=false so nothing else is contracted).  A strided sweep over all
-float32 bit patterns must agree bit-for-bit; the exhaustive 2^32 sweep (run once by
-hand) differs for exactly 2 inputs, neither reachable from a softmax."""
+compiled with -fmad=false so nothing else is contracted).  Every one of the 2^32
+float32 bit patterns must agree bit-for-bit with the host's expf (glibc selects its FMA
+build on every x86-64 CPU with FMA3, which the header follows), for expf itself, for the
+clamped core the softmax uses and for the sigmoid built on it.  The sweep runs on all
+host cores (pthreads); ``MGD_EXPF_SWEEP_STEP`` thins it out on a slow machine."""
 import os
 import subprocess
 
@@ -16,9 +18,27 @@ SRC = r'''
 #include <stdint.h>
 #include <string.h>
 #include "libm_emul.h"
+#include <pthread.h>
+typedef struct { uint64_t lo, hi, step, n, bad; } job_t;
+static void* run(void* p);
 int main(int argc, char** argv){
-  uint64_t step = strtoull(argv[1], 0, 10), bad = 0, n = 0;
-  for (uint64_t u = 0; u <= 0xffffffffULL; u += step) {
+  uint64_t step = strtoull(argv[1], 0, 10);
+  int nt = atoi(argv[2]); if (nt < 1) nt = 1; if (nt > 256) nt = 256;
+  pthread_t th[256]; job_t jobs[256];
+  uint64_t per = (0x100000000ULL / step + nt) / nt * step;          /* a multiple of step */
+  for (int t = 0; t < nt; ++t) {
+    jobs[t].lo = (uint64_t)t * per; jobs[t].hi = jobs[t].lo + per; jobs[t].step = step;
+    if (jobs[t].hi > 0x100000000ULL) jobs[t].hi = 0x100000000ULL;
+    pthread_create(&th[t], 0, run, &jobs[t]);
+  }
+  uint64_t n = 0, bad = 0;
+  for (int t = 0; t < nt; ++t) { pthread_join(th[t], 0); n += jobs[t].n; bad += jobs[t].bad; }
+  printf("%llu %llu\n", (unsigned long long)n, (unsigned long long)bad);
+  return 0;
+}
+static void* run(void* p){
+  job_t* j = (job_t*)p; uint64_t step = j->step, bad = 0, n = 0;
+  for (uint64_t u = j->lo; u < j->hi; u += step) {
     uint32_t v = (uint32_t)u, ua, ub; float x; memcpy(&x, &v, 4);
     float a = expf(x), b = mgd_expf(x);
     memcpy(&ua, &a, 4); memcpy(&ub, &b, 4);
@@ -32,7 +52,7 @@ int main(int argc, char** argv){
     memcpy(&ua, &s1, 4); memcpy(&ub, &s2, 4);
     if (ua != ub && !(s1 != s1 && s2 != s2)) bad++;
   }
-  printf("%llu %llu\n", (unsigned long long)n, (unsigned long long)bad);
+  j->n = n; j->bad = bad;
   return 0;
 }
 '''
@@ -42,8 +62,11 @@ def test_expf_emulation_matches_libm(tmp_path):
     src = tmp_path / "t.c"
     src.write_text(SRC)
     exe = tmp_path / "t"
-    subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-I",
+    subprocess.run(["gcc", "-O2", "-mfma", "-ffp-contract=off", "-pthread", "-I",
                     os.path.join(ROOT, "multigriddet_b200", "csrc"), str(src), "-o", str(exe), "-lm"],
                    check=True)
-    n, bad = subprocess.run([str(exe), "211"], capture_output=True, text=True).stdout.split()
-    assert int(n) > 20_000_000 and int(bad) == 0
+    step = int(os.environ.get("MGD_EXPF_SWEEP_STEP", "1"))
+    n, bad = subprocess.run([str(exe), str(step), str(os.cpu_count() or 1)], capture_output=True,
+                            text=True, timeout=900).stdout.split()
+    assert int(n) == (2 ** 32 + step - 1) // step            # step 1: all 4 294 967 296 inputs
+    assert int(bad) == 0
