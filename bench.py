@@ -21,10 +21,11 @@ are inside the timed region.  The batch is far larger than L2 (2 x 2.67 MB per
 image), so no L2 flush is needed.
 
 `--scaling strong` (BASELINE.json configs[4] as written): 4 096 images IN TOTAL are
-split over the ranks and the step ends with the gather of the detection lists
-(`sharding.gather_detections_device`, one all-gather over NVLink); the default weak
-line (4 096 images per rank, no collective) carries the strong numbers as
-`strong_scaling` as well.
+split over the ranks and every rank ends the step holding all detections: the NMS
+kernels store each image's rows into every rank's tensors as they produce them
+(`sharding.DetectionExchange`: peer stores over NVLink, no collective call; the NCCL
+all-gather and the host gather it replaces are timed beside it).  The default weak line
+(4 096 images per rank, no collective) carries the strong numbers as `strong_scaling`.
 """
 from __future__ import annotations
 
@@ -390,10 +391,22 @@ def run_b200(args):
         out_keep[:] = [det]
         return det
 
-    def strong_step(gather="device"):
-        """configs[4] as written: this rank's slice of the 4 096-image batch, then the exchange
-        step -- every rank ends with all detections (one all-gather of the padded lists)."""
+    exchange = [None]
+
+    def strong_step(gather="exchange"):
+        """configs[4] as written: this rank's slice of the 4 096-image batch plus the exchange
+        step -- every rank ends with all detections.  "exchange": the NMS kernels store every
+        image's rows into all ranks' tensors while they run (sharding.DetectionExchange: peer
+        stores over NVLink, no collective call); "device": one NCCL all-gather of the packed
+        lists after the step; "host": all_gather_object of host copies."""
         n = hi_s - lo_s
+        if gather == "exchange":
+            if exchange[0] is None:
+                exchange[0] = sharding.DetectionExchange(Bs, POST["max_boxes"], device=local)
+            ex = exchange[0]
+            engine.grid_step(d_boxes[:n], [y[:n] for y in y_out], [p[:n] for p in preds], d_hw[:n],
+                             (S, S), anchors, C, sync=False, want=WANT, out=ex.local(WANT), **POST)
+            return ex.full()
         det = fused(n)
         det = {k: v for k, v in det.items() if not k.startswith("_")}
         if gather == "device":
@@ -437,7 +450,7 @@ def run_b200(args):
     strong_line = None
     if not strong:
         res = {}
-        for how in ("device", "host"):
+        for how in ("exchange", "device", "host"):
             fn = (lambda h=how: strong_step(h))
             if how == "host":
                 # host gather synchronises inside (all_gather_object): wall clock, max over ranks
@@ -454,10 +467,15 @@ def run_b200(args):
             res[how] = {"value": Bs * args.steps / (t / 1e3), "ms_per_step": t / args.steps}
         t_nog = max_over_ranks(_time_gpu(lambda: fused(hi_s - lo_s), args.steps, 1, barrier))
         strong_line = {"scaling": "strong", "total_images_per_step": Bs, "images_per_rank": hi_s - lo_s,
-                       "unit": UNIT, "value": res["device"]["value"],
-                       "ms_per_step": res["device"]["ms_per_step"],
-                       "gather": "gather_detections_device: all-gather of the padded lists "
-                                 "(NCCL over NVLink for N > 1; every rank ends with all detections)",
+                       "unit": UNIT, "value": res["exchange"]["value"],
+                       "ms_per_step": res["exchange"]["ms_per_step"],
+                       "gather": "sharding.DetectionExchange: the NMS kernels store each image's rows into "
+                                 "every rank's tensors as they produce them (peer stores through CUDA-IPC "
+                                 "mappings, NVLink for N > 1; two one-warp flag barriers per step, no "
+                                 "collective call); every rank ends with all detections",
+                       "exchange_timeouts": exchange[0].timeouts() if exchange[0] is not None else None,
+                       "nccl_gather": dict(res["device"], note="gather_detections_device: one NCCL all-gather "
+                                           "of the packed lists after the step (the baseline the exchange replaces)"),
                        "host_gather": dict(res["host"], note="gather_detections: all_gather_object of host copies"),
                        "compute_only_ms_per_step": t_nog / args.steps}
 
@@ -733,7 +751,7 @@ def run_b200(args):
                        "images_per_rank_per_step": n_step_images,
                        "images_per_step_total": Bs if strong else B * world,
                        "sharding": (f"image-sharded x{world}; " +
-                                    ("detection lists all-gathered every step" if strong else "no collective")),
+                                    ("detections written into every rank's tensors by the NMS kernels (peer stores, no collective call)" if strong else "no collective")),
                        "step": "one mgd_encode_decode_nms call per rank (encode + decode + NMS; the library "
                                "overlaps the y_true writer with the NMS internally)",
                        "cpus_bound_to_rank": numa,

@@ -399,6 +399,38 @@ MGD_API int mgd_host_alloc(size_t bytes, void **ptr);
 MGD_API int mgd_host_free(void *ptr);
 
 /*
+ * Detection exchange: the one exchange step of the image-sharded multi-GPU path.
+ * The reference evaluates image by image on one host (evaluator.py:254-289) and owns every
+ * detection afterwards; with the batch sharded over the GPUs of a node (one process per GPU),
+ * each rank decodes its slice and every rank needs every image's padded rows.  An exchange
+ * is `bytes` of device memory per rank, every rank's buffer mapped into every process through
+ * CUDA IPC.  Detection outputs of mgd_decode_nms / mgd_encode_decode_nms that the caller
+ * places inside its exchange buffer -- at the offsets they have in the whole-batch tensors --
+ * are written by the NMS kernels into ALL ranks' buffers as they are produced (peer stores,
+ * NVLink on a B200 box): no collective call, no packing pass.  Such a call is collective:
+ * every rank of the exchange makes it, in the same order, with >= 1 image; all of its
+ * output tensors (any may be NULL except counts) must lie in the buffer, the two box
+ * tensors 16-byte aligned (remote rows travel as 16-byte stores); when the call's work
+ * completes on `stream`, the rows of all ranks are present locally.
+ * Ranks wait for each other on the device (flag words in the buffers); a peer that does not
+ * arrive within 20 s is counted in mgd_exchange_timeouts instead of hanging the stream.
+ *
+ *   create   allocates this rank's buffer and returns its IPC handle (MGD_IPC_HANDLE_BYTES)
+ *   connect  takes the handles of all ranks, (world_size, MGD_IPC_HANDLE_BYTES) in rank
+ *            order (exchanged by the host: torch.distributed.all_gather, MPI, a file ...),
+ *            and maps the peers' buffers; world_size == 1 needs no connect
+ *   buffer   this rank's buffer (device pointer, zero-initialised)
+ */
+#define MGD_IPC_HANDLE_BYTES 64
+typedef struct mgd_exchange mgd_exchange;
+MGD_API int mgd_exchange_create(int device, int world_size, int rank, size_t bytes,
+                        mgd_exchange **exchange, unsigned char *handle);
+MGD_API int mgd_exchange_connect(mgd_exchange *exchange, const unsigned char *handles);
+MGD_API int mgd_exchange_buffer(mgd_exchange *exchange, void **base, size_t *bytes);
+MGD_API int mgd_exchange_timeouts(mgd_exchange *exchange, void *stream, int *timeouts);
+MGD_API int mgd_exchange_destroy(mgd_exchange *exchange);
+
+/*
  * Host-memory calls stage through device buffers cached per (host thread, device); this
  * returns the calling thread's cached buffers to the driver.  Optional: they are reused
  * by the thread's next call and sized by the largest batch chunk (<= ~0.5 GB).

@@ -73,7 +73,10 @@ EXPORTS = ("mgd_version", "mgd_last_error", "mgd_device_count", "mgd_encode_targ
            "mgd_profile_end", "mgd_match_detections", "mgd_iou_matrix", "mgd_host_alloc",
            "mgd_host_free", "mgd_release_workspace", "mgd_reshape_boxes", "mgd_mosaic_merge_boxes",
            "mgd_ignore_mask", "mgd_encode_decode_nms", "mgd_letterbox_boxes",
-           "mgd_encode_ignore_mask")
+           "mgd_encode_ignore_mask", "mgd_exchange_create", "mgd_exchange_connect",
+           "mgd_exchange_buffer", "mgd_exchange_timeouts", "mgd_exchange_destroy")
+
+IPC_HANDLE_BYTES = 64
 
 
 def load():
@@ -181,6 +184,18 @@ def load():
     lib.mgd_host_free.restype = ctypes.c_int
     lib.mgd_host_free.argtypes = [ctypes.c_void_p]
     lib.mgd_release_workspace.restype = ctypes.c_int
+    lib.mgd_exchange_create.restype = ctypes.c_int
+    lib.mgd_exchange_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t,
+                                        ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]
+    lib.mgd_exchange_connect.restype = ctypes.c_int
+    lib.mgd_exchange_connect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.mgd_exchange_buffer.restype = ctypes.c_int
+    lib.mgd_exchange_buffer.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                        ctypes.POINTER(ctypes.c_size_t)]
+    lib.mgd_exchange_timeouts.restype = ctypes.c_int
+    lib.mgd_exchange_timeouts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, _IP]
+    lib.mgd_exchange_destroy.restype = ctypes.c_int
+    lib.mgd_exchange_destroy.argtypes = [ctypes.c_void_p]
     lib.mgd_profile_begin.restype = ctypes.c_int
     lib.mgd_profile_end.restype = ctypes.c_int
     lib.mgd_profile_end.argtypes = [_DP, _LLP]

@@ -75,6 +75,7 @@ struct DecodeArgs {
     int debug;                        // MGD_DECODE_DEBUG (measurements only): 1 scan only, 2 no level 3, 4 no level 2/3
 };
 
+#define MGD_MAX_MIRRORS 7            /* peers of a detection exchange: world size <= 8 */
 struct NmsArgs {
     HeadGeom g;                       // decode mode: geometry for the box reconstruction
     int B;
@@ -106,7 +107,23 @@ struct NmsArgs {
     double* out_xywh; int* out_xyxy; double* out_scores; int* out_classes; int* out_index;
     int* out_counts;
     unsigned long long* stats;        // [candidates, detections]
+    // detection exchange (mgd_exchange_*): the outputs above lie in this rank's exchange buffer
+    // and every store is repeated at the same offset of each peer's buffer (nms.cu: mirror_store)
+    int n_mirrors;
+    long long mirror_delta[MGD_MAX_MIRRORS];
+    int warp_ctas_per_sm;             // host side: resident nms_warp_kernel CTAs per SM (0: all that fit)
 };
+
+// ---- detection exchange (exchange.cu, api.cu: mgd_exchange_*) ----------------------------
+#define MGD_EXCHANGE_MAX_RANKS 8
+#define MGD_EXCHANGE_HEADER_BYTES 512     /* flag words in front of the caller's bytes */
+#define MGD_EXCHANGE_TIMEOUT_WORD 32      /* header word counting barrier timeouts */
+struct ExchangeView {
+    int world, rank;
+    unsigned* header[MGD_EXCHANGE_MAX_RANKS];   // every rank's header as mapped in THIS process:
+                                                // [kind 0 | 1][source rank] epochs, timeout word
+};
+cudaError_t launch_exchange_barrier(const ExchangeView& v, int which, unsigned epoch, cudaStream_t stream);
 
 // ---- mAP matching -----------------------------------------------------------
 #define MGD_MAX_IOU_THRESHOLDS 16

@@ -109,6 +109,80 @@ __device__ __forceinline__ int approx_verdict(const float4& a, const float4& b, 
     return -1;                                   // also every NaN
 }
 
+// ---- output stores ----------------------------------------------------------------------
+// Every detection leaves the kernels through these helpers: into the caller's tensors and,
+// when those live in a detection exchange (mgd_exchange_*, api.cu), into the same tensors
+// of every peer rank -- plain stores through the peers' IPC mappings, i.e. straight over
+// NVLink, issued as each image's greedy pass produces its rows.  mirror_delta[r] is the byte
+// distance from this rank's exchange buffer to its mapping of peer r's buffer, so one
+// address computation serves every copy; the exchange guarantees 16-byte alignment, which
+// lets the remote copies go out as 16-byte stores (fewer NVLink packets than the scalar
+// stores the local tensors, whose alignment is the caller's business, get).  kMirror is a
+// template parameter: the single-GPU kernels carry none of this.
+template <bool kMirror, class T>
+__device__ __forceinline__ void mirror_store(const NmsArgs& a, T* p, const T& v)
+{
+    if (kMirror) {
+        #pragma unroll
+        for (int r = 0; r < MGD_MAX_MIRRORS; ++r)
+            if (r < a.n_mirrors)
+                *reinterpret_cast<T*>(reinterpret_cast<char*>(p) + a.mirror_delta[r]) = v;
+    }
+}
+
+// multigrid_decode.py:409-420 (_convert_to_xyxy): clip to the image, round half up
+template <bool kMirror>
+__device__ __forceinline__ void emit_det(const NmsArgs& a, size_t o, double W, double H, double x,
+                                         double y, double w, double h, double score, int cls, int index)
+{
+    if (a.out_xywh) {
+        double* p = a.out_xywh + o * 4;
+        p[0] = x; p[1] = y; p[2] = w; p[3] = h;
+        mirror_store<kMirror>(a, reinterpret_cast<double2*>(p), make_double2(x, y));
+        mirror_store<kMirror>(a, reinterpret_cast<double2*>(p) + 1, make_double2(w, h));
+    }
+    if (a.out_xyxy) {
+        int* p = a.out_xyxy + o * 4;
+        int4 q;
+        q.x = (int)floor(__dadd_rn(clipd(x, 0.0, W), 0.5));
+        q.y = (int)floor(__dadd_rn(clipd(y, 0.0, H), 0.5));
+        q.z = (int)floor(__dadd_rn(clipd(__dadd_rn(x, w), 0.0, W), 0.5));
+        q.w = (int)floor(__dadd_rn(clipd(__dadd_rn(y, h), 0.0, H), 0.5));
+        p[0] = q.x; p[1] = q.y; p[2] = q.z; p[3] = q.w;
+        mirror_store<kMirror>(a, reinterpret_cast<int4*>(p), q);
+    }
+    if (a.out_scores) { a.out_scores[o] = score; mirror_store<kMirror>(a, a.out_scores + o, score); }
+    if (a.out_classes) { a.out_classes[o] = cls; mirror_store<kMirror>(a, a.out_classes + o, cls); }
+    if (a.out_index) { a.out_index[o] = index; mirror_store<kMirror>(a, a.out_index + o, index); }
+}
+
+// rows beyond the image's detections: 0 / -1
+template <bool kMirror>
+__device__ __forceinline__ void emit_pad(const NmsArgs& a, size_t o)
+{
+    if (a.out_xywh) {
+        double* p = a.out_xywh + o * 4;
+        for (int e = 0; e < 4; ++e) p[e] = 0.0;
+        mirror_store<kMirror>(a, reinterpret_cast<double2*>(p), make_double2(0.0, 0.0));
+        mirror_store<kMirror>(a, reinterpret_cast<double2*>(p) + 1, make_double2(0.0, 0.0));
+    }
+    if (a.out_xyxy) {
+        int* p = a.out_xyxy + o * 4;
+        for (int e = 0; e < 4; ++e) p[e] = 0;
+        mirror_store<kMirror>(a, reinterpret_cast<int4*>(p), make_int4(0, 0, 0, 0));
+    }
+    if (a.out_scores) { a.out_scores[o] = 0.0; mirror_store<kMirror>(a, a.out_scores + o, 0.0); }
+    if (a.out_classes) { a.out_classes[o] = -1; mirror_store<kMirror>(a, a.out_classes + o, -1); }
+    if (a.out_index) { a.out_index[o] = -1; mirror_store<kMirror>(a, a.out_index + o, -1); }
+}
+
+template <bool kMirror>
+__device__ __forceinline__ void emit_count(const NmsArgs& a, int b, int n)
+{
+    a.out_counts[b] = n;
+    mirror_store<kMirror>(a, a.out_counts + b, n);
+}
+
 // Top-K window for images with more candidates than the shared-memory sort holds.  Greedy NMS
 // visits candidates in descending score and stops at max_boxes kept, so a prefix of the
 // order is usually all it ever looks at.  A 1 024-bin histogram of the float32 score bits
@@ -162,6 +236,7 @@ __device__ int select_top_window(const Cand* cand, int M, unsigned long long* ke
     return *s_n;
 }
 
+template <bool kMirror>
 __global__ void __launch_bounds__(kThreads, 3)
 nms_kernel(const __grid_constant__ NmsArgs a)
 {
@@ -365,21 +440,11 @@ nms_kernel(const __grid_constant__ NmsArgs a)
             const BoxD cd = c_box[i];
             const int pos = c_pos[i];
             const size_t o = (size_t)b * a.max_boxes + slot;
-            if (a.out_xywh) {
-                a.out_xywh[o * 4 + 0] = cd.x; a.out_xywh[o * 4 + 1] = cd.y;
-                a.out_xywh[o * 4 + 2] = cd.w; a.out_xywh[o * 4 + 3] = cd.h;
-            }
-            if (a.out_xyxy) {
-                const double W = (double)(a.image_hw ? a.image_hw[2 * b + 1] : a.in_w);
-                const double H = (double)(a.image_hw ? a.image_hw[2 * b] : a.in_h);
-                a.out_xyxy[o * 4 + 0] = (int)floor(__dadd_rn(clipd(cd.x, 0.0, W), 0.5));
-                a.out_xyxy[o * 4 + 1] = (int)floor(__dadd_rn(clipd(cd.y, 0.0, H), 0.5));
-                a.out_xyxy[o * 4 + 2] = (int)floor(__dadd_rn(clipd(__dadd_rn(cd.x, cd.w), 0.0, W), 0.5));
-                a.out_xyxy[o * 4 + 3] = (int)floor(__dadd_rn(clipd(__dadd_rn(cd.y, cd.h), 0.0, H), 0.5));
-            }
-            if (a.out_scores) a.out_scores[o] = cand ? (double)cand[pos].score : a.in_scores[pos];
-            if (a.out_classes) a.out_classes[o] = c_cls[i];
-            if (a.out_index) a.out_index[o] = cand ? cand[pos].index : pos;
+            const double W = (double)(a.image_hw ? a.image_hw[2 * b + 1] : a.in_w);
+            const double H = (double)(a.image_hw ? a.image_hw[2 * b] : a.in_h);
+            emit_det<kMirror>(a, o, W, H, cd.x, cd.y, cd.w, cd.h,
+                              cand ? (double)cand[pos].score : a.in_scores[pos], c_cls[i],
+                              cand ? cand[pos].index : pos);
         }
         __syncthreads();
     }
@@ -395,14 +460,10 @@ nms_kernel(const __grid_constant__ NmsArgs a)
     const int kept = s_kept;
     for (int q = kept + tid; q < a.max_boxes; q += kThreads) {
         const size_t o = (size_t)b * a.max_boxes + q;
-        if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = 0.0;
-        if (a.out_xyxy) for (int e = 0; e < 4; ++e) a.out_xyxy[o * 4 + e] = 0;
-        if (a.out_scores) a.out_scores[o] = 0.0;
-        if (a.out_classes) a.out_classes[o] = -1;
-        if (a.out_index) a.out_index[o] = -1;
+        emit_pad<kMirror>(a, o);
     }
     if (tid == 0) {
-        a.out_counts[b] = kept;
+        emit_count<kMirror>(a, b, kept);
         if (a.stats) {
             atomicAdd(&a.stats[0], (unsigned long long)M);
             atomicAdd(&a.stats[1], (unsigned long long)kept);
@@ -468,7 +529,7 @@ __device__ __forceinline__ unsigned overlap_sweep(const float4* k_out, const int
     return m;
 }
 
-template <int kWarpCap>
+template <int kWarpCap, bool kMirror>
 __global__ void __launch_bounds__(kWarpsPerCtaW * 32, 7)
 nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
 {
@@ -697,19 +758,8 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
                 const int slot = kept + __popc(keep_bits & ((1u << lane) - 1u));
                 k_out[slot] = co; k_cls[slot] = ccls; k_pos[slot] = (unsigned short)pos;
                 const size_t o = (size_t)b * a.max_boxes + slot;
-                if (a.out_xywh) {
-                    a.out_xywh[o * 4 + 0] = cb.x; a.out_xywh[o * 4 + 1] = cb.y;
-                    a.out_xywh[o * 4 + 2] = cb.w; a.out_xywh[o * 4 + 3] = cb.h;
-                }
-                if (a.out_xyxy) {
-                    a.out_xyxy[o * 4 + 0] = (int)floor(__dadd_rn(clipd(cb.x, 0.0, W), 0.5));
-                    a.out_xyxy[o * 4 + 1] = (int)floor(__dadd_rn(clipd(cb.y, 0.0, H), 0.5));
-                    a.out_xyxy[o * 4 + 2] = (int)floor(__dadd_rn(clipd(__dadd_rn(cb.x, cb.w), 0.0, W), 0.5));
-                    a.out_xyxy[o * 4 + 3] = (int)floor(__dadd_rn(clipd(__dadd_rn(cb.y, cb.h), 0.0, H), 0.5));
-                }
-                if (a.out_scores) a.out_scores[o] = (double)cand[pos].score;
-                if (a.out_classes) a.out_classes[o] = ccls;
-                if (a.out_index) a.out_index[o] = cand[pos].index;
+                emit_det<kMirror>(a, o, W, H, cb.x, cb.y, cb.w, cb.h, (double)cand[pos].score, ccls,
+                                  cand[pos].index);
             }
             kept = k;
             __syncwarp();
@@ -717,14 +767,10 @@ nms_warp_kernel(const __grid_constant__ NmsArgs a, int kept_cap, int min_count)
         // ---- padding + counts -------------------------------------------------------------
         for (int q = kept + lane; q < a.max_boxes; q += 32) {
             const size_t o = (size_t)b * a.max_boxes + q;
-            if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = 0.0;
-            if (a.out_xyxy) for (int e = 0; e < 4; ++e) a.out_xyxy[o * 4 + e] = 0;
-            if (a.out_scores) a.out_scores[o] = 0.0;
-            if (a.out_classes) a.out_classes[o] = -1;
-            if (a.out_index) a.out_index[o] = -1;
+            emit_pad<kMirror>(a, o);
         }
         if (lane == 0) {
-            a.out_counts[b] = kept;
+            emit_count<kMirror>(a, b, kept);
             if (a.stats) {
                 atomicAdd(&a.stats[0], (unsigned long long)M);
                 atomicAdd(&a.stats[1], (unsigned long long)kept);
@@ -771,6 +817,7 @@ __device__ void cta_bitonic(unsigned long long* key, unsigned long long* val, in
     }
 }
 
+template <bool kMirror>
 __global__ void __launch_bounds__(kThreads, 3)
 soft_nms_kernel(const __grid_constant__ NmsArgs a)
 {
@@ -876,29 +923,15 @@ soft_nms_kernel(const __grid_constant__ NmsArgs a)
         if (q < n_out) {
             const int pos = (int)(val[q] & 0xffffffffu);
             const BoxD cd = boxes[pos];
-            if (a.out_xywh) {
-                a.out_xywh[o * 4 + 0] = cd.x; a.out_xywh[o * 4 + 1] = cd.y;
-                a.out_xywh[o * 4 + 2] = cd.w; a.out_xywh[o * 4 + 3] = cd.h;
-            }
-            if (a.out_xyxy) {
-                a.out_xyxy[o * 4 + 0] = (int)floor(__dadd_rn(clipd(cd.x, 0.0, W), 0.5));
-                a.out_xyxy[o * 4 + 1] = (int)floor(__dadd_rn(clipd(cd.y, 0.0, H), 0.5));
-                a.out_xyxy[o * 4 + 2] = (int)floor(__dadd_rn(clipd(__dadd_rn(cd.x, cd.w), 0.0, W), 0.5));
-                a.out_xyxy[o * 4 + 3] = (int)floor(__dadd_rn(clipd(__dadd_rn(cd.y, cd.h), 0.0, H), 0.5));
-            }
-            if (a.out_scores) a.out_scores[o] = soft[pos];
-            if (a.out_classes) a.out_classes[o] = cand ? cand[pos].cls : (a.in_classes ? a.in_classes[pos] : 0);
-            if (a.out_index) a.out_index[o] = cand ? cand[pos].index : pos;
+            emit_det<kMirror>(a, o, W, H, cd.x, cd.y, cd.w, cd.h, soft[pos],
+                              cand ? cand[pos].cls : (a.in_classes ? a.in_classes[pos] : 0),
+                              cand ? cand[pos].index : pos);
         } else {
-            if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = 0.0;
-            if (a.out_xyxy) for (int e = 0; e < 4; ++e) a.out_xyxy[o * 4 + e] = 0;
-            if (a.out_scores) a.out_scores[o] = 0.0;
-            if (a.out_classes) a.out_classes[o] = -1;
-            if (a.out_index) a.out_index[o] = -1;
+            emit_pad<kMirror>(a, o);
         }
     }
     if (tid == 0) {
-        a.out_counts[b] = n_out;
+        emit_count<kMirror>(a, b, n_out);
         if (a.stats) {
             atomicAdd(&a.stats[0], (unsigned long long)M);
             atomicAdd(&a.stats[1], (unsigned long long)n_out);
@@ -953,6 +986,7 @@ __device__ double np_sum_f64(F get, int first, int n)
     return __dadd_rn(np_sum_f64(get, first, n2), np_sum_f64(get, first + n2, n - n2));
 }
 
+template <bool kMirror>
 __global__ void __launch_bounds__(kThreads)
 wbf_kernel(const __grid_constant__ NmsArgs a)
 {
@@ -1127,26 +1161,13 @@ wbf_kernel(const __grid_constant__ NmsArgs a)
             const int rank = by_score ? (int)val[q] : q;
             const double* f = fused + (size_t)rank * 5;
             const int lead_pos = order[tmp[rank]];
-            if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = f[e];
-            if (a.out_xyxy) {
-                a.out_xyxy[o * 4 + 0] = (int)floor(__dadd_rn(clipd(f[0], 0.0, W), 0.5));
-                a.out_xyxy[o * 4 + 1] = (int)floor(__dadd_rn(clipd(f[1], 0.0, H), 0.5));
-                a.out_xyxy[o * 4 + 2] = (int)floor(__dadd_rn(clipd(__dadd_rn(f[0], f[2]), 0.0, W), 0.5));
-                a.out_xyxy[o * 4 + 3] = (int)floor(__dadd_rn(clipd(__dadd_rn(f[1], f[3]), 0.0, H), 0.5));
-            }
-            if (a.out_scores) a.out_scores[o] = f[4];
-            if (a.out_classes) a.out_classes[o] = class_of(lead_pos);
-            if (a.out_index) a.out_index[o] = index_of(lead_pos);
+            emit_det<kMirror>(a, o, W, H, f[0], f[1], f[2], f[3], f[4], class_of(lead_pos), index_of(lead_pos));
         } else {
-            if (a.out_xywh) for (int e = 0; e < 4; ++e) a.out_xywh[o * 4 + e] = 0.0;
-            if (a.out_xyxy) for (int e = 0; e < 4; ++e) a.out_xyxy[o * 4 + e] = 0;
-            if (a.out_scores) a.out_scores[o] = 0.0;
-            if (a.out_classes) a.out_classes[o] = -1;
-            if (a.out_index) a.out_index[o] = -1;
+            emit_pad<kMirror>(a, o);
         }
     }
     if (tid == 0) {
-        a.out_counts[b] = n_out;
+        emit_count<kMirror>(a, b, n_out);
         if (a.stats) {
             atomicAdd(&a.stats[0], (unsigned long long)M);
             atomicAdd(&a.stats[1], (unsigned long long)n_out);
@@ -1173,13 +1194,16 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
     NmsArgs a = a_in;
     cudaError_t err;
     prof_mark_begin(PROF_NMS, stream);
+    const bool mirror = a.n_mirrors > 0;
     if (a.soft) {
-        soft_nms_kernel<<<a.B, kThreads, 0, stream>>>(a);
+        if (mirror) soft_nms_kernel<true><<<a.B, kThreads, 0, stream>>>(a);
+        else        soft_nms_kernel<false><<<a.B, kThreads, 0, stream>>>(a);
         prof_mark_end(PROF_NMS, stream);
         return cudaGetLastError();
     }
     if (a.wbf) {
-        wbf_kernel<<<a.B, kThreads, 0, stream>>>(a);
+        if (mirror) wbf_kernel<true><<<a.B, kThreads, 0, stream>>>(a);
+        else        wbf_kernel<false><<<a.B, kThreads, 0, stream>>>(a);
         prof_mark_end(PROF_NMS, stream);
         return cudaGetLastError();
     }
@@ -1202,6 +1226,10 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
             if (e != cudaSuccess) return e;
             int ctas_per_sm = (int)((220 * 1024) / (dyn + 1024));
             if (ctas_per_sm > 16) ctas_per_sm = 16;
+            static int env_cap = -1;                             // measurements: resident NMS CTAs per SM
+            if (env_cap < 0) { const char* e = getenv("MGD_NMS_WARP_CTAS_PER_SM"); env_cap = e ? atoi(e) : 0; }
+            const int want_cap = env_cap > 0 ? env_cap : a.warp_ctas_per_sm;
+            if (want_cap > 0 && ctas_per_sm > want_cap) ctas_per_sm = want_cap;
             if (ctas_per_sm < 1) ctas_per_sm = 1;
             long long grid = ((long long)a.B + kWarpsPerCtaW - 1) / kWarpsPerCtaW;
             const long long cap_grid = (long long)num_sms * ctas_per_sm;
@@ -1209,16 +1237,19 @@ cudaError_t launch_nms(const NmsArgs& a_in, int num_sms, cudaStream_t stream)
             kernel<<<(unsigned)grid, kWarpsPerCtaW * 32, dyn, stream>>>(a, a.max_boxes, min_count);
             return cudaGetLastError();
         };
-        err = run(nms_warp_kernel<kWarpCapLarge>, kWarpCapLarge, kWarpCapLarge / 4);
+        err = mirror ? run(nms_warp_kernel<kWarpCapLarge, true>, kWarpCapLarge, kWarpCapLarge / 4)
+                     : run(nms_warp_kernel<kWarpCapLarge, false>, kWarpCapLarge, kWarpCapLarge / 4);
         if (err != cudaSuccess) return err;
         prof_mark_end(PROF_NMS, stream);          // one span (= one counted launch) per kernel
         prof_mark_begin(PROF_NMS, stream);
         a.skip_small = kWarpCapLarge;
     }
     const size_t dyn = a.kept_scratch ? 16 : nms_kept_bytes(a.max_boxes);
-    err = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    err = mirror ? cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)
+                 : cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (err != cudaSuccess) return err;
-    nms_kernel<<<a.B, kThreads, dyn, stream>>>(a);
+    if (mirror) nms_kernel<true><<<a.B, kThreads, dyn, stream>>>(a);
+    else        nms_kernel<false><<<a.B, kThreads, dyn, stream>>>(a);
     prof_mark_end(PROF_NMS, stream);
     return cudaGetLastError();
 }

@@ -135,14 +135,35 @@ def poll_status(device=None, stream=None):
 # decode + NMS
 # ------------------------------------------------------------------------------
 
+def _check_out(given, spec, B, device):
+    """Validate caller-provided output tensors (decode_nms / grid_step ``out=``)."""
+    import torch
+    if "counts" not in given:
+        raise ValueError("out= needs a 'counts' tensor")
+    res = {}
+    for k, t in given.items():
+        shape, dt = ((B,), "int32") if k == "counts" else spec.get(k, (None, None))
+        if shape is None:
+            raise ValueError(f"out= has an unknown tensor {k!r}")
+        dt = getattr(torch, dt) if isinstance(dt, str) else dt
+        if not (_is_torch(t) and t.is_cuda and t.device == device and t.is_contiguous()
+                and t.dtype == dt and tuple(t.shape) == tuple(shape)):
+            raise ValueError(f"out[{k!r}] must be a contiguous {dt} CUDA tensor of shape {tuple(shape)}")
+        res[k] = t
+    return res
+
+
 def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_boxes=100,
                confidence=0.1, nms_threshold=0.5, nms_method="diou", per_class=False,
                use_softmax=True, rescore_confidence=True, sync=True, return_stats=False,
-               want=("boxes_xywh", "boxes_xyxy", "scores", "classes", "index")):
+               want=("boxes_xywh", "boxes_xyxy", "scores", "classes", "index"), out=None):
     """Batched decode -> threshold -> NMS -> top-k (B independent reference calls).
 
     preds: list of L (B, Gh, Gw, 5+A+C) float32 NumPy arrays or torch CUDA tensors.
     image_shapes: None (model input size), one (h, w), or (B, 2).
+    out: (torch path) dict of preallocated contiguous CUDA tensors to write into -- 'counts'
+    (B,) int32 plus any of ``want`` with the shapes / dtypes below; tensors taken from a
+    ``sharding.DetectionExchange`` are mirrored to every rank by the kernels.
     Returns a dict of padded arrays/tensors + 'counts' (B,).
     """
     lib = _lib.load()
@@ -177,14 +198,19 @@ def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_
     spec = {"boxes_xywh": ((B, M, 4), "float64"), "boxes_xyxy": ((B, M, 4), "int32"),
             "scores": ((B, M), "float64"), "classes": ((B, M), "int32"),
             "index": ((B, M), "int32")}
-    out = {}
+    given, out = out, {}
+    if given is not None and not _is_torch(preds[0]):
+        raise ValueError("out= is only supported with torch CUDA tensors")
     if _is_torch(preds[0]):
         import torch
         dev = preds[0].device.index or 0
         tp = [p.to(torch.float32).contiguous() for p in preds]
-        for k in want:
-            out[k] = torch.empty(spec[k][0], dtype=getattr(torch, spec[k][1]), device=tp[0].device)
-        out["counts"] = torch.empty((B,), dtype=torch.int32, device=tp[0].device)
+        if given is not None:
+            out = _check_out(given, spec, B, tp[0].device)
+        else:
+            for k in want:
+                out[k] = torch.empty(spec[k][0], dtype=getattr(torch, spec[k][1]), device=tp[0].device)
+            out["counts"] = torch.empty((B,), dtype=torch.int32, device=tp[0].device)
         if d_hw is None and hw is not None:
             d_hw = torch.from_numpy(hw).to(tp[0].device, non_blocking=False)
         addr = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else None
@@ -219,7 +245,7 @@ def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_
 def grid_step(true_boxes, y_true, preds, image_shapes, input_shape, anchors, num_classes,
               max_boxes=100, confidence=0.1, nms_threshold=0.5, nms_method="diou", per_class=False,
               use_softmax=True, rescore_confidence=True, sync=True,
-              want=("boxes_xywh", "boxes_xyxy", "scores", "classes", "index")):
+              want=("boxes_xywh", "boxes_xyxy", "scores", "classes", "index"), out=None):
     """Both halves of the grid path in one library call on torch CUDA tensors
     (``mgd_encode_decode_nms``): ``y_true`` (list of preallocated (Be, G, G, D) tensors) is
     overwritten with the targets of ``true_boxes`` while ``preds`` are decoded and suppressed;
@@ -253,8 +279,11 @@ def grid_step(true_boxes, y_true, preds, image_shapes, input_shape, anchors, num
     spec = {"boxes_xywh": ((B, M, 4), torch.float64), "boxes_xyxy": ((B, M, 4), torch.int32),
             "scores": ((B, M), torch.float64), "classes": ((B, M), torch.int32),
             "index": ((B, M), torch.int32)}
-    out = {k: torch.empty(spec[k][0], dtype=spec[k][1], device=preds[0].device) for k in want}
-    out["counts"] = torch.empty((B,), dtype=torch.int32, device=preds[0].device)
+    if out is not None:
+        out = _check_out(out, spec, B, preds[0].device)
+    else:
+        out = {k: torch.empty(spec[k][0], dtype=spec[k][1], device=preds[0].device) for k in want}
+        out["counts"] = torch.empty((B,), dtype=torch.int32, device=preds[0].device)
     addr = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else None
     rc = lib.mgd_encode_decode_nms(
         ctypes.byref(cfg), ctypes.byref(pc), ctypes.c_void_p(tb.data_ptr()), Be, N,

@@ -136,6 +136,101 @@ def gather_detections_device(local: Dict, n_total: Optional[int] = None) -> Dict
     return out
 
 
+_EXCHANGE_SPEC = (("boxes_xywh", "float64", 4), ("scores", "float64", 1), ("boxes_xyxy", "int32", 4),
+                  ("classes", "int32", 1), ("index", "int32", 1))
+
+
+def exchange_layout(n_total: int, max_boxes: int) -> Tuple[Dict[str, Tuple[int, Tuple[int, ...], str]], int]:
+    """Byte layout of the whole-batch detection tensors inside an exchange buffer:
+    ``{name: (offset, shape, dtype)}`` and the total size.  Every tensor starts on a
+    256-byte boundary (the kernels send remote rows as 16-byte stores)."""
+    off, out = 0, {}
+    for name, dt, width in _EXCHANGE_SPEC:
+        shape = (n_total, max_boxes, 4) if width == 4 else (n_total, max_boxes)
+        out[name] = (off, shape, dt)
+        off += (int(np.prod(shape)) * np.dtype(dt).itemsize + 255) & ~255
+    out["counts"] = (off, (n_total,), "int32")
+    off += (n_total * 4 + 255) & ~255
+    return out, off
+
+
+class _DeviceSpan:
+    """A span of device memory as a ``__cuda_array_interface__`` provider (keeps ``owner`` alive)."""
+
+    def __init__(self, ptr, shape, dtype, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": np.dtype(dtype).str,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class DetectionExchange:
+    """Whole-batch detection tensors that every rank ends up holding -- without a collective.
+
+    SURVEY.md 8e: the path's one exchange step.  Each rank owns ``bytes`` of device memory laid
+    out as the padded detection tensors of the WHOLE batch (``n_total`` images); the buffers
+    of all ranks are mapped into every process (CUDA IPC, ``mgd_exchange_*`` in libmgd).  A
+    rank decodes its shard with ``out=self.local()``: the NMS kernels store each image's rows
+    into every rank's tensors while they run (peer stores over NVLink), so when the call's
+    work completes on the stream ``self.full()`` holds all images on every rank.  Collective
+    semantics: every rank makes the same sequence of mirrored calls.
+
+    One process per GPU on one node; ``torch.distributed`` only carries the 64-byte IPC
+    handles at construction.  World size 1 works without ``torch.distributed``."""
+
+    def __init__(self, n_total: int, max_boxes: int, device: Optional[int] = None, group=None):
+        import ctypes
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        d = _dist()
+        self.rank, self.world_size = (d.get_rank(group), d.get_world_size(group)) if d else (0, 1)
+        self.n_total, self.max_boxes = int(n_total), int(max_boxes)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.layout, self.bytes = exchange_layout(self.n_total, self.max_boxes)
+        self._lib = lib
+        self._h = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+        _lib.raise_for_status(lib.mgd_exchange_create(self.device, self.world_size, self.rank, self.bytes,
+                                                      ctypes.byref(self._h), handle))
+        if self.world_size > 1:
+            handles: List = [None] * self.world_size
+            d.all_gather_object(handles, bytes(handle), group=group)
+            blob = (ctypes.c_ubyte * (_lib.IPC_HANDLE_BYTES * self.world_size)).from_buffer_copy(b"".join(handles))
+            _lib.raise_for_status(lib.mgd_exchange_connect(self._h, blob))
+        base, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.raise_for_status(lib.mgd_exchange_buffer(self._h, ctypes.byref(base), ctypes.byref(nbytes)))
+        dev = torch.device("cuda", self.device)
+        self._full = {k: torch.as_tensor(_DeviceSpan(base.value + off, shape, dt, self), device=dev)
+                      for k, (off, shape, dt) in self.layout.items()}
+        if self.world_size > 1:
+            d.barrier(group=group)            # every rank has mapped every buffer before the first store
+
+    def full(self) -> Dict:
+        """The whole batch's tensors in this rank's memory (valid once a mirrored call completed)."""
+        return dict(self._full)
+
+    def local(self, keys: Optional[Sequence[str]] = None) -> Dict:
+        """This rank's slice of every tensor (``shard_bounds`` order): pass as ``out=``."""
+        lo, hi = shard_bounds(self.n_total, self.rank, self.world_size)
+        keys = list(self._full) if keys is None else list(keys) + ["counts"]
+        return {k: self._full[k][lo:hi] for k in dict.fromkeys(keys)}
+
+    def timeouts(self) -> int:
+        """Device-side barrier timeouts so far (a peer that never made its call); 0 is healthy."""
+        import ctypes
+        import torch
+        n = ctypes.c_int()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._lib.raise_for_status(self._lib.mgd_exchange_timeouts(self._h, ctypes.c_void_p(stream), ctypes.byref(n)))
+        return int(n.value)
+
+    def close(self):
+        if self._h:
+            self._full = {}
+            self._lib.mgd_exchange_destroy(self._h)
+            self._h = None
+
+
 class ShardedGridPath:
     """Runs the hot path on this rank's slice of a global batch.
 
@@ -163,13 +258,22 @@ class ShardedGridPath:
         return self.compute.encode_targets(global_boxes[sl], self.input_shape, self.anchors,
                                            self.num_classes, **kw)
 
-    def decode_nms(self, global_preds, global_image_shapes=None, gather=True, dst=None, **kw):
+    def decode_nms(self, global_preds, global_image_shapes=None, gather=True, dst=None, exchange=None, **kw):
+        """``gather``: True (host lists), "device" (one all-gather), "exchange" (the NMS kernels
+        write every rank's tensors directly; needs ``exchange=DetectionExchange(n, max_boxes)``),
+        False (local shard only)."""
         n = global_preds[0].shape[0]
         sl = self.local_slice(n)
         shapes = None
         if global_image_shapes is not None:
             shapes = np.asarray(global_image_shapes).reshape(-1, 2)
             shapes = shapes[sl] if shapes.shape[0] == n else shapes
+        if gather == "exchange":
+            if exchange is None or exchange.n_total != n:
+                raise ValueError("gather='exchange' needs exchange=DetectionExchange(n_images, max_boxes)")
+            self.compute.decode_nms([p[sl] for p in global_preds], shapes, self.input_shape,
+                                    self.anchors, self.num_classes, out=exchange.local(kw.get("want")), **kw)
+            return exchange.full()
         det = self.compute.decode_nms([p[sl] for p in global_preds], shapes, self.input_shape,
                                       self.anchors, self.num_classes, **kw)
         if gather == "device":

@@ -1,9 +1,10 @@
 """Turn gpurun_out ncu captures into the committed summaries under profiles/.
 
-usage: python scripts/summarise_profiles.py <round tag> <launches.csv> <full.ncu-rep> <images per launch of the full capture: fill,decode,nms,assign>
+usage: python scripts/summarise_profiles.py <round tag> <launches.csv> <full.ncu-rep> [<more.ncu-rep> ...]
+(the first launch of every kernel name over all reports is summarised)
 """
 import collections, csv, json, os, subprocess, sys
-tag, launches_csv, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+tag, launches_csv, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
@@ -35,10 +36,7 @@ for (k, g, b), v in agg.items():
 open(os.path.join(out_dir, f"{tag}_launches.md"), "w").write("\n".join(lines) + "\n")
 
 # ---- full capture --------------------------------------------------------------------------
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-hdr = rows[0]; units = rows[1]; idx = {h: i for i, h in enumerate(hdr)}
-want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+want = ["gpu__time_duration.sum", "launch__waves_per_multiprocessor", "sm__cycles_active.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed" ,
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -54,8 +52,15 @@ md = [f"# ncu --set full summary, round {tag}", "",
       "`ncu --set full --clock-control none --import-source on` on the same bench command; one launch per kernel shown",
       "(B = 4096 images: encode kernels run per 1024-image chunk, decode / NMS once per step).", ""]
 traffic = {}
-for r in rows[2:]:
+all_rows = []
+for rep in reps:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]; units = rows[1]; idx = {h: i for i, h in enumerate(hdr)}
+    all_rows += [(r, units, idx, os.path.basename(rep)) for r in rows[2:]]
+for r, units, idx, rep_name in all_rows:
     k = short(r[idx["Kernel Name"]])
+    if rep_name.endswith("dense.ncu-rep"): k += " [dense random head, 256 images]"
     if k in seen: continue
     seen[k] = 1
     md.append(f"## `{k}`\n")

@@ -1,0 +1,105 @@
+"""Detection exchange (mgd_exchange_*, sharding.DetectionExchange): detections mirrored into
+every rank's tensors by the NMS kernels themselves.
+
+The driver's GPU box has one device, so the multi-rank case runs as TWO PROCESSES ON THE SAME
+GPU: the buffers still cross process boundaries through CUDA IPC and every remote row is a
+peer store through the mapping, exactly the code path of a 2-GPU node (where the mapping
+leads over NVLink; `bench.py --scaling strong` under torchrun measures that)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+S, C, N = 416, 20, 12
+KW = dict(max_boxes=50, confidence=0.05, nms_threshold=0.45, nms_method="diou")
+KEYS = ("boxes_xywh", "boxes_xyxy", "scores", "classes", "index", "counts")
+
+
+def _inputs(B, seed=5):
+    import torch
+    from multigriddet_b200 import engine, synth
+    anchors = synth.voc_anchors(np.float32) if hasattr(synth, "voc_anchors") else synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(seed, B, N, S, C)
+    y = engine.encode_targets(torch.from_numpy(boxes).cuda(), (S, S), anchors, C)
+    preds = synth.planted_head_outputs(y, 3, seed=seed)
+    shapes = synth.image_shapes(seed, B)
+    return anchors, preds, shapes
+
+
+def test_exchange_world_of_one_matches_plain_call():
+    import torch
+    from multigriddet_b200 import engine, sharding
+    B = 9
+    anchors, preds, shapes = _inputs(B)
+    ref = engine.decode_nms(preds, shapes, (S, S), anchors, C, **KW)
+    ex = sharding.DetectionExchange(B, KW["max_boxes"])
+    try:
+        got = engine.decode_nms(preds, shapes, (S, S), anchors, C, out=ex.local(), **KW)
+        full = ex.full()
+        for k in KEYS:
+            assert got[k].data_ptr() == full[k].data_ptr()
+            assert torch.equal(full[k], ref[k]), k
+        assert ex.timeouts() == 0
+        # outputs partly outside the exchange are refused, not silently half-mirrored
+        mixed = dict(ex.local())
+        mixed["scores"] = torch.empty_like(mixed["scores"])
+        with pytest.raises(ValueError, match="exchange"):
+            engine.decode_nms(preds, shapes, (S, S), anchors, C, out=mixed, **KW)
+    finally:
+        ex.close()
+
+
+def _rank_main(rank, world, port, B, method, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from multigriddet_b200 import engine, sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(0)
+    try:
+        anchors, preds, shapes = _inputs(B)
+        kw = dict(KW, nms_method=method)
+        ref = engine.decode_nms(preds, shapes, (S, S), anchors, C, **kw)
+        ex = sharding.DetectionExchange(B, kw["max_boxes"])
+        path = sharding.ShardedGridPath(anchors, C, (S, S))
+        ok = True
+        for it in range(3):                                   # repeated calls: epochs advance
+            full = path.decode_nms(preds, shapes, gather="exchange", exchange=ex, **kw)
+            torch.cuda.synchronize()
+            ok = ok and all(torch.equal(full[k], ref[k]) for k in KEYS)
+            if it == 0:                                       # wipe, so the next round must rewrite it
+                dist.barrier()
+                for k in KEYS:
+                    full[k].zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+        q.put((rank, bool(ok), ex.timeouts()))
+        dist.barrier()
+        ex.close()
+    except Exception as e:                                    # pragma: no cover
+        q.put((rank, False, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("method", ["diou", "soft"])
+def test_two_ranks_mirror_their_shards_into_each_other(method):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, B = 2, 11                                          # uneven shards: 6 + 5 images
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_rank_main, args=(r, world, port, B, method, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, timeouts in sorted(res):
+        assert ok is True, (rank, timeouts)
+        assert timeouts == 0, (rank, timeouts)

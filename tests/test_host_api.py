@@ -97,3 +97,22 @@ def test_pinned_pool_hands_out_plain_arrays_without_a_gpu():
     a = pool.empty((512, 512), np.float32)           # mgd_host_alloc -> MGD_ERR_NO_DEVICE -> np.empty
     assert a.shape == (512, 512) and a.dtype == np.float32 and pool._total == 0
     a[:] = 1.0
+
+
+def test_exchange_layout_is_aligned_and_disjoint():
+    """sharding.exchange_layout: whole-batch detection tensors inside an exchange buffer."""
+    from multigriddet_b200 import sharding
+    for n_total, m in ((1, 1), (11, 50), (4096, 100), (7, 3)):
+        layout, total = sharding.exchange_layout(n_total, m)
+        spans = []
+        for name, (off, shape, dt) in layout.items():
+            nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+            assert off % 256 == 0 and shape[0] == n_total
+            spans.append((off, off + nbytes))
+        spans.sort()
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= total
+        assert set(layout) == {"boxes_xywh", "boxes_xyxy", "scores", "classes", "index", "counts"}
+        # the two box tensors stay 16-byte aligned for every shard start (rows are 32 / 16 bytes)
+        for lo in range(n_total):
+            assert (layout["boxes_xywh"][0] + lo * m * 32) % 16 == 0
+            assert (layout["boxes_xyxy"][0] + lo * m * 16) % 16 == 0
