@@ -187,7 +187,7 @@ class DetectionExchange:
         self.n_total, self.max_boxes = int(n_total), int(max_boxes)
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.layout, self.bytes = exchange_layout(self.n_total, self.max_boxes)
-        self._lib = lib
+        self._lib, self._mod = lib, _lib
         self._h = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
         _lib.raise_for_status(lib.mgd_exchange_create(self.device, self.world_size, self.rank, self.bytes,
@@ -221,7 +221,7 @@ class DetectionExchange:
         import torch
         n = ctypes.c_int()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        self._lib.raise_for_status(self._lib.mgd_exchange_timeouts(self._h, ctypes.c_void_p(stream), ctypes.byref(n)))
+        self._mod.raise_for_status(self._lib.mgd_exchange_timeouts(self._h, ctypes.c_void_p(stream), ctypes.byref(n)))
         return int(n.value)
 
     def close(self):

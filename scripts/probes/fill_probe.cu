@@ -29,6 +29,27 @@ __global__ void k_ctatile(float4* p, size_t n, int per, int cs) {
         for (int f = threadIdx.x; f < (int)tile_units; f += blockDim.x) { if (cs) __stcs(d + f, z); else d[f] = z; }
     }
 }
+// TMA bulk stores: a CTA keeps one zeroed tile in shared memory and one thread per warp issues
+// cp.async.bulk.global.shared::cta copies of `tile` bytes (no LSU store instructions at all)
+__global__ void k_bulk(char* p, size_t bytes, int tile, int persistent) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    for (int i = threadIdx.x * 16; i < tile; i += blockDim.x * 16) *reinterpret_cast<float4*>(sm + i) = make_float4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const size_t tiles = bytes / tile;
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((size_t)gridDim.x * blockDim.x) >> 5;
+    if (lane == 0) {
+        const unsigned src = (unsigned)__cvta_generic_to_shared(sm);
+        for (size_t t = warp; t < tiles; t += nw) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p + t * tile), "r"(src), "r"(tile) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (!persistent) break;
+            asm volatile("cp.async.bulk.wait_group.read 8;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
 template <typename F> float timeit(F f) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     f(); f(); cudaDeviceSynchronize();
@@ -48,5 +69,17 @@ int main() {
         for (int per : {4, 11, 44})
             printf("ctatile   cs=%d per=%2d        %6.0f GB/s\n", cs, per, gbs(timeit([&] { k_ctatile<<<148 * 8, 256>>>(p, n, per, cs); })));
     }
+    for (int tile : {2048, 4096, 5632, 8192, 16384, 32768}) {
+        cudaFuncSetAttribute(k_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, tile);
+        for (int ctas : {148 * 2, 148 * 4, 148 * 8}) {
+            printf("bulk persistent tile=%5d ctas=%5d   %6.0f GB/s\n", tile, ctas,
+                   gbs(timeit([&] { k_bulk<<<ctas, 256, tile>>>((char*)p, bytes, tile, 1); })));
+        }
+        const size_t tiles = bytes / tile;
+        const unsigned blocks = (unsigned)((tiles + 7) / 8);
+        printf("bulk one-shot   tile=%5d blocks=%7u %6.0f GB/s\n", tile, blocks,
+               gbs(timeit([&] { k_bulk<<<blocks, 256, tile>>>((char*)p, bytes, tile, 0); })));
+    }
+    { cudaError_t e = cudaDeviceSynchronize(); if (e != cudaSuccess) printf("CUDA error: %s\n", cudaGetErrorString(e)); }
     return 0;
 }
