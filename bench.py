@@ -391,7 +391,13 @@ def run_b200(args):
         out_keep[:] = [det]
         return det
 
-    exchange = [None]
+    # the detection exchange is set up collectively, once; a host whose GPUs cannot map each
+    # other's memory falls back to the NCCL gather (and says so in the line)
+    exchange, exchange_error = [None], None
+    try:
+        exchange[0] = sharding.DetectionExchange(Bs, POST["max_boxes"], device=local)
+    except Exception as e:
+        exchange_error = repr(e)
 
     def strong_step(gather="exchange"):
         """configs[4] as written: this rank's slice of the 4 096-image batch plus the exchange
@@ -400,9 +406,9 @@ def run_b200(args):
         stores over NVLink, no collective call); "device": one NCCL all-gather of the packed
         lists after the step; "host": all_gather_object of host copies."""
         n = hi_s - lo_s
+        if gather == "exchange" and exchange[0] is None:
+            gather = "device"
         if gather == "exchange":
-            if exchange[0] is None:
-                exchange[0] = sharding.DetectionExchange(Bs, POST["max_boxes"], device=local)
             ex = exchange[0]
             engine.grid_step(d_boxes[:n], [y[:n] for y in y_out], [p[:n] for p in preds], d_hw[:n],
                              (S, S), anchors, C, sync=False, want=WANT, out=ex.local(WANT), **POST)
@@ -474,6 +480,7 @@ def run_b200(args):
                                  "mappings, NVLink for N > 1; two one-warp flag barriers per step, no "
                                  "collective call); every rank ends with all detections",
                        "exchange_timeouts": exchange[0].timeouts() if exchange[0] is not None else None,
+                       "exchange_error": exchange_error,
                        "nccl_gather": dict(res["device"], note="gather_detections_device: one NCCL all-gather "
                                            "of the packed lists after the step (the baseline the exchange replaces)"),
                        "host_gather": dict(res["host"], note="gather_detections: all_gather_object of host copies"),
@@ -751,7 +758,9 @@ def run_b200(args):
                        "images_per_rank_per_step": n_step_images,
                        "images_per_step_total": Bs if strong else B * world,
                        "sharding": (f"image-sharded x{world}; " +
-                                    ("detections written into every rank's tensors by the NMS kernels (peer stores, no collective call)" if strong else "no collective")),
+                                    (("detections written into every rank's tensors by the NMS kernels (peer stores, no collective call)"
+                                      if exchange[0] is not None else "detection lists all-gathered every step (NCCL)")
+                                     if strong else "no collective")),
                        "step": "one mgd_encode_decode_nms call per rank (encode + decode + NMS; the library "
                                "overlaps the y_true writer with the NMS internally)",
                        "cpus_bound_to_rank": numa,

@@ -196,14 +196,24 @@ class DetectionExchange:
             handles: List = [None] * self.world_size
             d.all_gather_object(handles, bytes(handle), group=group)
             blob = (ctypes.c_ubyte * (_lib.IPC_HANDLE_BYTES * self.world_size)).from_buffer_copy(b"".join(handles))
-            _lib.raise_for_status(lib.mgd_exchange_connect(self._h, blob))
+            err = None
+            try:
+                _lib.raise_for_status(lib.mgd_exchange_connect(self._h, blob))
+            except Exception as e:                        # e.g. no peer access between two devices
+                err = e
+            # all ranks agree on the outcome (and nobody stores before everybody has mapped everything)
+            oks: List = [None] * self.world_size
+            d.all_gather_object(oks, err is None, group=group)
+            if not all(oks):
+                lib.mgd_exchange_destroy(self._h)
+                self._h = None
+                raise RuntimeError(f"detection exchange unavailable on ranks {[r for r, ok in enumerate(oks) if not ok]}"
+                                   + (f": {err}" if err is not None else ""))
         base, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
         _lib.raise_for_status(lib.mgd_exchange_buffer(self._h, ctypes.byref(base), ctypes.byref(nbytes)))
         dev = torch.device("cuda", self.device)
         self._full = {k: torch.as_tensor(_DeviceSpan(base.value + off, shape, dt, self), device=dev)
                       for k, (off, shape, dt) in self.layout.items()}
-        if self.world_size > 1:
-            d.barrier(group=group)            # every rank has mapped every buffer before the first store
 
     def full(self) -> Dict:
         """The whole batch's tensors in this rank's memory (valid once a mirrored call completed)."""
@@ -212,6 +222,9 @@ class DetectionExchange:
     def local(self, keys: Optional[Sequence[str]] = None) -> Dict:
         """This rank's slice of every tensor (``shard_bounds`` order): pass as ``out=``."""
         lo, hi = shard_bounds(self.n_total, self.rank, self.world_size)
+        if hi == lo:
+            raise ValueError("every rank of a detection exchange needs at least one image "
+                             f"({self.n_total} images over {self.world_size} ranks)")
         keys = list(self._full) if keys is None else list(keys) + ["counts"]
         return {k: self._full[k][lo:hi] for k in dict.fromkeys(keys)}
 
@@ -224,8 +237,14 @@ class DetectionExchange:
         self._mod.raise_for_status(self._lib.mgd_exchange_timeouts(self._h, ctypes.c_void_p(stream), ctypes.byref(n)))
         return int(n.value)
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def close(self):
-        if self._h:
+        if getattr(self, "_h", None):
             self._full = {}
             self._lib.mgd_exchange_destroy(self._h)
             self._h = None
