@@ -94,6 +94,26 @@ def test_no_cpu_fallback(lib):
         engine.decode_dense(preds, anchors, 80, (608, 608))
 
 
+def test_exchange_argument_validation_and_no_device(lib):
+    """mgd_exchange_*: argument errors are reported before any device work; without a device
+    the exchange fails like every other entry point."""
+    ex = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+    bad = [(0, 0, 0, 1024), (0, 9, 0, 1024), (0, 2, 2, 1024), (0, 2, -1, 1024), (0, 1, 0, 0)]
+    for dev, world, rank, nbytes in bad:
+        rc = lib.mgd_exchange_create(dev, world, rank, nbytes, ctypes.byref(ex), handle)
+        assert rc in (_lib.ERR_INVALID_ARGUMENT, _lib.ERR_UNSUPPORTED), (world, rank, nbytes, rc)
+        assert not ex.value
+    assert lib.mgd_exchange_create(0, 1, 0, 1024, None, handle) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.mgd_exchange_connect(None, None) == _lib.ERR_INVALID_ARGUMENT
+    assert lib.mgd_exchange_destroy(None) == _lib.OK
+    if lib.mgd_device_count() == 0:
+        rc = lib.mgd_exchange_create(0, 1, 0, 1024, ctypes.byref(ex), handle)
+        assert rc == _lib.ERR_NO_DEVICE and not ex.value
+        with pytest.raises(_lib.MgdError, match="no CPU fallback"):
+            _lib.raise_for_status(rc)
+
+
 def test_product_package_never_touches_the_oracle():
     pkg = os.path.join(ROOT, "multigriddet_b200")
     for dirpath, _, names in os.walk(pkg):

@@ -78,6 +78,23 @@ def _rank_main(rank, world, port, B, method, q):
                     full[k].zero_()
                 torch.cuda.synchronize()
                 dist.barrier()
+        # the fused entry (encode + decode/NMS in one call) mirrors the same way
+        from multigriddet_b200 import synth
+        lo, hi = sharding.shard_bounds(B, rank, world)
+        for k in KEYS:
+            ex.full()[k].zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        boxes = torch.from_numpy(synth.synth_boxes(9, hi - lo, N, S, C)).cuda()
+        y_ref = engine.encode_targets(boxes, (S, S), anchors, C)
+        y_out = [torch.empty_like(y) for y in y_ref]
+        hw = torch.from_numpy(np.ascontiguousarray(shapes[lo:hi])).cuda()
+        engine.grid_step(boxes, y_out, [p[lo:hi].contiguous() for p in preds], hw, (S, S), anchors, C,
+                         out=ex.local(), **kw)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ok = ok and all(torch.equal(ex.full()[k], ref[k]) for k in KEYS)
+        ok = ok and all(torch.equal(a, b) for a, b in zip(y_out, y_ref))
         q.put((rank, bool(ok), ex.timeouts()))
         dist.barrier()
         ex.close()
