@@ -120,3 +120,40 @@ def test_two_ranks_mirror_their_shards_into_each_other(method):
     for rank, ok, timeouts in sorted(res):
         assert ok is True, (rank, timeouts)
         assert timeouts == 0, (rank, timeouts)
+
+
+def test_device_calls_are_cuda_graph_capturable():
+    """Device-memory calls neither synchronise nor allocate outside the stream: the fused step
+    can be captured into a CUDA graph and replayed (scripts/graph_probe.py times it; replay is
+    not faster than the eager calls, which are not launch-bound)."""
+    import torch
+    from multigriddet_b200 import engine, synth
+    B = 5
+    anchors, preds, shapes = _inputs(B, seed=8)
+    hw = torch.from_numpy(shapes).cuda()
+    boxes = torch.from_numpy(synth.synth_boxes(4, B, N, S, C)).cuda()
+    y_ref = engine.encode_targets(boxes, (S, S), anchors, C)
+    ref = engine.decode_nms(preds, hw, (S, S), anchors, C, **KW)
+    y_out = [torch.zeros_like(t) for t in y_ref]
+    out = {k: torch.zeros_like(ref[k]) for k in KEYS}
+
+    def step():
+        engine.grid_step(boxes, y_out, preds, hw, (S, S), anchors, C, sync=False, out=out, **KW)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()                                            # warm-up: lazy one-time allocations
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for t in list(out.values()) + y_out:
+        t.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    torch.cuda.synchronize()
+    assert int(out["counts"].sum()) == 0                  # captured, not executed
+    g.replay()
+    torch.cuda.synchronize()
+    assert all(torch.equal(out[k], ref[k]) for k in KEYS)
+    assert all(torch.equal(a, b) for a, b in zip(y_out, y_ref))
