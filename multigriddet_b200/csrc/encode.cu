@@ -36,6 +36,19 @@ namespace {
 constexpr int kAssignThreads = 256;
 constexpr int kFillThreads = 256;
 
+// The owner table travels from the assign kernel to the writer through L2 (32 MB per chunk).
+// Stored with the L2 evict_last priority: the writer's 3 GB store stream otherwise pushes it
+// out to DRAM before it is read back (ncu: 38 MB of DRAM reads per launch), and those reads
+// cost the write stream 4 % of its rate (0.418 -> 0.399 ms per 1 024 images; the lookup as a
+// whole costs 11 %: 0.372 ms without it, MGD_FILL_DEBUG=1).  A matching evict_first hint on
+// the read changes nothing.
+__device__ __forceinline__ void st_table_keep(int* p, int v)
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 // generators.py:2486-2494 + np.round(iol, 3) + first maximum (lowest global index)
 __device__ __forceinline__ int match_anchor(const HeadGeom& g, float bw, float bh)
 {
@@ -256,7 +269,7 @@ encode_assign_kernel(const __grid_constant__ EncodeArgs a)
         const int* src = owner + g.cell_off[l];
         for (int i = tid; i < n; i += kAssignThreads) {
             const int v = src[i];
-            dst[i] = v < 0 ? -1 : v + rec_base;
+            st_table_keep(dst + i, v < 0 ? -1 : v + rec_base);
             n_pos += (v >= 0);
         }
     }
@@ -277,6 +290,7 @@ struct FillPlan {
     int R[MGD_MAX_LAYERS];                  // rows per warp tile = 32 / gcd(dv, 32)
     long long tile_first[MGD_MAX_LAYERS + 1];
     long long rows[MGD_MAX_LAYERS];
+    int debug;                              // MGD_FILL_DEBUG=1 (measurements): no owner lookup, no patches
 };
 
 template <int VEC> struct VecT;
@@ -312,7 +326,7 @@ encode_fill_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__
     };
     // owner code of row `lane` of a tile (-1 beyond the tile / the layer's last row)
     auto load_codes = [&](long long tile) {
-        if (tile >= total) return -1;
+        if (tile >= total || (p.debug & 1)) return -1;
         const int l = tile_layer(tile);
         const long long row = (tile - p.tile_first[l]) * p.R[l] + lane;
         if (lane >= p.R[l] || row >= p.rows[l]) return -1;
@@ -417,6 +431,9 @@ cudaError_t launch_encode_fill(const EncodeArgs& a, int num_sms, cudaStream_t st
         tiles += (p.rows[l] + p.R[l] - 1) / p.R[l];
     }
     p.tile_first[g.L] = tiles;
+    static int env_dbg = -1;
+    if (env_dbg < 0) { const char* e = getenv("MGD_FILL_DEBUG"); env_dbg = e ? atoi(e) : 0; }
+    p.debug = env_dbg;
     // One tile per warp and no persistent loop: on B200 a write-only stream reaches
     // ~7.5 TB/s with hundreds of thousands of short-lived CTAs but only ~6 TB/s from a
     // single resident wave looping over the same bytes (scripts/probes/fill_probe.cu).
