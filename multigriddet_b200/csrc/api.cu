@@ -560,6 +560,9 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
                 return fail(MGD_ERR_INVALID_ARGUMENT, "%s inside a detection exchange must be 16-byte aligned", o.name);
         }
         ++ex->epoch;
+        // "ready", first half: this rank no longer reads the rows the call is about to overwrite
+        if (ex->world > 1)
+            CUDA_TRY(launch_exchange_barrier(exchange_view(ex), 0, ex->epoch, MGD_EXCHANGE_SIGNAL, stream));
     }
     for (int b0 = 0; b0 < batch; b0 += step) {
         const int nb = batch - b0 < step ? batch - b0 : step;
@@ -646,13 +649,14 @@ int decode_nms_device(const HeadGeom& g, const mgd_post_config& post, const floa
             for (int r = 0; r < ex->world; ++r)
                 if (r != ex->rank)
                     n.mirror_delta[n.n_mirrors++] = (long long)(ex->alloc[r] - ex->alloc[ex->rank]);
-            // "ready": no peer still reads the rows this call overwrites (waits under the decoder)
-            if (b0 == 0) CUDA_TRY(launch_exchange_barrier(exchange_view(ex), 0, ex->epoch, stream));
+            // "ready", second half: every peer has entered its call (it may still be decoding)
+            if (b0 == 0) CUDA_TRY(launch_exchange_barrier(exchange_view(ex), 0, ex->epoch, MGD_EXCHANGE_WAIT, stream));
         }
         CUDA_TRY(launch_nms(n, num_sms, stream));
         // "complete": every rank's rows of this call have landed everywhere
         if (ex && ex->world > 1 && b0 + nb >= batch)
-            CUDA_TRY(launch_exchange_barrier(exchange_view(ex), 1, ex->epoch, stream));
+            CUDA_TRY(launch_exchange_barrier(exchange_view(ex), 1, ex->epoch,
+                                             MGD_EXCHANGE_SIGNAL | MGD_EXCHANGE_WAIT, stream));
         CUDA_TRY(al.put(n.sort_scratch));
         CUDA_TRY(al.put(n.kept_scratch));
         CUDA_TRY(al.put(n.soft_scratch));

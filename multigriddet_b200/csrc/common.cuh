@@ -123,7 +123,9 @@ struct ExchangeView {
     unsigned* header[MGD_EXCHANGE_MAX_RANKS];   // every rank's header as mapped in THIS process:
                                                 // [kind 0 | 1][source rank] epochs, timeout word
 };
-cudaError_t launch_exchange_barrier(const ExchangeView& v, int which, unsigned epoch, cudaStream_t stream);
+enum { MGD_EXCHANGE_SIGNAL = 1, MGD_EXCHANGE_WAIT = 2 };
+cudaError_t launch_exchange_barrier(const ExchangeView& v, int which, unsigned epoch, int phase,
+                                    cudaStream_t stream);
 
 // ---- mAP matching -----------------------------------------------------------
 #define MGD_MAX_IOU_THRESHOLDS 16

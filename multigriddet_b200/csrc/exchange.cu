@@ -9,7 +9,8 @@
 // words in the same buffers.
 //   entry barrier ("ready"):   before a rank's first remote store of a call, every peer has
 //                              enqueued past the previous call's consumers (nobody still
-//                              reads the rows about to be overwritten);
+//                              reads the rows about to be overwritten); signalled at the start
+//                              of the call, waited for just before the NMS;
 //   exit barrier ("complete"): after a rank's last remote store; when it returns on the
 //                              stream, every rank's rows of this call are in local memory.
 // Flags are monotonically increasing call counters (epochs), one word per (kind, source
@@ -29,16 +30,23 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
+// phase bit 0: signal (tell every peer this rank has reached the point), bit 1: wait (for every
+// peer's signal).  The "ready" barrier is issued as two launches -- the signal at the very start
+// of a call, the wait just before the first remote store -- so a peer only has to have ENTERED
+// its call, not finished its decoder, for this rank's NMS to start.
 __global__ void __launch_bounds__(32)
-exchange_barrier_kernel(const __grid_constant__ ExchangeView v, int which, unsigned epoch)
+exchange_barrier_kernel(const __grid_constant__ ExchangeView v, int which, unsigned epoch, int phase)
 {
     const int r = threadIdx.x;
     if (r >= v.world || r == v.rank) return;
-    // everything this stream did before (the NMS kernels' remote stores completed with their
-    // grid) is ordered before the flag by the fence's cumulativity
-    __threadfence_system();
-    unsigned* theirs = v.header[r] + which * MGD_EXCHANGE_MAX_RANKS + v.rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+    if (phase & 1) {
+        // everything this stream did before (the NMS kernels' remote stores completed with their
+        // grid) is ordered before the flag by the fence's cumulativity
+        __threadfence_system();
+        unsigned* theirs = v.header[r] + which * MGD_EXCHANGE_MAX_RANKS + v.rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+    }
+    if (!(phase & 2)) return;
     const unsigned* mine = v.header[v.rank] + which * MGD_EXCHANGE_MAX_RANKS + r;
     const unsigned long long t0 = global_ns();
     for (;;) {
@@ -55,9 +63,10 @@ exchange_barrier_kernel(const __grid_constant__ ExchangeView v, int which, unsig
 
 }  // namespace
 
-cudaError_t launch_exchange_barrier(const ExchangeView& v, int which, unsigned epoch, cudaStream_t stream)
+cudaError_t launch_exchange_barrier(const ExchangeView& v, int which, unsigned epoch, int phase,
+                                    cudaStream_t stream)
 {
     if (v.world <= 1) return cudaSuccess;
-    exchange_barrier_kernel<<<1, 32, 0, stream>>>(v, which, epoch);
+    exchange_barrier_kernel<<<1, 32, 0, stream>>>(v, which, epoch, phase);
     return cudaGetLastError();
 }
