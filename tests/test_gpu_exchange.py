@@ -55,6 +55,10 @@ def test_exchange_world_of_one_matches_plain_call():
 
 def _rank_main(rank, world, port, B, method, q):
     sys.path.insert(0, ROOT)
+    if method.endswith("+chunks"):                            # several internal chunks per mirrored call
+        method = method.split("+")[0]
+        os.environ["MGD_DECODE_CHUNK_IMAGES"] = "2"
+        os.environ["MGD_ENCODE_CHUNK_IMAGES"] = "2"
     import torch
     import torch.distributed as dist
     from multigriddet_b200 import engine, sharding
@@ -104,7 +108,7 @@ def _rank_main(rank, world, port, B, method, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("method", ["diou", "soft"])
+@pytest.mark.parametrize("method", ["diou", "soft", "diou+chunks"])
 def test_two_ranks_mirror_their_shards_into_each_other(method):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
