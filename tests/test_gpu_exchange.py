@@ -114,7 +114,10 @@ def test_two_ranks_mirror_their_shards_into_each_other(method):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     world, B = 2, 11                                          # uneven shards: 6 + 5 images
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:                               # a port that is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_rank_main, args=(r, world, port, B, method, q)) for r in range(world)]
     for p in procs:
         p.start()

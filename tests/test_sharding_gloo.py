@@ -78,7 +78,10 @@ def _worker(rank, world, port, out_dir):
 def test_two_rank_sharding_reproduces_single_process(tmp_path):
     from oracle import c_oracle
     c_oracle.build()
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:                               # a port that is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     S, C, anchors, boxes, preds, shapes = _inputs()
     full_y = c_oracle.encode_targets(boxes, (S, S), anchors, C)
