@@ -543,13 +543,16 @@ def run_b200(args):
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(2)
 
+        zc = [False, False]            # [decoder reads the page-locked predictions in place,
+                                       #  writer stores y_true straight into host memory]
+
         def e2e_encode():
             torch.cuda.set_device(local)
-            return engine.encode_targets(h_boxes.numpy(), (S, S), anchors, C, out=np_y)
+            return engine.encode_targets(h_boxes.numpy(), (S, S), anchors, C, out=np_y, zerocopy=zc[1])
 
         def e2e_decode():
             torch.cuda.set_device(local)
-            return engine.decode_nms(np_preds, hw_np, (S, S), anchors, C, want=WANT, **POST)
+            return engine.decode_nms(np_preds, hw_np, (S, S), anchors, C, want=WANT, zerocopy=zc[0], **POST)
 
         def e2e_concurrent():
             fe, fd = pool.submit(e2e_encode), pool.submit(e2e_decode)
@@ -564,17 +567,26 @@ def run_b200(args):
         # host: alone on its link a GPU moves both directions at once (concurrent wins); with
         # several GPUs saturating the host's memory interface the directions only get in each
         # other's way.  Time both on warm-up steps, all ranks together, and use the faster one.
+        # The same goes for HOW the predictions reach the decoder: staged through device memory
+        # in bulk copies, or read in place by the kernel (MGD_FLAG_HOST_ZEROCOPY: only the
+        # sectors the filter asks for cross the link -- fewer bytes through the host's memory
+        # interface, which is what several GPUs on one host run out of; finer-grained traffic on
+        # the link, which is what a single GPU runs out of).
         trial = {}
-        for name, fn in (("concurrent", e2e_concurrent), ("sequential", e2e_sequential)):
-            fn()
-            barrier()
-            tt = time.perf_counter()
-            fn()
-            fn()
-            torch.cuda.synchronize()
-            trial[name] = max_over_ranks(time.perf_counter() - tt) / 2
+        zc_modes = {"": (False, False), "+zerocopy": (True, False), "+zerocopy_both": (True, True)}
+        for suffix, mode in zc_modes.items():
+            zc[:] = mode
+            for name, fn in (("concurrent", e2e_concurrent), ("sequential", e2e_sequential)):
+                fn()
+                barrier()
+                tt = time.perf_counter()
+                fn()
+                fn()
+                torch.cuda.synchronize()
+                trial[name + suffix] = max_over_ranks(time.perf_counter() - tt) / 2
         issue = min(trial, key=trial.get)
-        e2e_step = e2e_concurrent if issue == "concurrent" else e2e_sequential
+        zc[:] = zc_modes[issue[issue.index("+"):] if "+" in issue else ""]
+        e2e_step = e2e_concurrent if issue.startswith("concurrent") else e2e_sequential
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -625,9 +637,13 @@ def run_b200(args):
                                 "after the other, whichever is faster) issued by ALL ranks at once behind "
                                 "a barrier, max over ranks: the contended rate of this host"},
                "issue": issue, "issue_trial_ms": {k: v * 1e3 for k, v in trial.items()},
-               "note": "pinned host buffers, host<->device copies inside; the two calls of a step are "
-                       "issued concurrently from two host threads or back to back, whichever the "
-                       "warm-up steps found faster on this host (see issue / issue_trial_ms)"}
+               "note": "pinned host buffers, host<->device traffic inside; the two calls of a step are "
+                       "issued concurrently from two host threads or back to back, and the decoder gets "
+                       "its predictions staged in bulk copies or reads them in place over the link "
+                       "(+zerocopy: MGD_FLAG_HOST_ZEROCOPY, then only the sectors its filter asks for "
+                       "cross, h2d_bytes_per_step stays the size of the tensors handed over; "
+                       "+zerocopy_both: the writer also stores y_true straight into host memory) -- whichever "
+                       "the warm-up steps found fastest on this host (see issue / issue_trial_ms)"}
         pool.shutdown()
         del h_preds, h_y, np_preds, np_y
 

@@ -53,6 +53,18 @@ enum { MGD_MEM_HOST = 0, MGD_MEM_DEVICE = 1 };
 enum {
     MGD_FLAG_SYNC = 1,             /* synchronise `stream` before returning and
                                       report deferred device-side errors          */
+    MGD_FLAG_HOST_ZEROCOPY = 4,    /* MGD_MEM_HOST calls on page-locked tensors: the
+                                      kernels access the big host tensor in place over
+                                      the link instead of staging it through device
+                                      memory -- mgd_decode_nms reads only the sectors
+                                      of the predictions its filter asks for (about a
+                                      third of the bytes of a trained-looking head; a
+                                      dense head is ~30 % slower this way),
+                                      mgd_encode_targets writes y_true straight into
+                                      host memory.  Pays off where the host's memory
+                                      interface, not the link, is the limit (several
+                                      GPUs on one host).  Pageable tensors ignore it.
+                                      MGD_HOST_ZEROCOPY (env, bits 0 / 1) forces it on.  */
     MGD_FLAG_TF_COMPAT = 2         /* mgd_encode_targets: the semantics of the
                                       reference's TensorFlow encoder
                                       tf_preprocess_true_boxes (generators.py:

@@ -19,6 +19,7 @@ MGD_MAX_ANCHORS_PER_LAYER = 8
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_SYNC = 1
 FLAG_TF_COMPAT = 2
+FLAG_HOST_ZEROCOPY = 4
 NMS_IOU, NMS_DIOU, NMS_SOFT, NMS_WBF = 0, 1, 2, 3
 IOU_CORNER, IOU_CENTRE = 0, 1
 BOXES_I32, BOXES_F64 = 0, 1

@@ -1109,7 +1109,7 @@ int mgd_encode_targets(const mgd_head_config* cfg, const float* boxes, int batch
     CUDA_TRY(cudaStreamWaitEvent(ss[1], ev[0], 0));
     int step = host_chunk(g, batch);
     float* z_y[MGD_MAX_LAYERS];
-    bool zero_copy = (zerocopy_mode() & 2) != 0;
+    bool zero_copy = (zerocopy_mode() & 2) != 0 || (flags & MGD_FLAG_HOST_ZEROCOPY) != 0;
     for (int l = 0; l < g.L && zero_copy; ++l) {
         z_y[l] = mapped_alias(y_true[l], (size_t)batch * g.gh[l] * g.gw[l] * g.D[l] * 4);
         zero_copy = z_y[l] != nullptr;
@@ -1273,7 +1273,7 @@ int mgd_decode_nms(const mgd_head_config* cfg, const mgd_post_config* post,
     int step = host_chunk(g, batch);
     // pinned predictions: the decode kernel can read them in place
     const float* z_pred[MGD_MAX_LAYERS];
-    bool zero_copy = (zerocopy_mode() & 1) != 0;
+    bool zero_copy = (zerocopy_mode() & 1) != 0 || (flags & MGD_FLAG_HOST_ZEROCOPY) != 0;
     for (int l = 0; l < g.L && zero_copy; ++l) {
         z_pred[l] = mapped_alias(preds[l], (size_t)batch * g.gh[l] * g.gw[l] * g.D[l] * 4);
         zero_copy = z_pred[l] != nullptr;

@@ -67,7 +67,7 @@ def post_config(max_boxes=100, confidence=0.1, nms_threshold=0.5, nms_method="di
 # ------------------------------------------------------------------------------
 
 def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=None,
-                   out=None, sync=True, return_stats=False, semantics="numpy"):
+                   out=None, sync=True, return_stats=False, semantics="numpy", zerocopy=False):
     """Multi-grid y_true encoder.  ``semantics="numpy"``: the reference's
     ``preprocess_true_boxes``; ``"tf_compat"``: its TensorFlow encoder
     ``tf_preprocess_true_boxes`` (MGD_FLAG_TF_COMPAT, include/mgd.h).
@@ -76,7 +76,8 @@ def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=No
     Returns a list of L arrays/tensors (B, Gh, Gw, 5+A+C) float32 in the same
     memory space.  ``sync=False`` (device tensors only) returns right after the
     kernels are enqueued on the current stream; class-range errors then surface
-    at the next ``poll_status``.
+    at the next ``poll_status``.  ``zerocopy=True`` (host arrays in page-locked memory): the
+    writer stores y_true straight into host memory (MGD_FLAG_HOST_ZEROCOPY).
     """
     lib = _lib.load()
     if semantics not in ("numpy", "tf_compat"):
@@ -115,7 +116,7 @@ def encode_targets(true_boxes, input_shape, anchors, num_classes, grid_shapes=No
         ptrs = _lib.ptr_array([o.ctypes.data for o in out])
         rc = lib.mgd_encode_targets(ctypes.byref(cfg), ctypes.c_void_p(boxes.ctypes.data), B, N,
                                     ptrs, _lib.MEM_HOST, _current_device(), None,
-                                    _lib.FLAG_SYNC | mode, stats)
+                                    _lib.FLAG_SYNC | mode | (_lib.FLAG_HOST_ZEROCOPY if zerocopy else 0), stats)
     _lib.raise_for_status(rc)
     if return_stats:
         return out, {"n_valid_boxes": int(stats[0]), "n_skipped_writes": int(stats[1]),
@@ -156,7 +157,8 @@ def _check_out(given, spec, B, device):
 def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_boxes=100,
                confidence=0.1, nms_threshold=0.5, nms_method="diou", per_class=False,
                use_softmax=True, rescore_confidence=True, sync=True, return_stats=False,
-               want=("boxes_xywh", "boxes_xyxy", "scores", "classes", "index"), out=None):
+               want=("boxes_xywh", "boxes_xyxy", "scores", "classes", "index"), out=None,
+               zerocopy=False):
     """Batched decode -> threshold -> NMS -> top-k (B independent reference calls).
 
     preds: list of L (B, Gh, Gw, 5+A+C) float32 NumPy arrays or torch CUDA tensors.
@@ -164,6 +166,8 @@ def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_
     out: (torch path) dict of preallocated contiguous CUDA tensors to write into -- 'counts'
     (B,) int32 plus any of ``want`` with the shapes / dtypes below; tensors taken from a
     ``sharding.DetectionExchange`` are mirrored to every rank by the kernels.
+    zerocopy=True (NumPy predictions in page-locked memory): the decoder reads them in place
+    over the link, only the sectors its filter asks for (MGD_FLAG_HOST_ZEROCOPY).
     Returns a dict of padded arrays/tensors + 'counts' (B,).
     """
     lib = _lib.load()
@@ -232,7 +236,7 @@ def decode_nms(preds, image_shapes, model_image_size, anchors, num_classes, max_
             ctypes.c_void_p(hw.ctypes.data) if hw is not None else None,
             addr("boxes_xywh"), addr("boxes_xyxy"), addr("scores"), addr("classes"),
             addr("index"), addr("counts"), _lib.MEM_HOST, _current_device(), None,
-            _lib.FLAG_SYNC, stats)
+            _lib.FLAG_SYNC | (_lib.FLAG_HOST_ZEROCOPY if zerocopy else 0), stats)
     _lib.raise_for_status(rc)
     if not sync:
         return out

@@ -164,3 +164,30 @@ def test_device_calls_are_cuda_graph_capturable():
     torch.cuda.synchronize()
     assert all(torch.equal(out[k], ref[k]) for k in KEYS)
     assert all(torch.equal(a, b) for a, b in zip(y_out, y_ref))
+
+
+def test_host_zerocopy_flag_gives_the_staged_result():
+    """MGD_FLAG_HOST_ZEROCOPY: page-locked host tensors accessed in place by the kernels (the
+    decoder reads only the sectors it asks for, the writer stores y_true over the link) -- same
+    bits as the staged path; pageable arrays silently take the staged path."""
+    import torch
+    from multigriddet_b200 import _lib, engine, synth
+    B = 7
+    anchors, preds, shapes = _inputs(B, seed=12)
+    pinned = [_lib.pinned.empty(tuple(p.shape), np.float32) for p in preds]
+    for dst, p in zip(pinned, preds):
+        dst[...] = p.cpu().numpy()
+    ref = engine.decode_nms(pinned, shapes, (S, S), anchors, C, **KW)
+    got = engine.decode_nms(pinned, shapes, (S, S), anchors, C, zerocopy=True, **KW)
+    pageable = [np.array(p) for p in pinned]
+    got_pageable = engine.decode_nms(pageable, shapes, (S, S), anchors, C, zerocopy=True, **KW)
+    for k in KEYS:
+        assert np.array_equal(got[k], ref[k]), k
+        assert np.array_equal(got_pageable[k], ref[k]), k
+    boxes = synth.synth_boxes(6, B, N, S, C)
+    y_ref = engine.encode_targets(boxes, (S, S), anchors, C)
+    y_out = [_lib.pinned.empty(y.shape, np.float32) for y in y_ref]
+    for y in y_out:
+        y[...] = -7.0
+    engine.encode_targets(boxes, (S, S), anchors, C, out=y_out, zerocopy=True)
+    assert all(np.array_equal(a, b) for a, b in zip(y_out, y_ref))
