@@ -432,6 +432,10 @@ MGD_API int mgd_host_free(void *ptr);
  *            order (exchanged by the host: torch.distributed.all_gather, MPI, a file ...),
  *            and maps the peers' buffers; world_size == 1 needs no connect
  *   buffer   this rank's buffer (device pointer, zero-initialised)
+ *   destroy  unmaps the peers and frees this rank's buffer after synchronising the device;
+ *            the ranks must agree that no mirrored call is in flight any more (a barrier of
+ *            the host-side job) before any of them destroys its end
+ * One thread per exchange at a time: the calls on it are ordered by a per-exchange counter.
  */
 #define MGD_IPC_HANDLE_BYTES 64
 typedef struct mgd_exchange mgd_exchange;
