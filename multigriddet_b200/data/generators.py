@@ -59,10 +59,10 @@ def tf_preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, mult
     NOT what ``preprocess_true_boxes`` computes: exact box centres,
     unrounded IoL with the Keras epsilon, every in-bounds cell of the 3x3 block written,
     the highest box index wins a contested cell (CPU ``tensor_scatter_nd_update`` order),
-    xy stored as ``[-dcol + frac(cy), -drow + frac(cx)]``, no class-range error.  Parity
-    against real TensorFlow is UNPINNED: TF is not installed in this image and no
-    reference test pins more than one symmetric box; the oracle is a line-by-line
-    restatement of the TF ops (see tests/test_tf_compat.py).
+    xy stored as ``[-dcol + frac(cy), -drow + frac(cx)]``, no class-range error.  TensorFlow
+    is not installed in this image; the semantics are pinned against the reference function's
+    own source executed with a NumPy stand-in answering its ``tf.*`` calls (the test suite's
+    ``oracle/tf_shim.py``; fixtures ``tests/golden/tfencode_*.npz``), logarithms to 1e-5.
     ``semantics="numpy"`` routes to the NumPy encoder's self-consistent rules instead.
 
     A ctypes library cannot be traced into a TF graph: inside ``dataset.map`` call

@@ -81,6 +81,57 @@ def encode_cases():
                         **{f"c{i}_{key}": v for i, k in enumerate(ka) for key, v in sparse(k[2]).items()})
 
 
+def tf_adversarial_boxes(S, C):
+    """Hand-made inputs for the points where the TF encoder differs from the NumPy one or where
+    its scatter is order-dependent: two boxes with the same centre (the later one must win every
+    shared cell), boxes whose 3x3 block leaves the grid on each side, centres exactly on a cell
+    boundary, zero-area and inverted rows between valid ones, class ids outside [0, C)."""
+    rows = [
+        [100, 200, 180, 260, 3], [100, 200, 180, 260, 7],            # identical boxes, classes differ
+        [96, 196, 184, 264, 1],                                      # same centre, other size (other anchor?)
+        [0, 0, 40, 30, 2], [S - 30, S - 44, S, S, 4],                # corners of the image
+        [0, S / 2 - 20, 24, S / 2 + 20, 5], [S / 2 - 9, 0, S / 2 + 9, 20, 6],
+        [296, 296, 312, 312, 0],                                     # centre 304 = a stride-8/16/32 boundary
+        [50, 50, 50, 90, 1], [300, 300, 280, 320, 1],                # zero area, inverted
+        [200, 400, 330, 560, C], [210, 410, 320, 550, -1],           # class ids out of range
+        [411.5, 97.25, 468.75, 171.5, C - 1],                        # fractional corners
+        [0, 0, 0, 0, 0],
+        [5, 5, S - 5, S - 5, 0],                                     # almost the whole image
+    ]
+    return np.array([rows], dtype=np.float32)
+
+
+def tf_encode_cases():
+    """The reference's TensorFlow encoder (generators.py:2696-3390) run over oracle/tf_shim.py."""
+    enc = ref_loader.load_tf_encoder()
+    cases = [
+        # name, S, C, N, B, layout, corners, padding, anchor set
+        ("coco608", 608, 80, 100, 2, "uniform", "int", "tail", "coco"),
+        ("coco608_frac", 608, 80, 100, 2, "mosaic", "frac", "interleaved", "coco"),
+        ("voc416", 416, 20, 30, 3, "uniform", "frac", "tail", "coco"),
+        ("oneclass352", 352, 1, 40, 2, "mosaic", "frac", "tail", "small_first"),
+    ]
+    for i, (name, S, C, N, B, layout, corners, padding, aset) in enumerate(cases):
+        anchors = (synth.coco_anchors(np.float32) if aset == "coco"
+                   else [np.array(a, dtype=np.float32) for a in SMALL_FIRST])
+        boxes = synth.synth_boxes(500 + i, B, N, S, C, corners=corners, layout=layout,
+                                  padding=padding, anchors=anchors)
+        grids = [(S // 32, S // 32), (S // 16, S // 16), (S // 8, S // 8)]
+        y = enc(boxes.copy(), (S, S), anchors, C, grids)
+        np.savez_compressed(os.path.join(OUT, f"tfencode_{name}.npz"), boxes=boxes,
+                            anchors=np.stack(anchors).astype(np.float64),
+                            anchors_f64=np.array(False), S=S, C=C, **sparse(y))
+        print("tf encode", name, [int(a[..., 4].sum()) for a in y])
+    S, C = 608, 80
+    anchors = synth.coco_anchors(np.float32)
+    boxes = tf_adversarial_boxes(S, C)
+    y = enc(boxes.copy(), (S, S), anchors, C, [(19, 19), (38, 38), (76, 76)])
+    np.savez_compressed(os.path.join(OUT, "tfencode_adversarial608.npz"), boxes=boxes,
+                        anchors=np.stack(anchors).astype(np.float64), anchors_f64=np.array(False),
+                        S=S, C=C, **sparse(y))
+    print("tf encode adversarial", [int(a[..., 4].sum()) for a in y])
+
+
 def decode_cases():
     post = ref_loader.load_postprocess()
     enc = ref_loader.load_encoder()
@@ -384,9 +435,11 @@ if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found at " + ref_loader.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
-    only = sys.argv[1:] or ["encode", "decode", "nms", "metrics", "boxes", "perclass", "coco608"]
+    only = sys.argv[1:] or ["encode", "tfencode", "decode", "nms", "metrics", "boxes", "perclass", "coco608"]
     if "encode" in only:
         encode_cases()
+    if "tfencode" in only:
+        tf_encode_cases()
     if "decode" in only:
         decode_cases()
     if "nms" in only:

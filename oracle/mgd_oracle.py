@@ -147,9 +147,14 @@ def encode_targets_tf_compat(true_boxes, input_shape, anchors, num_classes, grid
     """The TensorFlow encoder's semantics -- generators.py:2696-3390
     (``tf_preprocess_true_boxes``, the reference's default training path).
 
-    PARITY UNPINNED: TensorFlow is not installed in this image and no reference test
-    pins this function beyond one symmetric box (tests/test_9cell_alignment.py), so this
-    is a line-by-line restatement of the TF ops in float32 NumPy, not a checked one.
+    PINNED AGAINST THE REFERENCE'S OWN CODE OVER A TF-OP STAND-IN: TensorFlow is not installed
+    in this image, so the reference function cannot run as it is; its source is executed
+    statement by statement with ``oracle/tf_shim.py`` answering the ``tf.*`` calls in NumPy
+    (``ref_loader.load_tf_encoder``), and this restatement equals it bit for bit on random and
+    adversarial inputs (tests/test_oracle_vs_reference.py; fixtures tests/golden/tfencode_*.npz).
+    What stays assumed is the semantics of the primitive ops listed in tf_shim's header
+    (notably: duplicate scatter updates applied in order, TensorFlow's CPU behaviour, and the
+    float32 log -- Eigen's in TensorFlow -- which is why tw/th are only claimed to 1e-5).
     It differs from the NumPy encoder above in every one of these points:
 
     * centre = (x1y1 + x2y2) / 2.0, no floor (:2730); valid <=> w*h > 0 (:2757);

@@ -84,6 +84,40 @@ def load_staged_encoder():
     return preprocess_true_boxes
 
 
+def load_tf_encoder():
+    """The reference's TensorFlow encoder ``tf_preprocess_true_boxes`` (generators.py:2696-3390,
+    the default training path) executed over ``oracle/tf_shim.py``: the function's own source,
+    cut out with ``ast`` where it lies, with a NumPy stand-in answering its ``tf.*`` calls
+    (TensorFlow is not installed here).  Returns ``f(true_boxes, input_shape, anchors,
+    num_classes, grid_shapes) -> list of float32 arrays``."""
+    if "tf_enc" in _cache:
+        return _cache["tf_enc"]
+    import typing
+    import numpy as np
+    from . import tf_shim
+    path = os.path.join(REFERENCE_ROOT, "multigriddet", "data", "generators.py")
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    picked = [n for n in tree.body
+              if isinstance(n, ast.FunctionDef) and n.name == "tf_preprocess_true_boxes"]
+    if len(picked) != 1:
+        raise RuntimeError("tf_preprocess_true_boxes not found in " + path)
+    scope = {"tf": tf_shim, "np": np, "Tuple": typing.Tuple, "List": typing.List,
+             "Optional": typing.Optional, "Dict": typing.Dict, "Union": typing.Union}
+    exec(compile(ast.Module(body=picked, type_ignores=[]), path, "exec"), scope)
+    raw = scope["tf_preprocess_true_boxes"]
+
+    def tf_preprocess_true_boxes(true_boxes, input_shape, anchors, num_classes, grid_shapes):
+        tb = np.asarray(true_boxes, dtype=np.float32)
+        anc = [np.asarray(a, dtype=np.float32) for a in anchors]
+        out = raw(tb, tuple(int(v) for v in input_shape), anc, int(num_classes), False,
+                  [tuple(int(v) for v in g) for g in grid_shapes])
+        return [np.asarray(y, dtype=np.float32) for y in out]
+
+    _cache["tf_enc"] = tf_preprocess_true_boxes
+    return tf_preprocess_true_boxes
+
+
 _ENCODER_NAMES = ("get_anchor_mask", "iol_common_center", "best_fit_and_layer",
                   "preprocess_true_boxes")
 _cache: dict = {}

@@ -16,6 +16,27 @@ from multigriddet_b200.postprocess import (ClusterNMS, DIoUNMS, MultiGridDecoder
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("path", G.files("tfencode"))
+def test_tf_compat_encode_against_reference_golden(path):
+    """MGD_FLAG_TF_COMPAT against the outputs of the reference's own TensorFlow encoder
+    (generators.py:2696-3390, run over oracle/tf_shim.py when the fixtures were made); through
+    the C ABI with host arrays and with device tensors.  Logarithms to 1e-5 (TensorFlow's log
+    is Eigen's; the fixture's is glibc's logf)."""
+    import torch
+    from multigriddet_b200.data import tf_preprocess_true_boxes
+    z = np.load(path)
+    anchors = G.anchors_of(z)
+    S, C = int(z["S"]), int(z["C"])
+    ref = G.dense_y_true(z)
+    got = engine.encode_targets(z["boxes"], (S, S), anchors, C, semantics="tf_compat")
+    G.assert_encode_matches(got, ref, exact_floats=False)
+    got = engine.encode_targets(torch.from_numpy(z["boxes"]).cuda(), (S, S), anchors, C, semantics="tf_compat")
+    G.assert_encode_matches([g.cpu().numpy() for g in got], ref, exact_floats=False)
+    got = tf_preprocess_true_boxes(z["boxes"], (S, S), anchors, C, False,
+                                   [(S // 32,) * 2, (S // 16,) * 2, (S // 8,) * 2])
+    G.assert_encode_matches([np.asarray(g) for g in got], ref, exact_floats=False)
+
+
 @pytest.mark.parametrize("path", G.files("encode"))
 def test_encode_against_reference_golden(path):
     z = np.load(path)

@@ -156,3 +156,15 @@ def test_coco608_oracle_matches_reference_golden(c_oracle):
                 assert np.array_equal(cc["scores"][b, :n], ref_s)
                 assert np.array_equal(cc["classes"][b, :n], z[f"k{k}_b{b}_{tag}classes"])
                 assert np.array_equal(cc["boxes_xyxy"][b, :n], z[f"k{k}_b{b}_{tag}xyxy"].reshape(-1, 4))
+
+
+@pytest.mark.parametrize("path", G.files("tfencode"))
+def test_tf_encoder_oracle_matches_reference_golden(path):
+    """tests/golden/tfencode_*.npz: outputs of the reference's own tf_preprocess_true_boxes
+    (generators.py:2696-3390) executed over oracle/tf_shim.py in the build container."""
+    z = np.load(path)
+    anchors = G.anchors_of(z)
+    S, C = int(z["S"]), int(z["C"])
+    grids = [(S // 32,) * 2, (S // 16,) * 2, (S // 8,) * 2]
+    got = O.encode_targets_tf_compat(z["boxes"], (S, S), anchors, C, grids)
+    G.assert_encode_matches(got, G.dense_y_true(z), exact_floats=G.numpy_pinned())

@@ -103,3 +103,53 @@ def test_per_class_nms_equals_reference_per_partition(seed):
                 assert np.array_equal(scores[keep[:mx]], s)
                 assert np.array_equal(boxes[keep[:mx]], b)
                 assert np.array_equal(classes[keep[:mx]], c)
+
+
+@pytest.mark.parametrize("S,C,N,B,layout,corners,padding,aset,seed", [
+    (608, 80, 100, 3, "uniform", "int", "tail", "coco", 41),
+    (608, 80, 100, 2, "mosaic", "frac", "interleaved", "coco", 42),
+    (416, 20, 30, 4, "uniform", "frac", "tail", "coco", 43),
+    (352, 1, 40, 2, "mosaic", "frac", "tail", "small_first", 44),
+    (320, 80, 300, 2, "mosaic", "frac", "tail", "coco", 45),
+    (672, 80, 400, 1, "mosaic", "int", "interleaved", "coco", 46),
+])
+def test_tf_encoder_restatement_equals_reference_code_over_tf_shim(S, C, N, B, layout, corners, padding,
+                                                                   aset, seed):
+    """``O.encode_targets_tf_compat`` against the reference's OWN TensorFlow encoder
+    (generators.py:2696-3390), its source executed statement by statement with oracle/tf_shim.py
+    answering the tf.* calls in NumPy (TensorFlow is not installed).  Bit for bit, logarithms
+    included: both sides call the same float32 log here."""
+    from oracle.gen_golden import SMALL_FIRST
+    enc = ref_loader.load_tf_encoder()
+    anchors = (synth.coco_anchors(np.float32) if aset == "coco"
+               else [np.array(a, dtype=np.float32) for a in SMALL_FIRST])
+    boxes = synth.synth_boxes(seed, B, N, S, C, corners=corners, layout=layout, padding=padding,
+                              anchors=anchors)
+    grids = [(S // 32,) * 2, (S // 16,) * 2, (S // 8,) * 2]
+    ref = enc(boxes.copy(), (S, S), anchors, C, grids)
+    got = O.encode_targets_tf_compat(boxes, (S, S), anchors, C, grids)
+    assert sum(int(r[..., 4].sum()) for r in ref) > 0
+    for g, r in zip(got, ref):
+        assert g.dtype == np.float32 and np.array_equal(g, r)
+
+
+def test_tf_encoder_restatement_on_the_adversarial_inputs():
+    """Same, on the hand-made inputs of oracle/gen_golden.tf_adversarial_boxes: duplicate
+    centres (scatter order), blocks leaving the grid, cell-boundary centres, zero-area rows,
+    class ids outside [0, C)."""
+    from oracle.gen_golden import tf_adversarial_boxes
+    enc = ref_loader.load_tf_encoder()
+    S, C = 608, 80
+    anchors = synth.coco_anchors(np.float32)
+    grids = [(19, 19), (38, 38), (76, 76)]
+    boxes = tf_adversarial_boxes(S, C)
+    ref = enc(boxes.copy(), (S, S), anchors, C, grids)
+    got = O.encode_targets_tf_compat(boxes, (S, S), anchors, C, grids)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+    # boxes 0, 1 (identical) and 2 share their centre and their layer: the LAST one (class 1) owns
+    # every cell of the block, classes 3 and 7 appear nowhere; the ids outside [0, C) light no
+    # class channel at all
+    assert all(r[0][..., 5 + 3 + 3].sum() == 0 and r[0][..., 5 + 3 + 7].sum() == 0 for r in ref)
+    assert sum(float(r[0][..., 5 + 3 + 1].sum()) for r in ref) >= 9
+    assert any(np.any((r[0][..., 4] > 0) & (r[0][..., 8:].sum(-1) == 0)) for r in ref)

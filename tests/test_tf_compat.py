@@ -1,10 +1,11 @@
 """The TensorFlow encoder's semantics (MGD_FLAG_TF_COMPAT): reference
-multigriddet/data/generators.py:2696-3390.  PARITY UNPINNED against real TensorFlow
-(not installed here; the reference's own tests, tests/test_9cell_alignment.py and
-tests/test_target_consistency.py, use one symmetric box).  The CPU tests below check the
-oracle restatement against hand-derived values for exactly the points where the TF
-encoder differs from the NumPy one; the GPU tests check the CUDA path
-against that oracle bit for bit.
+multigriddet/data/generators.py:2696-3390.  TensorFlow is not installed here; the pin is the
+reference function's own source executed over a NumPy stand-in for its tf.* ops
+(oracle/tf_shim.py: tests/test_oracle_vs_reference.py live, tests/golden/tfencode_*.npz as
+fixtures).  The CPU tests below additionally check the oracle restatement against hand-derived
+values for exactly the points where the TF encoder differs from the NumPy one
+and the one input the reference's own tests pin; the GPU tests check the CUDA path against
+that oracle bit for bit.
 """
 import numpy as np
 import pytest
