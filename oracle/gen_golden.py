@@ -132,6 +132,82 @@ def tf_encode_cases():
     print("tf encode adversarial", [int(a[..., 4].sum()) for a in y])
 
 
+def ignoremask_inputs(seed, B, N, S, C, noise=0.05):
+    """Targets from the reference's NumPy encoder, planted head outputs with noisy boxes
+    (IoUs spread over (0, 1)); float16-rounded so the fixture stays small."""
+    enc = ref_loader.load_encoder()
+    anchors = synth.coco_anchors(np.float32)
+    boxes = synth.synth_boxes(seed, B, N, S, C, anchors=anchors)
+    y = enc(boxes.copy(), (S, S), anchors, C, False)
+    preds = [p.numpy() for p in synth.planted_head_outputs([torch.from_numpy(a) for a in y], 3, seed)]
+    rng = np.random.default_rng(seed)
+    for p in preds:
+        p[..., 0:4] += rng.normal(0, noise, p[..., 0:4].shape).astype(np.float32)
+    preds = [p.astype(np.float16).astype(np.float32) for p in preds]
+    return anchors, y, preds
+
+
+def ignoremask_cases():
+    """The reference's loss-side ignore mask (losses/multigrid_loss.py:445-703) run over
+    oracle/tf_shim.py: ``MultiGridLoss._compute_ignore_mask`` per layer, called like :285-320."""
+    f = ref_loader.load_tf_ignore_mask()
+    store = {}
+    cases = [(600, 3, 10, 160, 4), (601, 2, 40, 320, 20)]
+    store["n_cases"] = np.array(len(cases))
+    for i, (seed, B, N, S, C) in enumerate(cases):
+        anchors, y, preds = ignoremask_inputs(seed, B, N, S, C)
+        store[f"c{i}_meta"] = np.array([seed, B, N, S, C])
+        store[f"c{i}_anchors"] = np.stack(anchors).astype(np.float64)
+        for key, v in sparse(y).items():
+            store[f"c{i}_y_{key}"] = v
+        n_ignored = 0
+        for l in range(3):
+            store[f"c{i}_pred{l}"] = preds[l].astype(np.float16)
+            ig, asg, mx = f(preds[l], y[l], anchors[l], (S, S), 0.5)
+            store[f"c{i}_ignore{l}"] = np.packbits(ig.astype(np.uint8).reshape(-1))
+            store[f"c{i}_assigned{l}"] = asg
+            store[f"c{i}_maxiou{l}"] = mx
+            n_ignored += int(ig.sum())
+        print("ignore mask case", i, "ignored cells", n_ignored)
+    np.savez_compressed(os.path.join(OUT, "ignoremask_cases.npz"), **store)
+
+
+def tfboxes_inputs(seed, n_cases, cap=12):
+    """Random raw annotation boxes, source image sizes, multi-scale shapes, flips, capacity
+    factors for the tf.data box pre-step."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for t in range(n_cases):
+        src_h, src_w = int(rng.integers(120, 1600)), int(rng.integers(120, 1600))
+        S = int(rng.choice([320, 416, 608]))
+        n = int(rng.integers(0, cap + 1))
+        x1 = rng.uniform(0, src_w - 2, n)
+        y1 = rng.uniform(0, src_h - 2, n)
+        x2 = np.minimum(x1 + rng.uniform(1, src_w, n), src_w)
+        y2 = np.minimum(y1 + rng.uniform(1, src_h, n), src_h)
+        boxes = np.zeros((cap, 5), np.float32)
+        boxes[:n] = np.stack([x1, y1, x2, y2, rng.integers(0, 80, n)], 1)
+        if t % 4 == 0:
+            boxes[:n, :4] = np.round(boxes[:n, :4])              # integer annotations, the common case
+        ms = (0, 0) if t % 3 else (int(rng.choice([320, 352, 416, 480, 608, 672])),) * 2
+        cases.append((boxes, n, (src_h, src_w), S, ms, bool(rng.integers(0, 2)), int(rng.choice([1, 2, 4, 8]))))
+    return cases
+
+
+def tfboxes_cases():
+    """The box side of the reference's tf.data pipeline (generators.py:167-256, 1859-2034) run
+    over oracle/tf_shim.py."""
+    f = ref_loader.load_tf_box_prestep()
+    cases = tfboxes_inputs(700, 48)
+    store = {"n_cases": np.array(len(cases)), "cap": np.array(12)}
+    for i, (boxes, n, src, S, ms, flip, exp) in enumerate(cases):
+        store[f"c{i}_boxes"] = boxes
+        store[f"c{i}_meta"] = np.array([n, src[0], src[1], S, ms[0], ms[1], int(flip), exp])
+        store[f"c{i}_out"] = f(boxes[:n], src, (S, S), 12, exp, ms if ms[0] else None, flip)
+    np.savez_compressed(os.path.join(OUT, "tfboxes_cases.npz"), **store)
+    print("tf.data box cases", len(cases))
+
+
 def decode_cases():
     post = ref_loader.load_postprocess()
     enc = ref_loader.load_encoder()
@@ -435,11 +511,15 @@ if __name__ == "__main__":
     if not ref_loader.available():
         raise SystemExit("reference tree not found at " + ref_loader.REFERENCE_ROOT)
     os.makedirs(OUT, exist_ok=True)
-    only = sys.argv[1:] or ["encode", "tfencode", "decode", "nms", "metrics", "boxes", "perclass", "coco608"]
+    only = sys.argv[1:] or ["encode", "tfencode", "ignoremask", "tfboxes", "decode", "nms", "metrics", "boxes", "perclass", "coco608"]
     if "encode" in only:
         encode_cases()
     if "tfencode" in only:
         tf_encode_cases()
+    if "ignoremask" in only:
+        ignoremask_cases()
+    if "tfboxes" in only:
+        tfboxes_cases()
     if "decode" in only:
         decode_cases()
     if "nms" in only:

@@ -118,6 +118,123 @@ def load_tf_encoder():
     return tf_preprocess_true_boxes
 
 
+def load_tf_ignore_mask():
+    """The reference's loss-side ignore mask -- ``MultiGridLoss._compute_ignore_mask`` with
+    ``_compute_iou_batch`` (losses/multigrid_loss.py:445-703) -- executed over
+    ``oracle/tf_shim.py``: the two methods' own source, cut out of the class with ``ast`` and
+    bound to a bare object that carries the three attributes they read (``input_shape``,
+    ``ignore_thresh``, ``eps`` = ``K.epsilon()``, :122-123, :173).  The returned function takes
+    one layer the way the caller does (:285-320): ``f(y_pred_layer, y_true_layer, anchors_layer,
+    input_shape, ignore_thresh) -> (ignore_mask, assigned_anchor_iou, max_iou_map)``."""
+    if "tf_ignore" in _cache:
+        return _cache["tf_ignore"]
+    import typing
+    import numpy as np
+    from . import tf_shim
+    path = os.path.join(REFERENCE_ROOT, "multigriddet", "losses", "multigrid_loss.py")
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    wanted = ("_compute_iou_batch", "_compute_ignore_mask")
+    picked = [m for c in tree.body if isinstance(c, ast.ClassDef) and c.name == "MultiGridLoss"
+              for m in c.body if isinstance(m, ast.FunctionDef) and m.name in wanted]
+    if len(picked) != len(wanted):
+        raise RuntimeError("ignore-mask methods not found in " + path)
+    holder = ast.ClassDef(name="_RefLoss", bases=[], keywords=[], body=picked, decorator_list=[])
+    if "type_params" in ast.ClassDef._fields:
+        holder.type_params = []
+    mod = ast.fix_missing_locations(ast.Module(body=[holder], type_ignores=[]))
+    scope = {"tf": tf_shim, "K": tf_shim.keras.backend, "np": np, "Tuple": typing.Tuple,
+             "List": typing.List, "Optional": typing.Optional}
+    exec(compile(mod, path, "exec"), scope)
+    cls = scope["_RefLoss"]
+
+    def ignore_mask_layer(y_pred, y_true, anchors, input_shape, ignore_thresh=0.5):
+        y_pred = np.asarray(y_pred, dtype=np.float32)
+        y_true = np.asarray(y_true, dtype=np.float32)
+        obj = cls()
+        obj.input_shape = tuple(int(v) for v in input_shape)
+        obj.ignore_thresh = ignore_thresh
+        obj.eps = tf_shim.keras.backend.epsilon()
+        object_mask = (y_true[..., 4:5] > 0.5).astype(np.float32)            # :305
+        grid_shape = (np.int32(y_pred.shape[1]), np.int32(y_pred.shape[2]))  # :308
+        out = obj._compute_ignore_mask(y_pred[..., 0:2], y_pred[..., 2:4], y_true[..., 0:2],
+                                       y_true[..., 2:4], np.asarray(anchors), object_mask, y_true,
+                                       grid_shape)
+        return tuple(np.asarray(o, dtype=np.float32) for o in out)
+
+    _cache["tf_ignore"] = ignore_mask_layer
+    return ignore_mask_layer
+
+
+def load_tf_box_prestep():
+    """The box side of the reference's tf.data pipeline (``build_tf_dataset``) executed over
+    ``oracle/tf_shim.py``: ``tf_letterbox_resize`` (:167-209), ``tf_random_horizontal_flip``
+    (:227-256) and the two closures ``_preprocess_image_and_boxes`` (:1859-1958) and
+    ``_expand_box_capacity`` (:1983-2034), each function's own source cut out with ``ast``.
+    The closures' free variables (``self``, ``has_multiscale``, ``input_shape_list_tf``,
+    ``input_shape_base_tf``) are supplied per call; images are zero arrays of the right shape
+    (the box arithmetic only reads their shapes); ``self.augment`` is False for the transform
+    (the crop / colour / rotate augmentations between the two box steps are not on the path) and
+    the flip is called on its own with the coin forced; ``padded_batch`` (:1963-1976), a
+    tf.data method, is the zero-padding to ``max_boxes_per_image`` rows it documents.
+
+    Returns ``f(boxes (n, 5), src_hw, input_shape, max_boxes_per_image, expansion,
+    multiscale_shape=None, hflip=False) -> (max_boxes_per_image * expansion, 5) float32``."""
+    if "tf_boxes" in _cache:
+        return _cache["tf_boxes"]
+    import types as _types
+    import typing
+    import numpy as np
+    from . import tf_shim
+    path = os.path.join(REFERENCE_ROOT, "multigriddet", "data", "generators.py")
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    top = {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef)}
+    nested = {}                  # the closures of build_tf_dataset: the FIRST definitions in the file
+    for n in ast.walk(tree):     # (a later method defines closures of the same names)
+        if isinstance(n, ast.FunctionDef) and n.name in ("_preprocess_image_and_boxes", "_expand_box_capacity"):
+            if n.name not in nested or n.lineno < nested[n.name].lineno:
+                nested[n.name] = n
+    names = ("tf_letterbox_resize", "tf_random_horizontal_flip", "tf_normalize_image")
+    if any(k not in top for k in names) or len(nested) != 2:
+        raise RuntimeError("tf.data box functions not found in " + path)
+    body = [top[k] for k in names] + [nested["_preprocess_image_and_boxes"], nested["_expand_box_capacity"]]
+    scope = {"tf": tf_shim, "np": np, "Tuple": typing.Tuple, "List": typing.List,
+             "Optional": typing.Optional, "Dict": typing.Dict, "Union": typing.Union}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), scope)
+
+    def run(boxes, src_hw, input_shape, max_boxes_per_image, expansion=1, multiscale_shape=None,
+            hflip=False):
+        input_shape = tuple(int(v) for v in input_shape)
+        me = _types.SimpleNamespace(
+            input_shape=input_shape, augment=False, rescale_interval=10 if multiscale_shape else -1,
+            max_boxes_per_image=int(max_boxes_per_image),
+            enhance_augment="mosaic" if expansion in (4, 8) else None,
+            mosaic_prob=1.0 if expansion in (4, 8) else 0.0,
+            mixup_prob=1.0 if expansion in (2, 8) else 0.0)
+        scope["self"] = me
+        scope["has_multiscale"] = multiscale_shape is not None                      # :1849-1857
+        scope["input_shape_list_tf"] = (np.array([multiscale_shape], dtype=np.int32)
+                                        if multiscale_shape is not None else None)
+        scope["input_shape_base_tf"] = np.array(input_shape, dtype=np.int32)
+        tf_shim.random.forced[:] = [0] if multiscale_shape is not None else []       # the scale index drawn at :1868
+        image = np.zeros((int(src_hw[0]), int(src_hw[1]), 3), dtype=np.uint8)
+        bx = np.asarray(boxes, dtype=np.float32).reshape(-1, 5)
+        image_out, bx = scope["_preprocess_image_and_boxes"](image, bx, None)
+        tf_shim.random.forced[:] = [0.75 if hflip else 0.25]                        # the coin drawn at :241
+        _, bx = scope["tf_random_horizontal_flip"](image_out, bx)
+        bx = np.asarray(bx, dtype=np.float32)
+        if bx.shape[0] > me.max_boxes_per_image:
+            raise ValueError("padded_batch raises on a component longer than its padded shape")
+        dense = np.zeros((1, me.max_boxes_per_image, 5), dtype=np.float32)          # padded_batch :1963-1976
+        dense[0, :bx.shape[0]] = bx
+        _, expanded = scope["_expand_box_capacity"](np.zeros((1,) + input_shape + (3,), np.float32), dense)
+        return np.asarray(expanded, dtype=np.float32)[0]
+
+    _cache["tf_boxes"] = run
+    return run
+
+
 _ENCODER_NAMES = ("get_anchor_mask", "iol_common_center", "best_fit_and_layer",
                   "preprocess_true_boxes")
 _cache: dict = {}

@@ -6,7 +6,9 @@ own source, statement by statement, with every ``tf.*`` call answered by the Num
 below that implements the op's documented semantics on float32 / int32 / int64 / bool arrays:
 ``oracle/ref_loader.load_tf_encoder()`` cuts ``tf_preprocess_true_boxes`` out of
 ``multigriddet/data/generators.py`` (:2696-3390) with ``ast`` and executes it with this module
-bound to the name ``tf``.  The control flow, the op order, the indexing and the constants are
+bound to the name ``tf``; ``load_tf_ignore_mask()`` does the same with the two methods
+``MultiGridLoss._compute_iou_batch`` / ``_compute_ignore_mask``
+(``multigriddet/losses/multigrid_loss.py:445-703``; ``K`` = ``keras.backend`` below).  The control flow, the op order, the indexing and the constants are
 then the reference's; what is assumed is only what each primitive op does:
 
 * element-wise arithmetic / comparison in the operands' dtype (float32 stays float32; a
@@ -18,8 +20,10 @@ then the reference's; what is assumed is only what each primitive op does:
   the same position wins; TF documents the order as undefined in general and sequential on
   CPU), ``tf.math.unsorted_segment_sum`` sums by segment id, ``tf.one_hot`` yields a zero row
   for an index outside [0, depth);
-* ``tf.math.log`` on float32 is NumPy's float32 log (glibc ``logf`` with NumPy's AVX dispatch
-  off, tests/conftest.py) -- TensorFlow's is Eigen's, so logarithms are only claimed to 1e-5;
+* ``tf.math.log`` / ``tf.exp`` / ``tf.nn.tanh`` / ``tf.nn.sigmoid`` on float32 are NumPy's float32
+  functions (glibc's with NumPy's AVX dispatch off, tests/conftest.py; sigmoid = 1 / (1 + exp(-x)))
+  -- TensorFlow's are Eigen's, so values downstream of them are only claimed to 1e-5;
+* ``tf.map_fn`` applies the function to the elements in order and stacks the results;
 * ``tf.debugging.*`` and ``tf.print`` are no-ops, ``tf.function`` is the identity,
   ``tf.cond(pred, a, b)`` calls ``a()`` or ``b()``.
 
@@ -90,7 +94,11 @@ def squeeze(x, axis=None):
 
 
 def stack(values, axis=0):
-    return np.stack([_a(v) for v in values], axis=axis)
+    # TF converts Python scalars in the list to the dtype of the tensor elements
+    dts = [np.asarray(v).dtype for v in values if isinstance(v, (np.ndarray, np.generic))]
+    dt = dts[0] if dts else None
+    return np.stack([_a(v, dtype=dt) if not isinstance(v, (np.ndarray, np.generic)) else _a(v)
+                     for v in values], axis=axis)
 
 
 def concat(values, axis=0):
@@ -193,6 +201,33 @@ def tensor_scatter_nd_update(tensor, indices, updates):
     return out
 
 
+def exp(x):
+    return np.exp(_a(x))
+
+
+def reduce_sum(x, axis=None, keepdims=False):
+    x = _a(x)
+    return np.sum(x, axis=axis, keepdims=keepdims, dtype=x.dtype)
+
+
+def tensordot(a, b, axes):
+    a, b = _a(a), _a(b)
+    return np.tensordot(a, b, axes=axes).astype(np.result_type(a.dtype, b.dtype))
+
+
+def stop_gradient(x):
+    return x
+
+
+class TensorSpec:
+    def __init__(self, shape=None, dtype=None):
+        self.shape, self.dtype = shape, dtype
+
+
+def map_fn(fn, elems, fn_output_signature=None, **_kw):
+    return np.stack([_a(fn(e)) for e in _a(elems)], axis=0)
+
+
 def cond(pred, true_fn, false_fn):
     return true_fn() if np.asarray(pred).item() else false_fn()
 
@@ -216,18 +251,38 @@ class _Math:
 
 class _Debugging:
     @staticmethod
-    def assert_equal(*_a, **_k):
+    def _noop(*_a, **_k):
         return None
 
+    assert_equal = assert_shapes = assert_rank = assert_positive = assert_greater = _noop
+
+
+class _NN:
     @staticmethod
-    def assert_shapes(*_a, **_k):
-        return None
+    def tanh(x):
+        return np.tanh(_a(x))
+
+    @staticmethod
+    def sigmoid(x):
+        x = _a(x)
+        one = x.dtype.type(1)
+        return one / (one + np.exp(-x))
 
 
 class _Backend:
+    """tensorflow.keras.backend, as far as the loss code uses it"""
+
     @staticmethod
     def epsilon():
         return 1e-7
+
+    shape = staticmethod(shape)
+    maximum = staticmethod(maximum)
+    minimum = staticmethod(minimum)
+
+    @staticmethod
+    def cast(x, dtype):
+        return cast(x, np.dtype(dtype))
 
 
 class _Keras:
@@ -246,7 +301,42 @@ class _Compat:
     v1 = _V1()
 
 
+class _Image:
+    """Image-space ops: the box-side functions only ever look at the SHAPES of the images they
+    produce, so these return zero images of the documented output shape."""
+
+    @staticmethod
+    def resize(image, size, method="bilinear"):
+        image = _a(image)
+        return np.zeros((int(size[0]), int(size[1])) + image.shape[2:], dtype=np.float32)
+
+    @staticmethod
+    def pad_to_bounding_box(image, offset_height, offset_width, target_height, target_width):
+        image = _a(image)
+        return np.zeros((int(target_height), int(target_width)) + image.shape[2:], dtype=image.dtype)
+
+    @staticmethod
+    def flip_left_right(image):
+        return image
+
+
+class _Random:
+    """tf.random.uniform answers from a queue the test fills (``forced``): the reference draws
+    its coin / its scale index there, the tests decide them."""
+
+    def __init__(self):
+        self.forced = []
+
+    def uniform(self, shape, minval=0, maxval=None, dtype=np.float32, **_k):
+        if not self.forced:
+            raise RuntimeError("tf_shim.random.uniform called with no forced value queued")
+        return np.asarray(self.forced.pop(0), dtype=dtype)
+
+
 math = _Math()
+nn = _NN()
+image = _Image()
+random = _Random()
 debugging = _Debugging()
 keras = _Keras()
 compat = _Compat()

@@ -202,3 +202,54 @@ def test_tf_letterbox_boxes_match_oracle_and_feed_the_encoder():
     y_ref = O.encode_targets(O.tf_letterbox_boxes(boxes, counts, src, (608, 608), 40, 4), (608, 608), anchors, 80)
     for a, r in zip(y_dev, y_ref):
         assert np.array_equal(a.cpu().numpy()[..., 4:], r[..., 4:])
+
+
+def _tfboxes_golden():
+    import golden_util as G
+    z = np.load(G.GOLDEN + "/tfboxes_cases.npz")
+    cap = int(z["cap"])
+    for i in range(int(z["n_cases"])):
+        n, sh, sw, S, m0, m1, flip, exp = (int(v) for v in z[f"c{i}_meta"])
+        yield z[f"c{i}_boxes"], n, (sh, sw), S, ((m0, m1) if m0 else None), bool(flip), exp, cap, z[f"c{i}_out"]
+
+
+def test_tf_letterbox_oracle_matches_reference_code_golden():
+    """tests/golden/tfboxes_cases.npz: outputs of the reference's own tf.data box functions
+    (tf_letterbox_resize, _preprocess_image_and_boxes, tf_random_horizontal_flip,
+    _expand_box_capacity; generators.py:167-256, 1859-2034) executed over oracle/tf_shim.py."""
+    k = 0
+    for boxes, n, src, S, ms, flip, exp, cap, ref in _tfboxes_golden():
+        got = O.tf_letterbox_boxes(boxes[None], np.array([n]), [src], (S, S), cap, exp,
+                                   multiscale_shapes=None if ms is None else [ms], hflip=[flip])[0]
+        assert got.shape == ref.shape and np.array_equal(got, ref)
+        k += 1
+    assert k >= 40
+
+
+def test_tf_letterbox_oracle_matches_live_reference_code_over_tf_shim():
+    """Fresh seeds, where the reference tree exists."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle.gen_golden import tfboxes_inputs
+    f = ref_loader.load_tf_box_prestep()
+    for boxes, n, src, S, ms, flip, exp in tfboxes_inputs(701, 40):
+        ref = f(boxes[:n], src, (S, S), 12, exp, ms if ms[0] else None, flip)
+        got = O.tf_letterbox_boxes(boxes[None], np.array([n]), [src], (S, S), 12, exp,
+                                   multiscale_shapes=[ms] if ms[0] else None, hflip=[flip])[0]
+        assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+def test_gpu_letterbox_boxes_match_reference_code_golden():
+    """mgd_letterbox_boxes (host arrays and device tensors) against the fixtures made from the
+    reference's own code: bit for bit (IEEE float32 multiplies / adds and int truncations)."""
+    import torch
+    from multigriddet_b200 import engine
+    for boxes, n, src, S, ms, flip, exp, cap, ref in _tfboxes_golden():
+        kw = dict(counts=np.array([n], np.int32), expansion=exp,
+                  multiscale_shapes=None if ms is None else [ms], hflip=[flip])
+        got = engine.letterbox_boxes_batch(boxes[None], [src], (S, S), cap, **kw)[0]
+        assert np.array_equal(got, ref)
+        dev = engine.letterbox_boxes_batch(torch.from_numpy(boxes[None]).cuda(), [src], (S, S), cap, **kw)[0]
+        assert np.array_equal(dev.cpu().numpy(), ref)

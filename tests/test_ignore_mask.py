@@ -1,12 +1,15 @@
 """Loss-side ignore mask: reference
-multigriddet/losses/multigrid_loss.py:494-703.
+multigriddet/losses/multigrid_loss.py:445-703.
 
-PARITY UNPINNED against the reference: it is TensorFlow graph code, TensorFlow is not
-installed here and no reference test pins its outputs.  The CPU tests check the oracle
-restatement (oracle/loss_oracle.py) against hand-derived properties; the GPU tests check
-the CUDA path against that oracle: IoU maps to 1e-5, masks exactly except on cells whose
-best IoU lies within 1e-5 of the threshold (TF's float32 tanh / sigmoid / exp are not
-promised to match libm bit for bit, so neither side may claim those).
+TensorFlow is not installed here, so the reference's graph code cannot run as it is.  The pin
+is its own source -- ``MultiGridLoss._compute_ignore_mask`` / ``_compute_iou_batch`` --
+executed statement by statement with ``oracle/tf_shim.py`` answering the tf.* / K.* calls in
+NumPy: live against the oracle restatement (oracle/loss_oracle.py) where the reference tree
+exists, and as ``tests/golden/ignoremask_cases.npz`` everywhere else.  The CPU tests also check
+hand-derived properties of the oracle; the GPU tests check the CUDA path against the oracle and
+against the fixtures: IoU maps to 1e-5, masks exactly except on cells whose best IoU lies
+within 1e-5 of the threshold (TF's float32 tanh / sigmoid / exp are Eigen's, the fixtures' are
+libm's: neither side may claim more).
 """
 import numpy as np
 import pytest
@@ -118,3 +121,81 @@ def test_ignore_mask_fed_by_the_encoder_table_equals_the_dense_path():
             clear = (rm - 0.5).abs() > 1e-5
             assert torch.equal(gi[clear], ri[clear])
     assert sum(float(m[0].sum()) for m in m_ref) > 0       # the mask is not trivially empty
+
+
+def _golden_cases():
+    import golden_util as G
+    z = np.load(G.GOLDEN + "/ignoremask_cases.npz")
+    for i in range(int(z["n_cases"])):
+        seed, B, N, S, C = (int(v) for v in z[f"c{i}_meta"])
+        anchors = [np.array(a, dtype=np.float32) for a in z[f"c{i}_anchors"]]
+        y = G.dense_y_true(z, prefix=f"c{i}_y_")
+        preds = [z[f"c{i}_pred{l}"].astype(np.float32) for l in range(3)]
+        ref = []
+        for l in range(3):
+            shape = y[l].shape[:3] + (1,)
+            ig = np.unpackbits(z[f"c{i}_ignore{l}"])[:int(np.prod(shape))].reshape(shape).astype(np.float32)
+            ref.append((ig, z[f"c{i}_assigned{l}"], z[f"c{i}_maxiou{l}"]))
+        yield S, C, anchors, y, preds, ref
+
+
+def test_oracle_matches_reference_code_golden():
+    """oracle/loss_oracle.py against the outputs of the reference's own _compute_ignore_mask
+    (run over oracle/tf_shim.py when the fixture was made)."""
+    import golden_util as G
+    n = 0
+    for S, C, anchors, y, preds, ref in _golden_cases():
+        got = LO.ignore_masks(preds, y, anchors, (S, S), ignore_thresh=0.5)
+        for (ig, asg, mx), (rig, rasg, rmx) in zip(got, ref):
+            if G.numpy_pinned():
+                assert np.array_equal(mx, rmx) and np.array_equal(asg, rasg) and np.array_equal(ig, rig)
+            else:
+                np.testing.assert_allclose(mx, rmx, rtol=1e-5, atol=1e-6)
+                np.testing.assert_allclose(asg, rasg, rtol=1e-5, atol=1e-6)
+                sure = np.abs(rmx - 0.5) > 1e-5
+                assert np.array_equal(ig[sure], rig[sure])
+            n += int(rig.sum())
+    assert n > 1000
+
+
+def test_oracle_matches_live_reference_code_over_tf_shim():
+    """Fresh seeds, where the reference tree exists: the two reference methods' own source
+    executed over the TF-op stand-in against the restatement, bit for bit (both sides use the
+    same float32 exp / tanh here)."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference tree not present (GPU box)")
+    f = ref_loader.load_tf_ignore_mask()
+    for seed, B, N, S, C, thr in ((11, 3, 12, 160, 20, 0.5), (12, 2, 60, 416, 20, 0.7), (13, 1, 100, 608, 80, 0.3)):
+        anchors, y, preds = _inputs(seed, B, N, S, C)
+        for l in range(3):
+            ref = f(preds[l], y[l], anchors[l], (S, S), thr)
+            got = LO.ignore_mask_layer(preds[l], y[l], anchors[l], (S, S), ignore_thresh=thr)
+            for g, r in zip(got, ref):
+                assert g.shape == r.shape and np.array_equal(g, r)
+    # an image without objects takes the reference's tf.cond zero branch (:634-642)
+    anchors, y, preds = _inputs(14, 2, 5, 160, 20)
+    y0 = [np.zeros_like(t) for t in y]
+    for l in range(3):
+        for g, r in zip(LO.ignore_mask_layer(preds[l], y0[l], anchors[l], (160, 160)),
+                        f(preds[l], y0[l], anchors[l], (160, 160), 0.5)):
+            assert np.array_equal(g, r) and not r.any()
+
+
+@pytest.mark.gpu
+def test_gpu_ignore_mask_matches_reference_code_golden():
+    """The CUDA path against the fixtures made from the reference's own code."""
+    import torch
+    from multigriddet_b200 import engine
+    for S, C, anchors, y, preds, ref in _golden_cases():
+        for dev in (False, True):
+            yp = [torch.from_numpy(p).cuda() for p in preds] if dev else preds
+            yt = [torch.from_numpy(t).cuda() for t in y] if dev else y
+            got = engine.ignore_masks(yp, yt, anchors, (S, S), C, ignore_thresh=0.5)
+            for (ig, asg, mx), (rig, rasg, rmx) in zip(got, ref):
+                if dev:
+                    ig, asg, mx = ig.cpu().numpy(), asg.cpu().numpy(), mx.cpu().numpy()
+                np.testing.assert_allclose(mx, rmx, rtol=1e-5, atol=1e-6)
+                np.testing.assert_allclose(asg, rasg, rtol=1e-5, atol=1e-6)
+                sure = np.abs(rmx - 0.5) > 1e-5
+                assert np.array_equal(ig[sure], rig[sure])
