@@ -289,8 +289,10 @@ MGD_API int mgd_match_detections(const double *det_boxes, const double *det_scor
  * Loss-side ignore mask.  Replaces MultiGridLoss._compute_ignore_mask and
  * _compute_iou_batch (multigriddet/losses/multigrid_loss.py:494-703, 445-492), called once
  * per layer from the loss (:316).  Forward only: the reference casts the mask from a
- * boolean and wraps the two IoU maps in stop_gradient.  PARITY UNPINNED (TensorFlow graph
- * code; restated op by op in float32, reference quirks included -- see csrc/loss.cu).
+ * boolean and wraps the two IoU maps in stop_gradient.  TensorFlow graph code: parity is
+ * pinned against the two methods' own source executed over a NumPy stand-in for the tf.* /
+ * K.* ops (the test suite's oracle/tf_shim.py; fixtures tests/golden/ignoremask_cases.npz),
+ * reference quirks included -- see csrc/loss.cu; IoU values to 1e-5 (float32 exp / tanh).
  *
  *   y_pred, y_true  num_layers pointers, each (batch, grid_h, grid_w, 5+A_l+C) float32
  *   ignore_mask          (batch, grid_h, grid_w, 1) float32 per layer: 1 where the best IoU of

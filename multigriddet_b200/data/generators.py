@@ -110,8 +110,9 @@ def letterbox_boxes(boxes, src_shapes, input_shape, max_boxes_per_image, counts=
     multi-scale transform of ``_preprocess_image_and_boxes`` (generators.py:1859-1916), the
     flip of ``tf_random_horizontal_flip`` (:227-256, coin supplied by the caller), ``padded_batch``
     to ``max_boxes_per_image`` (:1963-1976) and ``_expand_box_capacity`` (:1983-2034), in one
-    kernel (``mgd_letterbox_boxes``).  Parity against TensorFlow itself is UNPINNED (TF is not
-    installed here); the oracle restates the float32 ops in their graph order."""
+    kernel (``mgd_letterbox_boxes``).  TensorFlow is not installed here; parity is pinned, bit
+    for bit, against those reference functions' own source executed over a NumPy stand-in for
+    their ``tf.*`` ops (``tests/test_box_transforms.py``, ``tests/golden/tfboxes_cases.npz``)."""
     factor = 8 if (mosaic_enabled and mixup_enabled) else 4 if mosaic_enabled else 2 if mixup_enabled else 1
     return engine.letterbox_boxes_batch(boxes, src_shapes, input_shape, max_boxes_per_image, counts,
                                         factor, multiscale_shapes, hflip)

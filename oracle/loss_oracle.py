@@ -3,12 +3,14 @@
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
 
-PARITY UNPINNED: the reference function is TensorFlow graph code, TensorFlow is not
-installed in this image, and no reference test pins its outputs.  This file restates the TF
-ops one by one in float32 NumPy (same operation order, same broadcasting); the
-transcendentals (``tanh``, ``sigmoid``, ``exp``) are NumPy's / libm's, which TF does not
-promise to match bit for bit, so comparisons against it use a 1e-5 tolerance and skip cells
-whose maximum IoU lies within 1e-5 of the ignore threshold.
+PINNED AGAINST THE REFERENCE'S OWN CODE OVER A TF-OP STAND-IN: TensorFlow is not installed in
+this image, so the two reference methods are executed from their own source with
+``oracle/tf_shim.py`` answering the ``tf.*`` / ``K.*`` calls in NumPy
+(``ref_loader.load_tf_ignore_mask``); this restatement equals them bit for bit
+(tests/test_ignore_mask.py; fixtures tests/golden/ignoremask_cases.npz).  The
+transcendentals (``tanh``, ``sigmoid``, ``exp``) are NumPy's / libm's on both sides, which
+TensorFlow does not promise to match bit for bit, so comparisons of the CUDA path use a 1e-5
+tolerance and skip cells whose maximum IoU lies within 1e-5 of the ignore threshold.
 
 Quirks of the reference that are restated as they are:
 * ``tf.meshgrid(grid_x, grid_y, indexing='ij')`` (:547) makes the grid offset of tensor

@@ -709,9 +709,11 @@ def merge_mosaic_bboxes(bboxes, crop_x, crop_y, image_size):
 
 
 # --------------------------------------------------------------------------
-# tf.data box pre-step (generators.py:1859-1916, 227-256, 1963-2034) -- PARITY UNPINNED:
-# TensorFlow is not installed; every op restated here is an IEEE float32 multiply / divide /
-# add or an int truncation, in the order the TF graph applies them.
+# tf.data box pre-step (generators.py:1859-1916, 227-256, 1963-2034).  TensorFlow is not
+# installed; every op restated here is an IEEE float32 multiply / divide / add or an int
+# truncation, in the order the TF graph applies them, and the restatement equals the reference
+# functions' own source executed over oracle/tf_shim.py bit for bit
+# (ref_loader.load_tf_box_prestep, tests/test_box_transforms.py, tests/golden/tfboxes_cases.npz).
 # --------------------------------------------------------------------------
 
 def tf_letterbox_params(src_h, src_w, input_shape, multiscale_shape=None):

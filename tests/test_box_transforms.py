@@ -141,7 +141,8 @@ def test_device_pipeline_reshape_then_encode():
 
 
 # ------------------------------------------------------------------------------
-# tf.data box pre-step (generators.py:1859-1916, 1963-2034): oracle unpinned (no TensorFlow)
+# tf.data box pre-step (generators.py:1859-1916, 1963-2034): the oracle is pinned against the
+# reference's own TF source run over oracle/tf_shim.py (tests at the end of this file)
 # ------------------------------------------------------------------------------
 
 def _tfdata_case(seed, B=12, N=40):
