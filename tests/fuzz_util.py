@@ -46,3 +46,23 @@ def tie_free(boxes, anchors):
         tie = np.abs(top2[..., 1] - top2[..., 0]) < 2e-3
         boxes[tie] = 0
     return boxes
+
+
+def tf_encoder_odd_case(rng):
+    """A random head geometry and box set for the TF encoder's semantics: 1-4 layers, 1-4 anchors
+    per layer, boxes that stick out of the image, negative sizes, class ids outside [0, C)."""
+    L = int(rng.integers(1, 5))
+    A = [int(rng.integers(1, 5)) for _ in range(L)]
+    S = int(rng.choice([64, 96, 160, 224, 320, 416]))
+    C = int(rng.choice([1, 3, 20, 80]))
+    grids = [(max(1, S // max(32 >> l, 4)),) * 2 for l in range(L)]
+    anchors = [np.abs(rng.normal(40 * (L - l), 20, (A[l], 2))).astype(np.float32) + 2 for l in range(L)]
+    B, N = int(rng.integers(1, 4)), int(rng.integers(1, 30))
+    x1 = rng.uniform(-10, S, (B, N))
+    y1 = rng.uniform(-10, S, (B, N))
+    w = rng.uniform(-5, S / 2, (B, N))
+    h = rng.uniform(-5, S / 2, (B, N))
+    boxes = np.stack([x1, y1, x1 + w, y1 + h, rng.integers(-1, C + 1, (B, N))], -1).astype(np.float32)
+    if rng.integers(0, 3) == 0:
+        boxes[..., :4] = np.round(boxes[..., :4])
+    return S, C, anchors, grids, boxes

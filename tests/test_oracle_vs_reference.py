@@ -153,3 +153,17 @@ def test_tf_encoder_restatement_on_the_adversarial_inputs():
     assert all(r[0][..., 5 + 3 + 3].sum() == 0 and r[0][..., 5 + 3 + 7].sum() == 0 for r in ref)
     assert sum(float(r[0][..., 5 + 3 + 1].sum()) for r in ref) >= 9
     assert any(np.any((r[0][..., 4] > 0) & (r[0][..., 8:].sum(-1) == 0)) for r in ref)
+
+
+def test_tf_encoder_restatement_on_odd_geometries():
+    """60 random heads (1-4 layers, 1-4 anchors per layer, grids down to 2 x 2) with boxes leaving
+    the image, negative sizes and class ids outside [0, C): the reference's TF encoder over the
+    TF-op stand-in against the restatement, bit for bit."""
+    from fuzz_util import tf_encoder_odd_case
+    enc = ref_loader.load_tf_encoder()
+    rng = np.random.default_rng(77)
+    for _ in range(60):
+        S, C, anchors, grids, boxes = tf_encoder_odd_case(rng)
+        ref = enc(boxes.copy(), (S, S), anchors, C, grids)
+        got = O.encode_targets_tf_compat(boxes, (S, S), anchors, C, grids)
+        assert all(np.array_equal(g, r) for g, r in zip(got, ref)), (S, C, [a.shape for a in anchors])

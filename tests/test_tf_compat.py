@@ -135,3 +135,22 @@ def test_gpu_tf_dropin_entry_point():
     same = tf_preprocess_true_boxes(boxes, (S, S), anchors, C, False, grids, semantics="numpy")
     base = preprocess_true_boxes(boxes, (S, S), anchors, C, False, grids)
     assert all(np.array_equal(a, b) for a, b in zip(same, base))
+
+
+@pytest.mark.gpu
+def test_gpu_tf_compat_on_odd_geometries():
+    """The same generator as tests/test_oracle_vs_reference.py::
+    test_tf_encoder_restatement_on_odd_geometries, CUDA against the oracle."""
+    import torch
+    from fuzz_util import tf_encoder_odd_case
+    from multigriddet_b200 import engine
+    rng = np.random.default_rng(78)
+    for _ in range(40):
+        S_, C_, anchors, grids, boxes = tf_encoder_odd_case(rng)
+        ref = O.encode_targets_tf_compat(boxes, (S_, S_), anchors, C_, grids)
+        got = engine.encode_targets(torch.from_numpy(boxes).cuda(), (S_, S_), anchors, C_, grids,
+                                    semantics="tf_compat")
+        for g, r in zip(got, ref):
+            g = g.cpu().numpy()
+            assert np.array_equal(g[..., 4:], r[..., 4:]) and np.array_equal(g[..., :2], r[..., :2])
+            np.testing.assert_allclose(g[..., 2:4], r[..., 2:4], rtol=1e-5, atol=1e-6)
