@@ -726,10 +726,16 @@ def run_b200(args):
                 t0 = time.perf_counter()
                 list(ex.map(one, range(n)))
                 t_thr = (time.perf_counter() - t0) / n
+            batch_in = [np.concatenate([im[l] for im in imgs]) for l in range(3)]     # pageable, like the rest
+
+            def batched():
+                return dec.postprocess_batch(batch_in, shp, (S, S), 100, POST["confidence"],
+                                             POST["nms_threshold"], "diou")
+            batched()                                      # warm-up (staging buffers), like `one(0)` above
             t0 = time.perf_counter()
-            dec.postprocess_batch([np.concatenate([im[l] for im in imgs]) for l in range(3)], shp, (S, S),
-                                  100, POST["confidence"], POST["nms_threshold"], "diou")
-            t_batch = (time.perf_counter() - t0) / n
+            for _ in range(3):
+                batched()
+            t_batch = (time.perf_counter() - t0) / 3 / n
             return {"images": n, "ms_per_image_serial": t_serial * 1e3, "images_per_s_serial": 1 / t_serial,
                     "ms_per_image_8_threads": t_thr * 1e3, "images_per_s_8_threads": 1 / t_thr,
                     "ms_per_image_one_batched_call": t_batch * 1e3,
