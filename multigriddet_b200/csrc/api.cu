@@ -374,6 +374,15 @@ struct EncodeScratch { int* table; BoxRec* recs; };
 // than one after the other: 4.6 ms against 3.6 ms per 4 096 images); the NMS that follows the
 // decoder is latency-bound and leaves the memory system idle.  So: every chunk's assign kernel
 // first, then the decoder, then the writer on a second stream underneath the NMS.
+// MGD_STEP_PDL=0: plain launches instead of programmatic dependent launches between the
+// independent per-chunk kernels of mgd_encode_decode_nms (measurements)
+bool step_pdl()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MGD_STEP_PDL"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 int encode_assign_all(const HeadGeom& g, const float* boxes, int batch, int N, float* const* y,
                       cudaStream_t stream, int* d_status, int tf_compat, std::vector<EncodeArgs>* chunks)
 {
@@ -401,7 +410,9 @@ int encode_assign_all(const HeadGeom& g, const float* boxes, int batch, int N, f
             CUDA_TRY(al.get(&c.big_tables, (size_t)nb * 2 * g.cells * sizeof(int)));
         CUDA_TRY(al.get(&c.table, (size_t)nb * g.cells * sizeof(int)));
         CUDA_TRY(al.get(&c.recs, (size_t)nb * (N > 0 ? N : 1) * sizeof(BoxRec)));
-        CUDA_TRY(launch_encode_assign(c, stream));
+        // (each chunk has its own tables here, alive until encode_free_all: the assign kernels of
+        //  consecutive chunks are independent and may overlap head to tail)
+        CUDA_TRY(launch_encode_assign(c, stream, b0 > 0 && step_pdl()));
     }
     return MGD_OK;
 }
@@ -410,9 +421,14 @@ int encode_assign_all(const HeadGeom& g, const float* boxes, int batch, int N, f
 int encode_fill_all(std::vector<EncodeArgs>& chunks, int num_sms, cudaStream_t stream)
 {
     nvtx_range nv("mgd:encode fill (preprocess_true_boxes)");
+    const bool env_pdl = step_pdl();
+    bool first = true;
     for (EncodeArgs& a : chunks) {
-        const cudaError_t e = launch_encode_fill(a, num_sms, stream);
+        // every chunk's tables are alive until the caller frees them: consecutive writers are
+        // independent and may overlap head to tail
+        const cudaError_t e = launch_encode_fill(a, num_sms, stream, env_pdl && !first);
         if (e != cudaSuccess) return fail(MGD_ERR_CUDA, "y_true writer launch failed: %s", cudaGetErrorString(e));
+        first = false;
     }
     return MGD_OK;
 }

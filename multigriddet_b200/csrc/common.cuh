@@ -197,8 +197,10 @@ void prof_mark_end(int kind, cudaStream_t stream);
 
 // launchers (each enqueues on `stream` and returns the launch error, if any)
 cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream);
-cudaError_t launch_encode_assign(const EncodeArgs& a, cudaStream_t stream);      // owner tables + box records
-cudaError_t launch_encode_fill(const EncodeArgs& a, int num_sms, cudaStream_t stream);   // the y_true writer
+cudaError_t launch_encode_assign(const EncodeArgs& a, cudaStream_t stream,
+                                 bool overlap_previous = false);                 // owner tables + box records
+cudaError_t launch_encode_fill(const EncodeArgs& a, int num_sms, cudaStream_t stream,
+                               bool overlap_previous = false);                   // the y_true writer
 cudaError_t launch_decode(const DecodeArgs& a, int num_sms, cudaStream_t stream);
 cudaError_t launch_nms(const NmsArgs& a, int num_sms, cudaStream_t stream);
 size_t encode_assign_smem_bytes(const HeadGeom& g, int N);

@@ -29,6 +29,7 @@
 // -fmad=false so nothing is contracted.
 #include <limits.h>
 #include <math.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace {
@@ -108,6 +109,9 @@ __global__ void __launch_bounds__(kAssignThreads)
 encode_assign_kernel(const __grid_constant__ EncodeArgs a)
 {
     extern __shared__ int sm[];
+    // (programmatic dependent launch, see encode_fill_kernel: the assign kernels of the chunks of
+    //  one mgd_encode_decode_nms call are independent of each other)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const HeadGeom& g = a.g;
     // the two per-cell tables live in shared memory; heads too large for that (e.g. a
     // stride-2 layer) fall back to a per-image slice of global scratch (L2-resident)
@@ -311,6 +315,11 @@ __global__ void __launch_bounds__(kFillThreads)
 encode_fill_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ FillPlan p)
 {
     using V = typename VecT<VEC>::type;
+    // Programmatic dependent launch: the writer of the NEXT chunk does not depend on this one, so
+    // when it was launched with the programmatic-serialization attribute (encode_fill_all) its
+    // CTAs may start filling the SMs while this grid drains its last wave.  (No effect on
+    // launches without the attribute.)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const HeadGeom& g = a.g;
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * kFillThreads + threadIdx.x) >> 5;
@@ -399,7 +408,7 @@ cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream)
     return launch_encode_fill(a, num_sms, stream);
 }
 
-cudaError_t launch_encode_assign(const EncodeArgs& a, cudaStream_t stream)
+cudaError_t launch_encode_assign(const EncodeArgs& a, cudaStream_t stream, bool overlap_previous)
 {
     const HeadGeom& g = a.g;
     const size_t smem = a.big_tables ? (size_t)a.N * sizeof(int) + 16 : encode_assign_smem_bytes(g, a.N);
@@ -407,12 +416,28 @@ cudaError_t launch_encode_assign(const EncodeArgs& a, cudaStream_t stream)
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     prof_mark_begin(PROF_ENCODE_ASSIGN, stream);
+    if (overlap_previous) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)a.B);
+        cfg.blockDim = dim3(kAssignThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, encode_assign_kernel, a);
+        prof_mark_end(PROF_ENCODE_ASSIGN, stream);
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     encode_assign_kernel<<<a.B, kAssignThreads, smem, stream>>>(a);
     prof_mark_end(PROF_ENCODE_ASSIGN, stream);
     return cudaGetLastError();
 }
 
-cudaError_t launch_encode_fill(const EncodeArgs& a, int num_sms, cudaStream_t stream)
+cudaError_t launch_encode_fill(const EncodeArgs& a, int num_sms, cudaStream_t stream, bool overlap_previous)
 {
     const HeadGeom& g = a.g;
     bool vec4 = true;
@@ -447,6 +472,24 @@ cudaError_t launch_encode_fill(const EncodeArgs& a, int num_sms, cudaStream_t st
     if (blocks > 0x7fffffffll) blocks = 0x7fffffffll;
     if (blocks < 1) blocks = 1;
     prof_mark_begin(PROF_ENCODE_FILL, stream);
+    if (overlap_previous) {
+        // (only where the previous kernel on `stream` is the writer of another chunk whose
+        //  tables are still alive: mgd_encode_decode_nms)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)blocks);
+        cfg.blockDim = dim3(kFillThreads);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = vec4 ? cudaLaunchKernelEx(&cfg, encode_fill_kernel<4>, a, p)
+                                   : cudaLaunchKernelEx(&cfg, encode_fill_kernel<1>, a, p);
+        prof_mark_end(PROF_ENCODE_FILL, stream);
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     if (vec4) encode_fill_kernel<4><<<(unsigned)blocks, kFillThreads, 0, stream>>>(a, p);
     else      encode_fill_kernel<1><<<(unsigned)blocks, kFillThreads, 0, stream>>>(a, p);
     prof_mark_end(PROF_ENCODE_FILL, stream);
