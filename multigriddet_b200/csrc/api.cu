@@ -60,30 +60,68 @@ struct Tracer {
     } while (0)
 
 // ---- per-kernel event timing (observability; off unless mgd_profile_begin) -------
-struct ProfSpan { int kind; cudaEvent_t t0, t1; };
+struct ProfSpan { int kind; int launches; cudaEvent_t t0, t1; };
 thread_local bool t_prof_on = false;
 thread_local std::vector<ProfSpan> t_prof_spans;
 thread_local cudaEvent_t t_prof_open = nullptr;
+// A group: ONE pair of events around several back-to-back launches of one kind (the per-chunk
+// kernels of mgd_encode_decode_nms, which overlap head to tail through programmatic dependent
+// launch -- an event record between two of them would serialise them again).  Inside a group
+// the per-launch marks of that kind only count.
+thread_local int t_prof_group_kind = -1;
+thread_local int t_prof_group_launches = 0;
+thread_local cudaEvent_t t_prof_group_open = nullptr;
 
 }  // namespace
 
-void prof_mark_begin(int, cudaStream_t stream)
+void prof_mark_begin(int kind, cudaStream_t stream)
 {
     if (!t_prof_on) return;
+    if (kind == t_prof_group_kind) return;
     cudaEventCreate(&t_prof_open);
     cudaEventRecord(t_prof_open, stream);
 }
 
 void prof_mark_end(int kind, cudaStream_t stream)
 {
-    if (!t_prof_on || !t_prof_open) return;
+    if (!t_prof_on) return;
+    if (kind == t_prof_group_kind) { ++t_prof_group_launches; return; }
+    if (!t_prof_open) return;
     ProfSpan s;
     s.kind = kind;
+    s.launches = 1;
     s.t0 = t_prof_open;
     cudaEventCreate(&s.t1);
     cudaEventRecord(s.t1, stream);
     t_prof_spans.push_back(s);
     t_prof_open = nullptr;
+}
+
+void prof_group_begin(int kind, cudaStream_t stream)
+{
+    if (!t_prof_on || t_prof_group_kind >= 0) return;
+    t_prof_group_kind = kind;
+    t_prof_group_launches = 0;
+    cudaEventCreate(&t_prof_group_open);
+    cudaEventRecord(t_prof_group_open, stream);
+}
+
+void prof_group_end(int kind, cudaStream_t stream)
+{
+    if (!t_prof_on || t_prof_group_kind != kind) return;
+    if (t_prof_group_launches > 0) {
+        ProfSpan s;
+        s.kind = kind;
+        s.launches = t_prof_group_launches;
+        s.t0 = t_prof_group_open;
+        cudaEventCreate(&s.t1);
+        cudaEventRecord(s.t1, stream);
+        t_prof_spans.push_back(s);
+    } else {
+        cudaEventDestroy(t_prof_group_open);
+    }
+    t_prof_group_open = nullptr;
+    t_prof_group_kind = -1;
 }
 
 namespace {
@@ -389,6 +427,8 @@ int encode_assign_all(const HeadGeom& g, const float* boxes, int batch, int N, f
     nvtx_range nv("mgd:encode assign (preprocess_true_boxes)");
     const Alloc al{nullptr, stream};
     const int step = chunk_images(g, batch);
+    // scratch of every chunk first, then the kernels back to back (nothing between two launches:
+    // they overlap head to tail through programmatic dependent launch)
     for (int b0 = 0; b0 < batch; b0 += step) {
         const int nb = batch - b0 < step ? batch - b0 : step;
         EncodeArgs a;
@@ -410,10 +450,16 @@ int encode_assign_all(const HeadGeom& g, const float* boxes, int batch, int N, f
             CUDA_TRY(al.get(&c.big_tables, (size_t)nb * 2 * g.cells * sizeof(int)));
         CUDA_TRY(al.get(&c.table, (size_t)nb * g.cells * sizeof(int)));
         CUDA_TRY(al.get(&c.recs, (size_t)nb * (N > 0 ? N : 1) * sizeof(BoxRec)));
-        // (each chunk has its own tables here, alive until encode_free_all: the assign kernels of
-        //  consecutive chunks are independent and may overlap head to tail)
-        CUDA_TRY(launch_encode_assign(c, stream, b0 > 0 && step_pdl()));
     }
+    struct Group {                                   // one event pair around the chunk launches
+        cudaStream_t st;
+        explicit Group(cudaStream_t s) : st(s) { prof_group_begin(PROF_ENCODE_ASSIGN, st); }
+        ~Group() { prof_group_end(PROF_ENCODE_ASSIGN, st); }
+    } group(stream);
+    // (each chunk has its own tables here, alive until encode_free_all: the assign kernels of
+    //  consecutive chunks are independent)
+    for (size_t k = 0; k < chunks->size(); ++k)
+        CUDA_TRY(launch_encode_assign((*chunks)[k], stream, k > 0 && step_pdl()));
     return MGD_OK;
 }
 
@@ -423,6 +469,8 @@ int encode_fill_all(std::vector<EncodeArgs>& chunks, int num_sms, cudaStream_t s
     nvtx_range nv("mgd:encode fill (preprocess_true_boxes)");
     const bool env_pdl = step_pdl();
     bool first = true;
+    prof_group_begin(PROF_ENCODE_FILL, stream);
+    struct GroupEnd { cudaStream_t st; ~GroupEnd() { prof_group_end(PROF_ENCODE_FILL, st); } } group_end{stream};
     for (EncodeArgs& a : chunks) {
         // every chunk's tables are alive until the caller frees them: consecutive writers are
         // independent and may overlap head to tail
@@ -1023,7 +1071,7 @@ int mgd_profile_end(double* ms, long long* launches)
         cudaError_t e = cudaEventSynchronize(s.t1);
         if (e == cudaSuccess) e = cudaEventElapsedTime(&t, s.t0, s.t1);
         if (e != cudaSuccess) rc = fail(MGD_ERR_CUDA, "profile: %s", cudaGetErrorString(e));
-        else { if (ms) ms[s.kind] += t; if (launches) launches[s.kind] += 1; }
+        else { if (ms) ms[s.kind] += t; if (launches) launches[s.kind] += s.launches; }
         cudaEventDestroy(s.t0);
         cudaEventDestroy(s.t1);
     }

@@ -194,6 +194,8 @@ enum ProfKind { PROF_ENCODE_ASSIGN = 0, PROF_ENCODE_FILL = 1, PROF_DECODE_COMPAC
                 PROF_NMS = 3, PROF_OTHER = 4, PROF_KINDS = 5 };
 void prof_mark_begin(int kind, cudaStream_t stream);
 void prof_mark_end(int kind, cudaStream_t stream);
+void prof_group_begin(int kind, cudaStream_t stream);   // one event pair around several launches of `kind`
+void prof_group_end(int kind, cudaStream_t stream);
 
 // launchers (each enqueues on `stream` and returns the launch error, if any)
 cudaError_t launch_encode(const EncodeArgs& a, int num_sms, cudaStream_t stream);
